@@ -1,0 +1,135 @@
+"""ctypes binding of libfegnn.so (the C ABI declared in include/fegnn.h).
+
+The library is the product: there is no CPU path and no torch fallback.  Importing this
+module without the built shared object raises immediately; calling any entry point on a
+machine without a CUDA device fails inside the CUDA runtime and is reported as an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_C", "libfegnn.so")
+
+H = 64
+MAX_C = 16
+MAX_FE = 8
+
+F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST = 1, 2, 4, 8, 16
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int32)
+lp = C.POINTER(C.c_int64)
+
+
+class Dims(C.Structure):
+    _fields_ = [("N", C.c_int32), ("Nl", C.c_int32), ("E", C.c_int32), ("B", C.c_int32), ("C", C.c_int32),
+                ("Fe", C.c_int32), ("flags", C.c_uint32), ("gravity", C.c_float * 3), ("eps", C.c_float)]
+
+
+class Graph(C.Structure):
+    _fields_ = [("row", C.c_void_p), ("col", C.c_void_p), ("batch", C.c_void_p), ("edge_attr", C.c_void_p),
+                ("dinv", C.c_void_p), ("inv_nb", C.c_void_p)]
+
+
+# member order of fegnn_layer_params / fegnn_layer_grads -> reference state_dict suffix
+LAYER_FIELDS = [
+    ("edge_w0", "edge_mlp.0.weight"), ("edge_b0", "edge_mlp.0.bias"),
+    ("edge_w2", "edge_mlp.2.weight"), ("edge_b2", "edge_mlp.2.bias"),
+    ("edgev_w0", "edge_mlp_virtual.0.weight"), ("edgev_b0", "edge_mlp_virtual.0.bias"),
+    ("edgev_w2", "edge_mlp_virtual.2.weight"), ("edgev_b2", "edge_mlp_virtual.2.bias"),
+    ("cr_w0", "coord_mlp_r.0.weight"), ("cr_b0", "coord_mlp_r.0.bias"), ("cr_w2", "coord_mlp_r.2.weight"),
+    ("crv_w0", "coord_mlp_r_virtual.0.weight"), ("crv_b0", "coord_mlp_r_virtual.0.bias"),
+    ("crv_w2", "coord_mlp_r_virtual.2.weight"),
+    ("cvv_w0", "coord_mlp_v_virtual.0.weight"), ("cvv_b0", "coord_mlp_v_virtual.0.bias"),
+    ("cvv_w2", "coord_mlp_v_virtual.2.weight"),
+    ("vel_w0", "coord_mlp_vel.0.weight"), ("vel_b0", "coord_mlp_vel.0.bias"),
+    ("vel_w2", "coord_mlp_vel.2.weight"), ("vel_b2", "coord_mlp_vel.2.bias"),
+    ("grav_w0", "gravity_mlp.0.weight"), ("grav_b0", "gravity_mlp.0.bias"),
+    ("grav_w2", "gravity_mlp.2.weight"), ("grav_b2", "gravity_mlp.2.bias"),
+    ("node_w0", "node_mlp.0.weight"), ("node_b0", "node_mlp.0.bias"),
+    ("node_w2", "node_mlp.2.weight"), ("node_b2", "node_mlp.2.bias"),
+    ("nodev_w0", "node_mlp_virtual.0.weight"), ("nodev_b0", "node_mlp_virtual.0.bias"),
+    ("nodev_w2", "node_mlp_virtual.2.weight"), ("nodev_b2", "node_mlp_virtual.2.bias"),
+    ("att_w", "att_mlp.0.weight"), ("att_b", "att_mlp.0.bias"),
+    ("attv_w", "att_mlp_virtual.0.weight"), ("attv_b", "att_mlp_virtual.0.bias"),
+]
+assert len(LAYER_FIELDS) == 37
+
+
+class LayerPtrs(C.Structure):
+    """fegnn_layer_params and fegnn_layer_grads share this layout (const-ness aside)."""
+    _fields_ = [(n, C.c_void_p) for n, _ in LAYER_FIELDS]
+
+
+SAVED_FIELDS = ["P", "Q", "Av", "Uh", "sv", "sg", "M", "Zc", "G1", "msum", "tsum", "u", "zh1", "Dsum", "Usum"]
+
+
+class Saved(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in SAVED_FIELDS]
+
+
+class FegnnError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  fastegnn_b200 has no CPU or eager fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+vp = C.c_void_p
+i32 = C.c_int32
+_PD, _PG, _PP, _PS = C.POINTER(Dims), C.POINTER(Graph), C.POINTER(LayerPtrs), C.POINTER(Saved)
+
+SIGNATURES = {
+    "fegnn_last_error": (C.c_char_p, []),
+    "fegnn_version": (C.c_int, []),
+    "fegnn_graph_prep_workspace_bytes": (C.c_size_t, [i32, i32]),
+    "fegnn_graph_prep": (C.c_int, [i32, i32, i32, i32] + [vp] * 12 + [vp, C.c_size_t, vp]),
+    "fegnn_embed_forward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),
+    "fegnn_embed_backward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_graph_xsum": (C.c_int, [i32, i32, vp, vp, vp, vp]),
+    "fegnn_graph_pre_forward": (C.c_int, [_PD, _PG, _PP, vp, vp, vp, _PS, vp]),
+    "fegnn_node_pre_forward": (C.c_int, [_PD, _PP, vp, _PS, vp]),
+    "fegnn_edge_forward": (C.c_int, [_PD, _PG, _PP, vp, _PS, vp]),
+    "fegnn_virtual_forward": (C.c_int, [_PD, _PG, _PP, vp, vp, vp, _PS, vp, vp, vp]),
+    "fegnn_node_h_forward": (C.c_int, [_PD, _PG, _PP, vp, _PS, vp, vp]),
+    "fegnn_graph_post_forward": (C.c_int, [_PD, _PG, _PP, vp, vp, _PS, vp, vp, vp]),
+    "fegnn_graph_post_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_node_h_backward": (C.c_int, [_PD, _PG, _PP, _PP, _PS, vp, vp, vp, vp, vp]),
+    "fegnn_virtual_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, vp, vp, _PS] + [vp] * 12 + [vp]),
+    "fegnn_edge_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp, vp]),
+    "fegnn_graph_pre_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp]),
+    "fegnn_node_pre_backward": (C.c_int, [_PD, _PP, _PP, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_layer_saved_floats": (C.c_size_t, [_PD]),
+    "fegnn_layer_saved_bind": (C.c_int, [_PD, vp, _PS]),
+    "fegnn_model_workspace_floats": (C.c_size_t, [_PD, i32]),
+    "fegnn_model_backward_scratch_floats": (C.c_size_t, [_PD]),
+    "fegnn_model_forward": (C.c_int, [_PD, i32, i32, _PG, _PP] + [vp] * 9 + [vp, C.c_size_t, vp]),
+    "fegnn_model_backward": (C.c_int, [_PD, i32, i32, _PG, _PP, _PP] + [vp] * 11 + [vp, vp, C.c_size_t, vp]),
+    "fegnn_mmd_forward": (C.c_int, [i32, i32, i32, C.c_float, vp, vp, vp, vp, vp]),
+    "fegnn_mmd_backward": (C.c_int, [i32, i32, i32, i32, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)      # AttributeError here == the .so does not export what fegnn.h declares
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.fegnn_last_error().decode("utf-8", "replace")
+        raise FegnnError(f"{what or 'fegnn'} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

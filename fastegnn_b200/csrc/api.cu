@@ -1,0 +1,558 @@
+// api.cu -- the C ABI of libfegnn.so (include/fegnn.h): argument checking, workspace
+// carving, phase launchers and the whole-layer / whole-stack drivers.
+// Single translation unit: the kernel files are included below.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "edge_kernels.cu"
+#include "graph_kernels.cu"
+#include "graph_prep.cu"
+#include "mmd.cu"
+#include "node_kernels.cu"
+#include "virtual_kernels.cu"
+
+using namespace fegnn;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(FEGNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__));    \
+  } while (0)
+#define RQ(cond)                                                              \
+  do {                                                                        \
+    if (!(cond)) return fail(FEGNN_EINVAL, "%s: requirement failed: %s", __func__, #cond); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int check_dims(const fegnn_dims* d) {
+  if (d == nullptr) return fail(FEGNN_EINVAL, "dims is null");
+  if (d->N < 0 || d->Nl < d->N || d->E < 0 || d->B < 0) return fail(FEGNN_EINVAL, "bad sizes N=%d Nl=%d E=%d B=%d", d->N, d->Nl, d->E, d->B);
+  if (d->C < 1 || d->C > FEGNN_MAX_C) return fail(FEGNN_EINVAL, "virtual_channels C=%d outside [1,%d]", d->C, FEGNN_MAX_C);
+  if (d->Fe < 0 || d->Fe > FEGNN_MAX_FE) return fail(FEGNN_EINVAL, "edge_attr width Fe=%d outside [0,%d]", d->Fe, FEGNN_MAX_FE);
+  return 0;
+}
+
+inline size_t al4(size_t n) { return (n + 3) & ~(size_t)3; }
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ld1(const fegnn_dims* d) { return 2 * kH + 1 + d->Fe; }
+inline int ldv(const fegnn_dims* d) { return 2 * kH + 1 + d->C; }
+inline int ldn(const fegnn_dims* d) { return 2 * kH + kH * d->C; }
+
+EdgeArgs edge_args(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                   const fegnn_layer_saved* sv) {
+  EdgeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.Nl = d->Nl; a.E = d->E; a.Fe = d->Fe; a.ld1 = ld1(d); a.flags = d->flags; a.eps = d->eps;
+  a.row = g->row; a.col = g->col; a.ea = g->edge_attr; a.x = x; a.P = sv->P; a.Q = sv->Q;
+  a.w1 = p->edge_w0; a.W2 = p->edge_w2; a.b2 = p->edge_b2; a.W3 = p->cr_w0; a.b3 = p->cr_b0; a.w4 = p->cr_w2;
+  a.wa = p->att_w; a.ba = p->att_b;
+  return a;
+}
+
+VirtArgs virt_args(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                   const float* v, const float* Z, const fegnn_layer_saved* sv) {
+  VirtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.B = d->B; a.C = d->C; a.ldv = ldv(d); a.flags = d->flags;
+  a.grav[0] = d->gravity[0]; a.grav[1] = d->gravity[1]; a.grav[2] = d->gravity[2];
+  a.batch = g->batch; a.x = x; a.v = v; a.Z = Z; a.Av = sv->Av; a.G1 = sv->G1; a.tsum = sv->tsum; a.dinv = g->dinv;
+  a.sv = sv->sv; a.sg = sv->sg;
+  a.wv1 = p->edgev_w0; a.V2 = p->edgev_w2; a.c2 = p->edgev_b2;
+  a.Wxv = p->crv_w0; a.bxv = p->crv_b0; a.wxv = p->crv_w2;
+  a.WX = p->cvv_w0; a.bX = p->cvv_b0; a.wX = p->cvv_w2;
+  a.wav = p->attv_w; a.bav = p->attv_b;
+  return a;
+}
+
+GraphArgs graph_args(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p) {
+  GraphArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = d->B; a.C = d->C; a.ldv = ldv(d); a.flags = d->flags; a.inv_nb = g->inv_nb;
+  a.wv1 = p->edgev_w0;
+  a.nodev_w0 = p->nodev_w0; a.nodev_b0 = p->nodev_b0; a.nodev_w2 = p->nodev_w2; a.nodev_b2 = p->nodev_b2;
+  return a;
+}
+
+NodePreArgs node_pre_args(const fegnn_dims* d, const fegnn_layer_params* p, const float* h) {
+  NodePreArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.ld1 = ld1(d); a.ldv = ldv(d); a.ldn = ldn(d); a.flags = d->flags; a.h = h;
+  a.edge_w0 = p->edge_w0; a.edge_b0 = p->edge_b0; a.edgev_w0 = p->edgev_w0; a.edgev_b0 = p->edgev_b0;
+  a.node_w0 = p->node_w0; a.node_b0 = p->node_b0;
+  a.vel_w0 = p->vel_w0; a.vel_b0 = p->vel_b0; a.vel_w2 = p->vel_w2; a.vel_b2 = p->vel_b2;
+  a.grav_w0 = p->grav_w0; a.grav_b0 = p->grav_b0; a.grav_w2 = p->grav_w2; a.grav_b2 = p->grav_b2;
+  return a;
+}
+
+int check_flags_params(const fegnn_dims* d, const fegnn_layer_params* p) {
+  if (p == nullptr) return fail(FEGNN_EINVAL, "layer params is null");
+  if ((d->flags & FEGNN_F_ATTENTION) && (!p->att_w || !p->att_b || !p->attv_w || !p->attv_b))
+    return fail(FEGNN_EINVAL, "attention flag set but att_mlp tensors are null");
+  if ((d->flags & FEGNN_F_GRAVITY) && (!p->grav_w0 || !p->grav_b0 || !p->grav_w2 || !p->grav_b2))
+    return fail(FEGNN_EINVAL, "gravity flag set but gravity_mlp tensors are null");
+  return 0;
+}
+
+__global__ void broadcast_vnf_kernel(int B, int C, const float* __restrict__ vnf, float* __restrict__ S) {
+  // S[b][c][k] = virtual_node_feat[0][k][c]   (models/FastEGNN.py:268 with channel-major layout)
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * C * kH) return;
+  int k = (int)(idx & 63), c = (int)((idx >> 6) % C);
+  S[idx] = vnf[k * C + c];
+}
+__global__ void reduce_gS_kernel(int B, int C, const float* __restrict__ gS, float* __restrict__ gvnf) {
+  // g_virtual_node_feat[0][k][c] += sum_b gS[b][c][k]
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * kH) return;
+  int k = idx & 63, c = idx >> 6;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += gS[((size_t)b * C + c) * kH + k];
+  atomicAdd(gvnf + k * C + c, acc);
+}
+__global__ void final_gx_kernel(int N, const float* __restrict__ gx, const float* __restrict__ gxsum,
+                                const int* __restrict__ batch, float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 3) return;
+  int i = idx / 3, k = idx - i * 3;
+  out[idx] = gx[idx] + gxsum[batch[i] * 3 + k];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fegnn_last_error(void) { return g_err; }
+int fegnn_version(void) { return 100; }
+
+// ------------------------------------------------------------------ graph prep
+size_t fegnn_graph_prep_workspace_bytes(int32_t N, int32_t E) { return graph_prep_workspace_bytes(N, E); }
+
+int fegnn_graph_prep(int32_t N, int32_t E, int32_t B, int32_t Fe, const int64_t* edge_index, const int64_t* data_batch,
+                     const float* edge_attr, int32_t* perm, int32_t* rowptr, int32_t* row, int32_t* col,
+                     int32_t* batch, int32_t* gptr, float* edge_attr_sorted, float* dinv, float* inv_nb,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  RQ(N >= 0 && E >= 0 && B >= 0 && Fe >= 0);
+  RQ(rowptr && gptr && (N == 0 || (batch && data_batch && dinv)) && (B == 0 || inv_nb));
+  RQ(E == 0 || (edge_index && perm && row && col && workspace));
+  RQ(E == 0 || Fe == 0 || (edge_attr && edge_attr_sorted));
+  if (workspace_bytes < graph_prep_workspace_bytes(N, E))
+    return fail(FEGNN_ENOMEM, "graph_prep workspace %zu < %zu bytes", workspace_bytes, graph_prep_workspace_bytes(N, E));
+  CK(graph_prep(N, E, B, Fe, edge_index, data_batch, edge_attr, perm, rowptr, row, col, batch, gptr,
+                edge_attr_sorted, dinv, inv_nb, workspace, S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ small phases
+int fegnn_embed_forward(int32_t N, int32_t Fin, const float* node_feat, const float* w, const float* b, float* h,
+                        void* stream) {
+  RQ(N >= 0 && Fin >= 1 && Fin <= 16 && (N == 0 || (node_feat && w && b && h)));
+  CK(launch_embed_fwd(N, Fin, node_feat, w, b, h, S(stream)));
+  return 0;
+}
+int fegnn_embed_backward(int32_t N, int32_t Fin, const float* node_feat, const float* w, const float* gh, float* gw,
+                         float* gb, float* gnode_feat, void* stream) {
+  RQ(N >= 0 && Fin >= 1 && Fin <= 16 && (N == 0 || (node_feat && w && gh && gw && gb)));
+  CK(launch_embed_bwd(N, Fin, node_feat, w, gh, gw, gb, gnode_feat, S(stream)));
+  return 0;
+}
+int fegnn_graph_xsum(int32_t N, int32_t B, const float* x, const int32_t* batch, float* xsum, void* stream) {
+  RQ(N >= 0 && B >= 0 && (B == 0 || xsum) && (N == 0 || (x && batch)));
+  CK(cudaMemsetAsync(xsum, 0, sizeof(float) * 3 * (size_t)B, S(stream)));
+  CK(launch_graph_xsum(N, x, batch, xsum, S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward phases
+int fegnn_graph_pre_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* Z,
+                            const float* Sf, const float* xsum, fegnn_layer_saved* sv, void* stream) {
+  TRY(check_dims(d));
+  RQ(g && p && Z && Sf && xsum && sv);
+  GraphArgs a = graph_args(d, g, p);
+  a.Z = Z; a.S = Sf; a.xsum = xsum; a.M = sv->M; a.Zc = sv->Zc; a.G1 = sv->G1;
+  CK(launch_graph_pre_fwd(a, S(stream)));
+  return 0;
+}
+
+int fegnn_node_pre_forward(const fegnn_dims* d, const fegnn_layer_params* p, const float* h, fegnn_layer_saved* sv,
+                           void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(h && sv);
+  NodePreArgs a = node_pre_args(d, p, h);
+  a.P = sv->P; a.Q = sv->Q; a.Av = sv->Av; a.Uh = sv->Uh; a.sv = sv->sv; a.sg = sv->sg;
+  CK(launch_node_pre_fwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_edge_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                       fegnn_layer_saved* sv, void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(g && x && sv);
+  EdgeArgs a = edge_args(d, g, p, x, sv);
+  a.msum = sv->msum; a.tsum = sv->tsum;
+  CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
+  CK(cudaMemsetAsync(sv->tsum, 0, sizeof(float) * 3 * (size_t)d->N, S(stream)));
+  CK(launch_edge_fwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                          const float* v, const float* Z, fegnn_layer_saved* sv, float* x_new, float* xsum_new,
+                          void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(g && x && v && Z && sv && x_new && xsum_new);
+  VirtArgs a = virt_args(d, g, p, x, v, Z, sv);
+  a.u = sv->u; a.x_new = x_new; a.Dsum = sv->Dsum; a.Usum = sv->Usum; a.xsum_new = xsum_new;
+  CK(cudaMemsetAsync(sv->Dsum, 0, sizeof(float) * 3 * d->C * (size_t)d->B, S(stream)));
+  CK(cudaMemsetAsync(sv->Usum, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
+  CK(cudaMemsetAsync(xsum_new, 0, sizeof(float) * 3 * (size_t)d->B, S(stream)));
+  CK(launch_virtual_fwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* h,
+                         fegnn_layer_saved* sv, float* h_new, void* stream) {
+  TRY(check_dims(d));
+  RQ(g && p && h && sv && h_new);
+  NodeHArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.C = d->C; a.ldn = ldn(d);
+  a.h = h; a.Uh = sv->Uh; a.msum = sv->msum; a.dinv = g->dinv; a.u = sv->u;
+  a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
+  a.zh1 = sv->zh1; a.h_new = h_new;
+  CK(launch_node_h_fwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_graph_post_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* Z,
+                             const float* Sf, const fegnn_layer_saved* sv, float* Z_new, float* S_new, void* stream) {
+  TRY(check_dims(d));
+  RQ(g && p && Z && Sf && sv && Z_new && ((d->flags & FEGNN_F_LAST) || S_new));
+  GraphArgs a = graph_args(d, g, p);
+  a.Z = Z; a.S = Sf; a.Dsum = sv->Dsum; a.Usum = sv->Usum; a.Z_new = Z_new; a.S_new = S_new;
+  CK(launch_graph_post_fwd(a, S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ backward phases
+int fegnn_graph_post_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                              fegnn_layer_grads* gr, const float* Sf, const fegnn_layer_saved* sv,
+                              const float* gZ_new, const float* gS_new, float* gZ, float* gS, float* gDsum,
+                              float* gUsum, void* stream) {
+  TRY(check_dims(d));
+  const bool last = d->flags & FEGNN_F_LAST;
+  RQ(g && p && gr && sv && gZ_new && gZ && gS && gDsum && gUsum && (last || (Sf && gS_new)));
+  GraphArgs a = graph_args(d, g, p);
+  a.S = Sf; a.Usum = sv->Usum; a.gZ_new = gZ_new; a.gS_new = gS_new;
+  a.gZ = gZ; a.gS = gS; a.gDsum = gDsum; a.gUsum = gUsum;
+  a.g_nodev_w0 = gr->nodev_w0; a.g_nodev_b0 = gr->nodev_b0; a.g_nodev_w2 = gr->nodev_w2; a.g_nodev_b2 = gr->nodev_b2;
+  CK(launch_graph_post_bwd(a, S(stream)));
+  return 0;
+}
+
+int fegnn_node_h_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                          fegnn_layer_grads* gr, const fegnn_layer_saved* sv, const float* gh_new, float* gzh1,
+                          float* gm, float* gu, void* stream) {
+  TRY(check_dims(d));
+  RQ(g && p && gr && sv && gh_new && gzh1 && gm && gu);
+  NodeHArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.C = d->C; a.ldn = ldn(d);
+  a.msum = sv->msum; a.dinv = g->dinv; a.u = sv->u; a.zh1 = sv->zh1;
+  a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
+  a.gh_new = gh_new; a.gzh1 = gzh1; a.gm = gm; a.gu = gu;
+  a.g_node_w0 = gr->node_w0; a.g_node_w2 = gr->node_w2; a.g_node_b2 = gr->node_b2;
+  CK(launch_node_h_bwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                           fegnn_layer_grads* gr, const float* x, const float* v, const float* Z,
+                           const fegnn_layer_saved* sv, const float* gx_new, const float* gxsum_next,
+                           const float* gDsum, const float* gUsum, const float* gu, float* gAv, float* gG1, float* gx,
+                           float* gZ, float* gsv, float* gsg, float* gt, void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(g && gr && x && v && Z && sv && gx_new && gDsum && gAv && gG1 && gx && gZ && gsv && gt);
+  RQ(!(d->flags & FEGNN_F_GRAVITY) || gsg);
+  VirtArgs a = virt_args(d, g, p, x, v, Z, sv);
+  a.gx_new = gx_new; a.gxsum_next = gxsum_next; a.gDsum = gDsum; a.gUsum = gUsum; a.gu = gu;
+  a.gAv = gAv; a.gG1 = gG1; a.gx = gx; a.gZ = gZ; a.gsv = gsv; a.gsg = gsg; a.gt = gt;
+  a.g_wv1 = gr->edgev_w0; a.g_V2 = gr->edgev_w2; a.g_c2 = gr->edgev_b2;
+  a.g_Wxv = gr->crv_w0; a.g_bxv = gr->crv_b0; a.g_wxv = gr->crv_w2;
+  a.g_WX = gr->cvv_w0; a.g_bX = gr->cvv_b0; a.g_wX = gr->cvv_w2;
+  a.g_wav = gr->attv_w; a.g_bav = gr->attv_b;
+  CK(cudaMemsetAsync(gG1, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
+  CK(cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)d->Nl, S(stream)));
+  CK(launch_virtual_bwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, fegnn_layer_grads* gr,
+                        const float* x, const fegnn_layer_saved* sv, const float* gm, const float* gt, float* gP,
+                        float* gQ, float* gx, void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(g && gr && x && sv && gt && gP && gQ && gx);
+  EdgeArgs a = edge_args(d, g, p, x, sv);
+  a.gm = gm; a.gt = gt; a.gP = gP; a.gQ = gQ; a.gx = gx;
+  a.g_w1 = gr->edge_w0; a.g_W2 = gr->edge_w2; a.g_b2 = gr->edge_b2;
+  a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
+  CK(cudaMemsetAsync(gP, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
+  CK(cudaMemsetAsync(gQ, 0, sizeof(float) * kH * (size_t)d->Nl, S(stream)));
+  CK(launch_edge_bwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+int fegnn_graph_pre_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                             fegnn_layer_grads* gr, const float* Sf, const fegnn_layer_saved* sv, const float* gG1,
+                             float* gS, float* gZ, float* gxsum, void* stream) {
+  TRY(check_dims(d));
+  RQ(g && p && gr && Sf && sv && gG1 && gS && gZ && gxsum);
+  GraphArgs a = graph_args(d, g, p);
+  a.S = Sf; a.M = sv->M; a.Zc = sv->Zc; a.gG1 = gG1; a.gS = gS; a.gZ = gZ; a.gxsum = gxsum;
+  a.g_wv1 = gr->edgev_w0;
+  CK(launch_graph_pre_bwd(a, S(stream)));
+  return 0;
+}
+
+int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fegnn_layer_grads* gr, const float* h,
+                            const float* gP, const float* gQ, const float* gAv, const float* gUh, const float* gsv,
+                            const float* gsg, float* gh, void* stream) {
+  TRY(check_dims(d));
+  TRY(check_flags_params(d, p));
+  RQ(gr && h && gP && gQ && gAv && gsv && gh);
+  RQ(!(d->flags & FEGNN_F_GRAVITY) || gsg);
+  NodePreArgs a = node_pre_args(d, p, h);
+  a.gP = gP; a.gQ = gQ; a.gAv = gAv; a.gUh = gUh; a.gsv = gsv; a.gsg = gsg; a.gh = gh;
+  a.g_edge_w0 = gr->edge_w0; a.g_edge_b0 = gr->edge_b0; a.g_edgev_w0 = gr->edgev_w0; a.g_edgev_b0 = gr->edgev_b0;
+  a.g_node_w0 = gr->node_w0; a.g_node_b0 = gr->node_b0;
+  a.g_vel_w0 = gr->vel_w0; a.g_vel_b0 = gr->vel_b0; a.g_vel_w2 = gr->vel_w2; a.g_vel_b2 = gr->vel_b2;
+  a.g_grav_w0 = gr->grav_w0; a.g_grav_b0 = gr->grav_b0; a.g_grav_w2 = gr->grav_w2; a.g_grav_b2 = gr->grav_b2;
+  CK(launch_node_pre_bwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ saved block / workspaces
+size_t fegnn_layer_saved_floats(const fegnn_dims* d) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  return 3 * al4(N * kH) /*P Av Uh*/ + al4(Nl * kH) /*Q*/ + 2 * al4(N) /*sv sg*/ + al4(B * C * C) + al4(B * 3 * C) +
+         al4(B * C * kH) /*M Zc G1*/ + al4(N * kH) + al4(N * 3) /*msum tsum*/ + al4(N * C * kH) /*u*/ +
+         al4(N * kH) /*zh1*/ + al4(B * 3 * C) + al4(B * C * kH) /*Dsum Usum*/;
+}
+int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out) {
+  TRY(check_dims(d));
+  RQ(block && out);
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  float* p = block;
+  auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  out->P = take(N * kH); out->Av = take(N * kH); out->Uh = take(N * kH); out->Q = take(Nl * kH);
+  out->sv = take(N); out->sg = take(N);
+  out->M = take(B * C * C); out->Zc = take(B * 3 * C); out->G1 = take(B * C * kH);
+  out->msum = take(N * kH); out->tsum = take(N * 3); out->u = take(N * C * kH); out->zh1 = take(N * kH);
+  out->Dsum = take(B * 3 * C); out->Usum = take(B * C * kH);
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct ModelWs {
+  // per layer l in [0, L]: state entering layer l (index L = outputs)
+  float *h[33], *x[33], *Z[33], *Sx[33], *xsum[33];
+  fegnn_layer_saved saved[32];
+};
+
+size_t model_ws_floats(const fegnn_dims* d, int L) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  size_t per_state = al4(N * kH) + al4(Nl * 3) + al4(B * 3 * C) + al4(B * C * kH) + al4(B * 3);
+  return (size_t)(L + 1) * per_state + (size_t)L * fegnn_layer_saved_floats(d);
+}
+void model_ws_bind(const fegnn_dims* d, int L, float* base, ModelWs* w) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  float* p = base;
+  auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  for (int l = 0; l <= L; ++l) {
+    w->h[l] = take(N * kH); w->x[l] = take(Nl * 3); w->Z[l] = take(B * 3 * C); w->Sx[l] = take(B * C * kH);
+    w->xsum[l] = take(B * 3);
+  }
+  for (int l = 0; l < L; ++l) {
+    fegnn_layer_saved_bind(d, p, &w->saved[l]);
+    p += fegnn_layer_saved_floats(d);
+  }
+}
+
+struct BwdScratch {
+  float *gh, *gx[2], *gZ[2], *gS[2], *gxsum[2], *gDsum, *gUsum, *gzh1, *gm, *gu, *gAv, *gG1, *gsv, *gsg, *gt, *gP, *gQ;
+};
+size_t bwd_scratch_floats(const fegnn_dims* d) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  return al4(N * kH) + 2 * al4(Nl * 3) + 2 * al4(B * 3 * C) + 2 * al4(B * C * kH) + 2 * al4(B * 3) + al4(B * 3 * C) +
+         al4(B * C * kH) + 2 * al4(N * kH) + al4(N * C * kH) + al4(N * kH) + al4(B * C * kH) + 2 * al4(N) +
+         al4(N * 3) + al4(N * kH) + al4(Nl * kH);
+}
+void bwd_scratch_bind(const fegnn_dims* d, float* base, BwdScratch* s) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  float* p = base;
+  auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  s->gh = take(N * kH);
+  s->gx[0] = take(Nl * 3); s->gx[1] = take(Nl * 3);
+  s->gZ[0] = take(B * 3 * C); s->gZ[1] = take(B * 3 * C);
+  s->gS[0] = take(B * C * kH); s->gS[1] = take(B * C * kH);
+  s->gxsum[0] = take(B * 3); s->gxsum[1] = take(B * 3);
+  s->gDsum = take(B * 3 * C); s->gUsum = take(B * C * kH);
+  s->gzh1 = take(N * kH); s->gm = take(N * kH); s->gu = take(N * C * kH);
+  s->gAv = take(N * kH); s->gG1 = take(B * C * kH);
+  s->gsv = take(N); s->gsg = take(N); s->gt = take(N * 3);
+  s->gP = take(N * kH); s->gQ = take(Nl * kH);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t fegnn_model_workspace_floats(const fegnn_dims* d, int32_t L) { return model_ws_floats(d, L); }
+size_t fegnn_model_backward_scratch_floats(const fegnn_dims* d) { return bwd_scratch_floats(d); }
+
+int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                        const fegnn_layer_params* layers, const float* embed_w, const float* embed_b,
+                        const float* vnf, const float* node_feat, const float* x0, const float* v,
+                        const float* loc_mean, float* x_out, float* Z_out, float* workspace, size_t workspace_floats,
+                        void* stream) {
+  TRY(check_dims(d));
+  RQ(L >= 1 && L <= 32 && g && layers && embed_w && embed_b && vnf && workspace && x_out && Z_out);
+  RQ(d->Nl == d->N);   // the partitioned path drives the phases itself (halo rows come from peers)
+  if (workspace_floats < model_ws_floats(d, L))
+    return fail(FEGNN_ENOMEM, "model workspace %zu < %zu floats", workspace_floats, model_ws_floats(d, L));
+  cudaStream_t st = S(stream);
+  ModelWs w;
+  model_ws_bind(d, L, workspace, &w);
+  const size_t N = d->N, B = d->B, C = d->C;
+  TRY(fegnn_embed_forward(d->N, Fin, node_feat, embed_w, embed_b, w.h[0], stream));
+  CK(cudaMemcpyAsync(w.x[0], x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(w.Z[0], loc_mean, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
+  if (B > 0) {
+    broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, w.Sx[0]);
+    CK(cudaGetLastError());
+  }
+  TRY(fegnn_graph_xsum(d->N, d->B, w.x[0], g->batch, w.xsum[0], stream));
+  for (int l = 0; l < L; ++l) {
+    fegnn_dims dl = *d;
+    const bool last = l == L - 1;
+    if (last) dl.flags |= FEGNN_F_LAST;
+    const fegnn_layer_params* p = &layers[l];
+    fegnn_layer_saved* sv = &w.saved[l];
+    TRY(fegnn_graph_pre_forward(&dl, g, p, w.Z[l], w.Sx[l], w.xsum[l], sv, stream));
+    TRY(fegnn_node_pre_forward(&dl, p, w.h[l], sv, stream));
+    TRY(fegnn_edge_forward(&dl, g, p, w.x[l], sv, stream));
+    TRY(fegnn_virtual_forward(&dl, g, p, w.x[l], v, w.Z[l], sv, w.x[l + 1], w.xsum[l + 1], stream));
+    if (!last) TRY(fegnn_node_h_forward(&dl, g, p, w.h[l], sv, w.h[l + 1], stream));
+    TRY(fegnn_graph_post_forward(&dl, g, p, w.Z[l], w.Sx[l], sv, w.Z[l + 1], w.Sx[l + 1], stream));
+  }
+  CK(cudaMemcpyAsync(x_out, w.x[L], sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(Z_out, w.Z[L], sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                         const fegnn_layer_params* layers, fegnn_layer_grads* grads, const float* embed_w,
+                         float* g_embed_w, float* g_embed_b, float* g_vnf, const float* node_feat, const float* v,
+                         const float* gx_out, const float* gZ_out, float* g_x0, float* g_loc_mean,
+                         float* g_node_feat, const float* workspace, float* scratch, size_t scratch_floats,
+                         void* stream) {
+  TRY(check_dims(d));
+  RQ(L >= 1 && L <= 32 && g && layers && grads && embed_w && g_embed_w && g_embed_b && g_vnf && workspace && scratch);
+  RQ(gx_out && gZ_out && g_x0 && g_loc_mean && d->Nl == d->N);
+  if (scratch_floats < bwd_scratch_floats(d))
+    return fail(FEGNN_ENOMEM, "backward scratch %zu < %zu floats", scratch_floats, bwd_scratch_floats(d));
+  cudaStream_t st = S(stream);
+  ModelWs w;
+  model_ws_bind(d, L, const_cast<float*>(workspace), &w);
+  BwdScratch s;
+  bwd_scratch_bind(d, scratch, &s);
+  const size_t N = d->N, B = d->B, C = d->C;
+  CK(cudaMemsetAsync(s.gh, 0, sizeof(float) * kH * N, st));
+  const float* gx_new = gx_out;
+  const float* gZ_new = gZ_out;
+  const float* gS_new = nullptr;
+  const float* gxsum_next = nullptr;
+  int cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    fegnn_dims dl = *d;
+    const bool last = l == L - 1;
+    if (last) dl.flags |= FEGNN_F_LAST;
+    const fegnn_layer_params* p = &layers[l];
+    fegnn_layer_grads* gr = &grads[l];
+    const fegnn_layer_saved* sv = &w.saved[l];
+    TRY(fegnn_graph_post_backward(&dl, g, p, gr, w.Sx[l], sv, gZ_new, gS_new, s.gZ[cur], s.gS[cur], s.gDsum, s.gUsum,
+                                  stream));
+    if (!last) TRY(fegnn_node_h_backward(&dl, g, p, gr, sv, s.gh, s.gzh1, s.gm, s.gu, stream));
+    TRY(fegnn_virtual_backward(&dl, g, p, gr, w.x[l], v, w.Z[l], sv, gx_new, gxsum_next, s.gDsum,
+                               last ? nullptr : s.gUsum, last ? nullptr : s.gu, s.gAv, s.gG1, s.gx[cur], s.gZ[cur],
+                               s.gsv, s.gsg, s.gt, stream));
+    TRY(fegnn_edge_backward(&dl, g, p, gr, w.x[l], sv, last ? nullptr : s.gm, s.gt, s.gP, s.gQ, s.gx[cur], stream));
+    TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[l], sv, s.gG1, s.gS[cur], s.gZ[cur], s.gxsum[cur], stream));
+    TRY(fegnn_node_pre_backward(&dl, p, gr, w.h[l], s.gP, s.gQ, s.gAv, last ? nullptr : s.gzh1, s.gsv, s.gsg, s.gh,
+                                stream));
+    gx_new = s.gx[cur]; gZ_new = s.gZ[cur]; gS_new = s.gS[cur]; gxsum_next = s.gxsum[cur];
+    cur ^= 1;
+  }
+  if (N > 0) {
+    final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, st>>>(d->N, gx_new, gxsum_next, g->batch, g_x0);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(g_loc_mean, gZ_new, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
+  TRY(fegnn_embed_backward(d->N, Fin, node_feat, embed_w, s.gh, g_embed_w, g_embed_b, g_node_feat, stream));
+  if (B > 0) {
+    reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ MMD
+int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
+                      const int32_t* sample_idx, float* loss, void* stream) {
+  RQ(B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 1 && sigma > 0.f && loss && (B == 0 || (x && Z && sample_idx)));
+  CK(launch_mmd_fwd(B, C, ns, sigma, x, Z, sample_idx, loss, S(stream)));
+  return 0;
+}
+int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
+                       const int32_t* sample_idx, const float* gloss, float* gx, float* gZ, void* stream) {
+  RQ(N >= 0 && B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 1 && sigma > 0.f && gloss && gx && gZ);
+  RQ(B == 0 || (x && Z && sample_idx));
+  CK(launch_mmd_bwd(N, B, C, ns, sigma, x, Z, sample_idx, gloss, gx, gZ, S(stream)));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// common.cuh -- device building blocks shared by every phase kernel.
+//
+// Geometry of all tile kernels: 256 threads, a tile of TM = 128 rows (edges, nodes or
+// (node,channel) pairs) x 64 columns.  Thread (ty = tid>>4, tx = tid&15) owns rows
+// ty*8 .. ty*8+7 and columns tx*4 .. tx*4+3 of every GEMM result, so epilogues that
+// follow one another (silu, its derivative, products with upstream gradients) stay in
+// the same thread and never round-trip through memory.
+//
+// Shared-memory layouts
+//   activation tile  A[128][64]   row-major, unpadded (all access patterns used here
+//                                 are conflict-free: quarter-warp-uniform float4 reads,
+//                                 contiguous float4 row writes, one-row-per-warp walks)
+//   weight tile      W[64][64]    the reference [out=n][in=k] matrix with the 16-byte
+//                                 chunk index XOR-swizzled by (n>>2)&7, so that ONE copy
+//                                 serves both  y = a W^T  (gemm_nt, forward) and
+//                                 g_in = g W  (gemm_nn, backward) without bank conflicts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fegnn.h"
+
+namespace fegnn {
+
+constexpr int kH = FEGNN_H;
+constexpr int kThreads = 256;
+constexpr int kTM = 128;        // rows per tile
+constexpr int kRT = 8;          // rows per thread
+constexpr int kTileFloats = kTM * kH;
+constexpr int kWFloats = kH * kH;
+
+__device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_f(float z) { return z * sigmoid_f(z); }
+// a = silu(z), d = silu'(z) = s (1 + z (1 - s))
+__device__ __forceinline__ void silu_grad_f(float z, float& a, float& d) {
+  float s = sigmoid_f(z);
+  a = z * s;
+  d = s + a * (1.f - s);
+}
+
+__device__ __forceinline__ int wswz(int n, int k) { return n * kH + ((((k >> 2) ^ ((n >> 2) & 7)) << 2) | (k & 3)); }
+
+// Stage a 64x64 block of a reference-layout weight into the swizzled tile.
+// element (n,k) = g[n*ld + off + k*kstride]
+__device__ __forceinline__ void stage_weight(float* __restrict__ Ws, const float* __restrict__ g, int ld, int off,
+                                             int kstride) {
+  for (int i = threadIdx.x; i < kWFloats; i += kThreads) {
+    int n = i >> 6, k = i & 63;
+    Ws[wswz(n, k)] = g[(size_t)n * ld + off + (size_t)k * kstride];
+  }
+}
+__device__ __forceinline__ void stage_vec(float* __restrict__ s, const float* __restrict__ g, int n, int stride = 1) {
+  for (int i = threadIdx.x; i < n; i += kThreads) s[i] = g[(size_t)i * stride];
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[kRT][4]) {
+#pragma unroll
+  for (int i = 0; i < kRT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// acc[i][j] += sum_k A[ty*8+i][k] * W[tx*4+j][k]          (y = a W^T)
+__device__ __forceinline__ void gemm_nt(float (&acc)[kRT][4], const float* __restrict__ A,
+                                        const float* __restrict__ W, int ty, int tx) {
+  const float* a0 = A + ty * kRT * kH;
+  const float* w0 = W + tx * 4 * kH;
+  const int sw = tx & 7;
+#pragma unroll 2
+  for (int k4 = 0; k4 < 16; ++k4) {
+    float4 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(w0 + j * kH + ((k4 ^ sw) << 2));
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      float4 a = *reinterpret_cast<const float4*>(a0 + i * kH + (k4 << 2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a.x, w[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a.y, w[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a.z, w[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a.w, w[j].w, acc[i][j]);
+      }
+    }
+  }
+}
+
+// acc[i][j] += sum_n G[ty*8+i][n] * W[n][tx*4+j]          (g_in = g W)
+__device__ __forceinline__ void gemm_nn(float (&acc)[kRT][4], const float* __restrict__ G,
+                                        const float* __restrict__ W, int ty, int tx) {
+  const float* g0 = G + ty * kRT * kH;
+#pragma unroll 2
+  for (int n4 = 0; n4 < 16; ++n4) {
+    float4 w[4];
+    const int chunk = (tx ^ (n4 & 7)) << 2;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) w[jj] = *reinterpret_cast<const float4*>(W + (n4 * 4 + jj) * kH + chunk);
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      float4 g = *reinterpret_cast<const float4*>(g0 + i * kH + (n4 << 2));
+      acc[i][0] = fmaf(g.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(g.x, w[0].y, acc[i][1]);
+      acc[i][2] = fmaf(g.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(g.x, w[0].w, acc[i][3]);
+      acc[i][0] = fmaf(g.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(g.y, w[1].y, acc[i][1]);
+      acc[i][2] = fmaf(g.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(g.y, w[1].w, acc[i][3]);
+      acc[i][0] = fmaf(g.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(g.z, w[2].y, acc[i][1]);
+      acc[i][2] = fmaf(g.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(g.z, w[2].w, acc[i][3]);
+      acc[i][0] = fmaf(g.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(g.w, w[3].y, acc[i][1]);
+      acc[i][2] = fmaf(g.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(g.w, w[3].w, acc[i][3]);
+    }
+  }
+}
+
+// Weight-gradient tile: wg[jn][jk] += sum_r G[r][tn*4+jn] * A[r][tk*4+jk]   (dW = g^T a)
+// thread (tn = tid>>4, tk = tid&15) owns the 4x4 block (n = tn*4.., k = tk*4..) of dW[n][k].
+__device__ __forceinline__ void wgrad_acc(float (&wg)[4][4], const float* __restrict__ G,
+                                          const float* __restrict__ A, int nrows) {
+  const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;
+#pragma unroll 4
+  for (int r = 0; r < nrows; ++r) {
+    float4 g = *reinterpret_cast<const float4*>(G + r * kH + tn * 4);
+    float4 a = *reinterpret_cast<const float4*>(A + r * kH + tk * 4);
+    wg[0][0] = fmaf(g.x, a.x, wg[0][0]); wg[0][1] = fmaf(g.x, a.y, wg[0][1]);
+    wg[0][2] = fmaf(g.x, a.z, wg[0][2]); wg[0][3] = fmaf(g.x, a.w, wg[0][3]);
+    wg[1][0] = fmaf(g.y, a.x, wg[1][0]); wg[1][1] = fmaf(g.y, a.y, wg[1][1]);
+    wg[1][2] = fmaf(g.y, a.z, wg[1][2]); wg[1][3] = fmaf(g.y, a.w, wg[1][3]);
+    wg[2][0] = fmaf(g.z, a.x, wg[2][0]); wg[2][1] = fmaf(g.z, a.y, wg[2][1]);
+    wg[2][2] = fmaf(g.z, a.z, wg[2][2]); wg[2][3] = fmaf(g.z, a.w, wg[2][3]);
+    wg[3][0] = fmaf(g.w, a.x, wg[3][0]); wg[3][1] = fmaf(g.w, a.y, wg[3][1]);
+    wg[3][2] = fmaf(g.w, a.z, wg[3][2]); wg[3][3] = fmaf(g.w, a.w, wg[3][3]);
+  }
+}
+__device__ __forceinline__ void zero_wg(float (&wg)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wg[i][j] = 0.f;
+}
+// Flush a per-CTA dW block into a reference-layout gradient: dst[n*ld + off + k*kstride] += wg
+__device__ __forceinline__ void wgrad_flush(const float (&wg)[4][4], float* __restrict__ dst, int ld, int off,
+                                            int kstride) {
+  if (dst == nullptr) return;
+  const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;
+#pragma unroll
+  for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk)
+      atomicAdd(dst + (size_t)(tn * 4 + jn) * ld + off + (size_t)(tk * 4 + jk) * kstride, wg[jn][jk]);
+}
+
+// Sum over the 16 threads that share a row (a half-warp: same ty, tx = 0..15).
+__device__ __forceinline__ float rowsum16(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ float warpsum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return rowsum16(v);
+}
+
+// Column sums kept per thread (its 4 columns over its 8 rows, across tiles) are
+// reduced over the 16 ty-threads with atomics at kernel end.
+__device__ __forceinline__ void colsum_flush(const float (&cs)[4], float* __restrict__ dst, int stride, int tx) {
+  if (dst == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) atomicAdd(dst + (size_t)(tx * 4 + j) * stride, cs[j]);
+}
+
+// Segmented inclusive sum inside a warp over lanes with equal, contiguous keys.
+// Returns the segment total in the LAST lane of each segment (is_tail == true there).
+__device__ __forceinline__ float warp_segsum(float v, int key, int lane, bool& is_tail) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float vu = __shfl_up_sync(0xffffffffu, v, o);
+    int ku = __shfl_up_sync(0xffffffffu, key, o);
+    if (lane >= o && ku == key) v += vu;
+  }
+  int kd = __shfl_down_sync(0xffffffffu, key, 1);
+  is_tail = (lane == 31) || (kd != key);
+  return v;
+}
+
+// Column-parallel walk over the rows of a tile with a sorted (contiguous) key per row:
+// thread (c = tid&63, grp = tid>>6) sums rows grp*32 .. grp*32+31 of column c and
+// flushes one atomicAdd per key run:  dst[key*64 + c] += run sum.  key < 0 rows are skipped.
+__device__ __forceinline__ void tile_segsum_rows(const float* __restrict__ T, const int* __restrict__ skey,
+                                                 float* __restrict__ dst) {
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  int cur = -1;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    int rr = grp * 32 + i;
+    int k = skey[rr];
+    if (k != cur) {
+      if (cur >= 0) atomicAdd(dst + (size_t)cur * kH + c, acc);
+      cur = k;
+      acc = 0.f;
+    }
+    if (k >= 0) acc += T[rr * kH + c];
+  }
+  if (cur >= 0) atomicAdd(dst + (size_t)cur * kH + c, acc);
+}
+
+// Load a [rows<=128][64] global block (row stride ld floats) into a tile; rows >= nvalid are zero.
+__device__ __forceinline__ void load_tile(float* __restrict__ T, const float* __restrict__ g, size_t ld, int nvalid,
+                                          float scale_unused = 1.f) {
+  for (int i = threadIdx.x; i < kTM * 16; i += kThreads) {
+    int r = i >> 4, c4 = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nvalid) v = *reinterpret_cast<const float4*>(g + (size_t)r * ld + c4 * 4);
+    *reinterpret_cast<float4*>(T + r * kH + c4 * 4) = v;
+  }
+}
+
+struct Launch {
+  static int sm_count();
+};
+
+}  // namespace fegnn

@@ -1,0 +1,292 @@
+// graph_prep.cu -- once-per-forward integer work: CSR-by-row of the edge list.
+//
+// The reference re-gathers with the unsorted int64 edge_index in every layer and reduces
+// with scatter_add (models/FastEGNN.py:182,210,279-294).  Here the edges are stably sorted
+// by row ONCE (bit-identical to torch.sort(row, stable=True)), indices narrowed to int32,
+// edge attributes gathered into sorted order, and the clamped counts of
+// unsorted_segment_mean (:294) / global_mean_pool turned into reciprocal vectors.
+//
+// Sort: least-significant-digit radix sort, 8-bit digits, ceil(bits(N-1)/8) passes.
+// Each pass = per-tile histogram -> exclusive scan (digit-major) -> stable scatter, where a
+// tile is 4096 consecutive elements and the in-tile stable rank comes from warp match masks.
+#include "common.cuh"
+
+namespace fegnn {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                             // rounds per warp
+constexpr int kSortTile = kSortThreads * kSortItems;       // 4096
+constexpr int kScanChunk = 4096;                           // 256 threads x 16
+
+// ---------------------------------------------------------------- exclusive scan (int32)
+__global__ void __launch_bounds__(256) scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ sums) {
+  __shared__ int red[8];
+  const int base = blockIdx.x * kScanChunk;
+  int acc = 0;
+  for (int i = threadIdx.x; i < kScanChunk; i += 256) {
+    int idx = base + i;
+    if (idx < n) acc += in[idx];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    sums[blockIdx.x] = t;
+  }
+}
+// single block: in-place exclusive scan of sums[0..nb)
+__global__ void __launch_bounds__(1024) scan_sums(int* __restrict__ sums, int nb) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < nb; base += 1024) {
+    int idx = base + threadIdx.x;
+    int v = idx < nb ? sums[idx] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int t = wsum[lane];
+      int ti = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      wsum[lane] = ti - t;   // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (idx < nb) sums[idx] = carry + wsum[w] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wsum[w] + inc;
+    __syncthreads();
+  }
+}
+// out[i] = exclusive prefix of in (may alias); if total != null and this is the last block, *total = sum
+__global__ void __launch_bounds__(256) scan_apply(const int* __restrict__ in, int n, const int* __restrict__ sums,
+                                                  int* __restrict__ out, int* __restrict__ total) {
+  __shared__ int wsum[8];
+  const int base = blockIdx.x * kScanChunk + threadIdx.x * 16;
+  int v[16];
+  int tsum = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    int idx = base + j;
+    v[j] = idx < n ? in[idx] : 0;
+    tsum += v[j];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = tsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < w; ++k) woff += wsum[k];
+  int run = sums[blockIdx.x] + woff + inc - tsum;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    int idx = base + j;
+    if (idx < n) out[idx] = run;
+    run += v[j];
+  }
+  if (total != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) *total = run;
+}
+
+static cudaError_t exclusive_scan(const int* in, int n, int* out, int* total, int* sums, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  int nb = (n + kScanChunk - 1) / kScanChunk;
+  scan_block_sums<<<nb, 256, 0, st>>>(in, n, sums);
+  scan_sums<<<1, 1024, 0, st>>>(sums, nb);
+  scan_apply<<<nb, 256, 0, st>>>(in, n, sums, out, total);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- counting
+__global__ void count_rows_kernel(int E, const int64_t* __restrict__ row64, int* __restrict__ deg) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(deg + (int)row64[e], 1);
+}
+__global__ void batch_kernel(int N, const int64_t* __restrict__ b64, int* __restrict__ batch, int* __restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    int b = (int)b64[i];
+    batch[i] = b;
+    atomicAdd(cnt + b, 1);
+  }
+}
+__global__ void recip_kernel(int n, const int* __restrict__ ptr, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int c = ptr[i + 1] - ptr[i];
+    out[i] = 1.f / (float)(c < 1 ? 1 : c);
+  }
+}
+
+// ---------------------------------------------------------------- radix passes
+// keys come from the int64 row vector in the first pass (vals implicit = index)
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(int E, int shift, const int64_t* __restrict__ row64,
+                                                                  const int* __restrict__ keys, int G,
+                                                                  int* __restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+  for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {
+    int idx = base + i;
+    if (idx < E) {
+      int k = FIRST ? (int)row64[idx] : keys[idx];
+      atomicAdd(&h[(k >> shift) & 255], 1);
+    }
+  }
+  __syncthreads();
+  hist[threadIdx.x * G + blockIdx.x] = h[threadIdx.x];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(int E, int shift,
+                                                                     const int64_t* __restrict__ row64,
+                                                                     const int* __restrict__ keys,
+                                                                     const int* __restrict__ vals, int G,
+                                                                     const int* __restrict__ hist_scan,
+                                                                     int* __restrict__ keys_out,
+                                                                     int* __restrict__ vals_out) {
+  __shared__ int wcount[8][256];    // per-warp digit counts, later running offsets
+  __shared__ int goff[256];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < 8 * 256; i += kSortThreads) (&wcount[0][0])[i] = 0;
+  goff[tid] = hist_scan[tid * G + blockIdx.x];
+  __syncthreads();
+  const int wbase = blockIdx.x * kSortTile + w * (kSortItems * 32);
+  int k[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    int idx = wbase + r * 32 + lane;
+    k[r] = idx < E ? (FIRST ? (int)row64[idx] : keys[idx]) : -1;
+  }
+  // phase 1: per-warp digit counts
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    int idx = wbase + r * 32 + lane;
+    if (idx < E) atomicAdd(&wcount[w][(k[r] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  // phase 2: exclusive prefix over warps per digit (thread tid owns digit tid)
+  {
+    int run = 0;
+    for (int ww = 0; ww < 8; ++ww) {
+      int c = wcount[ww][tid];
+      wcount[ww][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase 3: in-order stable ranking, 32 elements per round
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    int idx = wbase + r * 32 + lane;
+    const bool valid = idx < E;
+    const int d = valid ? ((k[r] >> shift) & 255) : 256 + lane;   // invalid lanes never match
+    unsigned m = __match_any_sync(0xffffffffu, d);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    int pos = 0;
+    if (valid) pos = goff[d] + wcount[w][d] + rank;
+    __syncwarp();
+    if (valid && rank == 0) wcount[w][d] += __popc(m);
+    __syncwarp();
+    if (valid) {
+      keys_out[pos] = k[r];
+      vals_out[pos] = FIRST ? idx : vals[idx];
+    }
+  }
+}
+
+__global__ void iota_copy_kernel(int E, const int64_t* __restrict__ row64, int* __restrict__ keys, int* __restrict__ vals) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    keys[e] = (int)row64[e];
+    vals[e] = e;
+  }
+}
+
+__global__ void finalize_kernel(int E, int Fe, const int* __restrict__ keys, const int* __restrict__ vals,
+                                const int64_t* __restrict__ col64, const float* __restrict__ ea,
+                                int* __restrict__ perm, int* __restrict__ row, int* __restrict__ col,
+                                float* __restrict__ ea_sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) {
+    int p = vals[i];
+    perm[i] = p;
+    row[i] = keys[i];
+    col[i] = (int)col64[p];
+    for (int f = 0; f < Fe; ++f) ea_sorted[(size_t)i * Fe + f] = ea[(size_t)p * Fe + f];
+  }
+}
+
+size_t graph_prep_workspace_bytes(int N, int E) {
+  size_t G = ((size_t)E + kSortTile - 1) / kSortTile;
+  size_t nscan = 256 * G > (size_t)N + 1 ? 256 * G : (size_t)N + 1;
+  size_t sums = (nscan + kScanChunk - 1) / kScanChunk + 1;
+  return ((size_t)4 * E + 256 * G + sums + 64) * sizeof(int);
+}
+
+cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, const int64_t* data_batch,
+                       const float* edge_attr, int* perm, int* rowptr, int* row, int* col, int* batch, int* gptr,
+                       float* ea_sorted, float* dinv, float* inv_nb, void* ws, cudaStream_t st) {
+  const int G = (E + kSortTile - 1) / kSortTile;
+  int* keysA = reinterpret_cast<int*>(ws);
+  int* keysB = keysA + E;
+  int* valsA = keysB + E;
+  int* valsB = valsA + E;
+  int* hist = valsB + E;
+  int* sums = hist + (size_t)256 * G;
+  cudaError_t e;
+  // counts -> rowptr, gptr, reciprocals
+  if ((e = cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(gptr, 0, sizeof(int) * ((size_t)B + 1), st)) != cudaSuccess) return e;
+  if (E > 0) count_rows_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, edge_index, rowptr);
+  if (N > 0) batch_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, data_batch, batch, gptr);
+  if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums, st)) != cudaSuccess) return e;
+  if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums, st)) != cudaSuccess) return e;
+  if (N > 0) recip_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, rowptr, dinv);
+  if (B > 0) recip_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, gptr, inv_nb);
+  if (E == 0) return cudaGetLastError();
+  // radix sort (row, edge id)
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < (long long)N) ++bits;
+  const int passes = (bits + 7) / 8;
+  const int* kin = nullptr;
+  const int* vin = nullptr;
+  int* kout = keysA;
+  int* vout = valsA;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    if (p == 0) radix_hist_kernel<true><<<G, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, G, hist);
+    else radix_hist_kernel<false><<<G, kSortThreads, 0, st>>>(E, shift, nullptr, kin, G, hist);
+    if ((e = exclusive_scan(hist, 256 * G, hist, nullptr, sums, st)) != cudaSuccess) return e;
+    if (p == 0)
+      radix_scatter_kernel<true><<<G, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, nullptr, G, hist, kout, vout);
+    else
+      radix_scatter_kernel<false><<<G, kSortThreads, 0, st>>>(E, shift, nullptr, kin, vin, G, hist, kout, vout);
+    kin = kout;
+    vin = vout;
+    kout = (kout == keysA) ? keysB : keysA;
+    vout = (vout == valsA) ? valsB : valsA;
+  }
+  finalize_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, Fe, kin, vin, edge_index + E, edge_attr, perm, row, col,
+                                                    ea_sorted);
+  return cudaGetLastError();
+}
+
+}  // namespace fegnn

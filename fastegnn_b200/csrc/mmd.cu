@@ -1,0 +1,101 @@
+// mmd.cu -- MMD regulariser between sampled real coordinates and virtual coordinates.
+//
+// Replaces utils/train.py:17-20 (Laplacian kernel on the plain L2 distance) and the
+// per-graph Python loop / boolean masking of :111-165.  The random sample is an input
+// (global node indices), so torch.randperm stays the caller's RNG.
+//   loss = 1/(B C^2) sum_b sum_{c,c'} k(Z_bc, Z_bc') - 2/(B ns C) sum_b sum_{s,c} k(x_s, Z_bc)
+//   k(p,q) = exp(-|p-q| / (2 sigma^2)),  d|p-q|/dp = 0 at p == q (torch.cdist convention).
+#include "common.cuh"
+
+namespace fegnn {
+
+__global__ void __launch_bounds__(128) mmd_fwd_kernel(int B, int C, int ns, float inv2s2, const float* __restrict__ x,
+                                                      const float* __restrict__ Z, const int* __restrict__ idx,
+                                                      float* __restrict__ loss) {
+  const int b = blockIdx.x;
+  const float cvv = 1.f / ((float)B * C * C), crv = 2.f / ((float)B * ns * C);
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < C * C + ns * C; p += blockDim.x) {
+    float px, py, pz, w;
+    int c;
+    if (p < C * C) {
+      const int c0 = p / C;
+      c = p - c0 * C;
+      px = Z[((size_t)b * 3 + 0) * C + c0]; py = Z[((size_t)b * 3 + 1) * C + c0]; pz = Z[((size_t)b * 3 + 2) * C + c0];
+      w = cvv;
+    } else {
+      const int q = p - C * C, s = q / C;
+      c = q - s * C;
+      const int i = idx[(size_t)b * ns + s];
+      px = x[(size_t)i * 3 + 0]; py = x[(size_t)i * 3 + 1]; pz = x[(size_t)i * 3 + 2];
+      w = -crv;
+    }
+    const float dx = px - Z[((size_t)b * 3 + 0) * C + c], dy = py - Z[((size_t)b * 3 + 1) * C + c],
+                dz = pz - Z[((size_t)b * 3 + 2) * C + c];
+    acc += w * __expf(-sqrtf(dx * dx + dy * dy + dz * dz) * inv2s2);
+  }
+  acc = warpsum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc);
+}
+
+__global__ void __launch_bounds__(128) mmd_bwd_kernel(int B, int C, int ns, float inv2s2, const float* __restrict__ x,
+                                                      const float* __restrict__ Z, const int* __restrict__ idx,
+                                                      const float* __restrict__ gloss, float* __restrict__ gx,
+                                                      float* __restrict__ gZ) {
+  __shared__ float gz[3 * FEGNN_MAX_C];
+  const int b = blockIdx.x;
+  const float gl = gloss[0];
+  const float cvv = gl / ((float)B * C * C), crv = 2.f * gl / ((float)B * ns * C);
+  if (threadIdx.x < 3 * C) gz[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int p = threadIdx.x; p < C * C + ns * C; p += blockDim.x) {
+    float px, py, pz, w;
+    int c, c0 = -1, i = -1;
+    if (p < C * C) {
+      c0 = p / C;
+      c = p - c0 * C;
+      px = Z[((size_t)b * 3 + 0) * C + c0]; py = Z[((size_t)b * 3 + 1) * C + c0]; pz = Z[((size_t)b * 3 + 2) * C + c0];
+      w = cvv;
+    } else {
+      const int q = p - C * C, s = q / C;
+      c = q - s * C;
+      i = idx[(size_t)b * ns + s];
+      px = x[(size_t)i * 3 + 0]; py = x[(size_t)i * 3 + 1]; pz = x[(size_t)i * 3 + 2];
+      w = -crv;
+    }
+    const float dx = px - Z[((size_t)b * 3 + 0) * C + c], dy = py - Z[((size_t)b * 3 + 1) * C + c],
+                dz = pz - Z[((size_t)b * 3 + 2) * C + c];
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (dist > 0.f) {
+      // d/dp of w*exp(-dist*inv2s2) = -w*inv2s2*k * (p-q)/dist ; d/dq is the negative
+      const float f = -w * inv2s2 * __expf(-dist * inv2s2) / dist;
+      const float fx = f * dx, fy = f * dy, fz = f * dz;
+      atomicAdd(&gz[0 * C + c], -fx); atomicAdd(&gz[1 * C + c], -fy); atomicAdd(&gz[2 * C + c], -fz);
+      if (c0 >= 0) {
+        atomicAdd(&gz[0 * C + c0], fx); atomicAdd(&gz[1 * C + c0], fy); atomicAdd(&gz[2 * C + c0], fz);
+      } else {
+        atomicAdd(gx + (size_t)i * 3 + 0, fx); atomicAdd(gx + (size_t)i * 3 + 1, fy);
+        atomicAdd(gx + (size_t)i * 3 + 2, fz);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C) gZ[(size_t)b * 3 * C + threadIdx.x] = gz[threadIdx.x];
+}
+
+cudaError_t launch_mmd_fwd(int B, int C, int ns, float sigma, const float* x, const float* Z, const int* idx,
+                           float* loss, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+  if (e != cudaSuccess || B == 0) return e;
+  mmd_fwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, loss);
+  return cudaGetLastError();
+}
+cudaError_t launch_mmd_bwd(int N, int B, int C, int ns, float sigma, const float* x, const float* Z, const int* idx,
+                           const float* gloss, float* gx, float* gZ, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)N, st);
+  if (e != cudaSuccess || B == 0) return e;
+  mmd_bwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, gloss, gx, gZ);
+  return cudaGetLastError();
+}
+
+}  // namespace fegnn

@@ -1,0 +1,145 @@
+"""Thin host wrappers over the C ABI: graph prep, per-layer pointer tables, the MMD op.
+
+Everything here is plumbing (device buffers from torch, raw pointers into libfegnn.so);
+no arithmetic of the path is done in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+lib = L.lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise L.FegnnError(
+            f"{name} is on {t.device}: fastegnn_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+
+
+class CsrGraph:
+    """CSR-by-row view of one batch (output of fegnn_graph_prep), shared by all layers
+    and by backward.  Replaces the per-layer int64 gathers / scatter_add of
+    models/FastEGNN.py:182,210,279-294."""
+
+    def __init__(self, edge_index: torch.Tensor, data_batch: torch.Tensor, edge_attr: Optional[torch.Tensor],
+                 n_graphs: int, n_local: Optional[int] = None):
+        _require_cuda(edge_index, "edge_index")
+        dev = edge_index.device
+        N = int(data_batch.numel())
+        E = int(edge_index.size(1))
+        Fe = 0 if edge_attr is None else int(edge_attr.size(1))
+        if edge_index.dtype != torch.int64 or data_batch.dtype != torch.int64:
+            raise L.FegnnError("edge_index / data_batch must be int64 (as produced by the reference loaders)")
+        ei = edge_index.contiguous()
+        db = data_batch.contiguous()
+        ea = None if edge_attr is None else edge_attr.contiguous().float()
+        self.N, self.E, self.B, self.Fe = N, E, n_graphs, Fe
+        self.Nl = N if n_local is None else n_local
+        i32 = dict(device=dev, dtype=torch.int32)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.perm = torch.empty(E, **i32)
+        self.rowptr = torch.empty(N + 1, **i32)
+        self.row = torch.empty(E, **i32)
+        self.col = torch.empty(E, **i32)
+        self.batch = torch.empty(N, **i32)
+        self.gptr = torch.empty(n_graphs + 1, **i32)
+        self.edge_attr = torch.empty(E, max(Fe, 1), **f32) if Fe else torch.empty(0, **f32)
+        self.dinv = torch.empty(N, **f32)
+        self.inv_nb = torch.empty(n_graphs, **f32)
+        nbytes = int(lib.fegnn_graph_prep_workspace_bytes(N, E))
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        L.check(lib.fegnn_graph_prep(N, E, n_graphs, Fe, L.ptr(ei), L.ptr(db), L.ptr(ea), L.ptr(self.perm),
+                                     L.ptr(self.rowptr), L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch),
+                                     L.ptr(self.gptr), L.ptr(self.edge_attr), L.ptr(self.dinv), L.ptr(self.inv_nb),
+                                     L.ptr(ws), nbytes, _stream()), "fegnn_graph_prep")
+        self._ws = ws   # stream-ordered: keep alive until the kernels that use it have been enqueued
+        self.c = L.Graph(L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch), L.ptr(self.edge_attr),
+                         L.ptr(self.dinv), L.ptr(self.inv_nb))
+
+
+def make_dims(N: int, Nl: int, E: int, B: int, C_: int, Fe: int, flags: int,
+              gravity: Optional[Sequence[float]] = None, eps: float = 1e-8) -> L.Dims:
+    d = L.Dims()
+    d.N, d.Nl, d.E, d.B, d.C, d.Fe, d.flags = N, Nl, E, B, C_, Fe, flags
+    g = (0.0, 0.0, 0.0) if gravity is None else tuple(float(x) for x in gravity)
+    d.gravity[0], d.gravity[1], d.gravity[2] = g
+    d.eps = eps
+    return d
+
+
+def layer_ptrs(tensors: Dict[str, torch.Tensor], prefix: str) -> L.LayerPtrs:
+    """Pointer table of one layer from reference-named tensors (missing names -> NULL)."""
+    p = L.LayerPtrs()
+    for field, suffix in L.LAYER_FIELDS:
+        t = tensors.get(f"{prefix}.{suffix}" if prefix else suffix)
+        if t is not None:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise L.FegnnError(f"parameter {prefix}.{suffix} must be a contiguous fp32 CUDA tensor")
+            setattr(p, field, t.data_ptr())
+    return p
+
+
+class SavedBlock:
+    """One layer's kept activations: a flat buffer carved by fegnn_layer_saved_bind."""
+
+    def __init__(self, dims: L.Dims, device):
+        n = int(lib.fegnn_layer_saved_floats(C.byref(dims)))
+        self.buf = torch.empty(n, device=device, dtype=torch.float32)
+        self.c = L.Saved()
+        L.check(lib.fegnn_layer_saved_bind(C.byref(dims), L.ptr(self.buf), C.byref(self.c)), "fegnn_layer_saved_bind")
+        self.dims = dims
+
+    def view(self, name: str, shape) -> torch.Tensor:
+        off = (getattr(self.c, name) - self.buf.data_ptr()) // 4
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buf[off:off + n].view(*shape)
+
+
+# ----------------------------------------------------------------------------- MMD
+class _MmdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Z, sample_idx, sigma):
+        _require_cuda(x, "node_loc")
+        x = x.contiguous()
+        Z = Z.contiguous()
+        B, _, C_ = Z.shape
+        ns = sample_idx.size(1)
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        L.check(lib.fegnn_mmd_forward(B, C_, ns, float(sigma), L.ptr(x), L.ptr(Z), L.ptr(sample_idx), L.ptr(loss),
+                                      _stream()), "fegnn_mmd_forward")
+        ctx.save_for_backward(x, Z, sample_idx)
+        ctx.sigma = float(sigma)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, Z, idx = ctx.saved_tensors
+        B, _, C_ = Z.shape
+        gx = torch.empty_like(x)
+        gZ = torch.empty_like(Z)
+        gl = g.reshape(1).contiguous().float()
+        L.check(lib.fegnn_mmd_backward(x.size(0), B, C_, idx.size(1), ctx.sigma, L.ptr(x), L.ptr(Z), L.ptr(idx),
+                                       L.ptr(gl), L.ptr(gx), L.ptr(gZ), _stream()), "fegnn_mmd_backward")
+        return gx, gZ, None, None
+
+
+def mmd_loss(node_loc: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx: torch.Tensor, sigma: float):
+    """l_vv - l_rv of utils/train.py:111-165 in one launch.
+
+    node_loc [N,3]; virtual_node_loc [B,3,C] exactly as FastEGNN.forward returns it (the
+    reference permutes it to [B,C,3] at :113); sample_idx int32 [B, ns] of GLOBAL node
+    indices (graph offset + the reference's torch.randperm(n_b)[:ns])."""
+    if sample_idx.dtype != torch.int32:
+        sample_idx = sample_idx.to(torch.int32)
+    return _MmdFn.apply(node_loc, virtual_node_loc, sample_idx.contiguous(), sigma)

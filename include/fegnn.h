@@ -1,0 +1,234 @@
+/* fegnn.h -- C ABI of the B200-native FastEGNN layer path (libfegnn.so).
+ *
+ * The reference (GLAD-RUC/FastEGNN) has no FFI: its "operator interface" for this
+ * path is the Python class API of models/FastEGNN.py (FastEGNN.forward :265-276,
+ * E_GCL_vel.forward :192-223) plus the MMD block of utils/train.py:111-165.
+ * Every entry point below states which reference lines it replaces.  A binding
+ * (ctypes) lives in fastegnn_b200/_lib.py; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - no allocation, no synchronisation, no host<->device copies inside any call
+ *     (fegnn_graph_prep_* use the caller's workspace); safe for CUDA-graph capture.
+ *   - return 0 on success, negative FEGNN_E* otherwise; fegnn_last_error() gives a
+ *     thread-local message.
+ *   - fp32 everywhere, indices int32 after graph prep (the reference's int64
+ *     edge_index / data_batch are converted once by fegnn_graph_prep).
+ *   - H (hidden_nf) must be 64; 1 <= C <= FEGNN_MAX_C; 0 <= Fe <= FEGNN_MAX_FE.
+ *   - "reference layout" = torch.nn.Linear weight [out, in] row-major, the tensors
+ *     of the reference state_dict, untouched.  Kernels re-tile them in shared memory.
+ */
+#ifndef FEGNN_H_
+#define FEGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEGNN_H 64
+#define FEGNN_MAX_C 16
+#define FEGNN_MAX_FE 8
+
+#define FEGNN_OK 0
+#define FEGNN_EINVAL (-1)   /* bad argument (shape / flag / null pointer)  */
+#define FEGNN_ECUDA (-2)    /* a CUDA runtime call or launch failed        */
+#define FEGNN_ENOMEM (-3)   /* caller workspace too small                  */
+
+/* flag word (reference ctor kwargs, models/FastEGNN.py:11-12,227-228) */
+#define FEGNN_F_ATTENTION 1u
+#define FEGNN_F_NORMALIZE 2u
+#define FEGNN_F_TANH 4u
+#define FEGNN_F_GRAVITY 8u
+#define FEGNN_F_LAST 16u      /* last layer of the stack: phi_h / phi_hv outputs are discarded (:276) */
+
+typedef struct fegnn_dims {
+  int32_t N;        /* owned real nodes                                             */
+  int32_t Nl;       /* rows of x / Q: owned + halo (== N on one GPU)                */
+  int32_t E;        /* directed real edges owned (row < N, col < Nl)                */
+  int32_t B;        /* graphs                                                       */
+  int32_t C;        /* virtual channels                                             */
+  int32_t Fe;       /* edge_attr width                                              */
+  uint32_t flags;   /* FEGNN_F_*                                                    */
+  float gravity[3]; /* models/FastEGNN.py:258-259                                   */
+  float eps;        /* normalize epsilon, :21                                       */
+} fegnn_dims;
+
+/* CSR-by-row graph, produced by fegnn_graph_prep (all int32 / fp32, device). */
+typedef struct fegnn_graph {
+  const int32_t* row;     /* [E] sorted ascending (stable)                          */
+  const int32_t* col;     /* [E] col[perm]                                          */
+  const int32_t* batch;   /* [N] graph id per node, non-decreasing                  */
+  const float* edge_attr; /* [E,Fe] edge_attr[perm]                                 */
+  const float* dinv;      /* [N]  1 / max(1, deg_row)        (:294 clamp(min=1))    */
+  const float* inv_nb;    /* [B]  1 / max(1, nodes in graph) (global_mean_pool)     */
+} fegnn_graph;
+
+/* One layer's parameters in reference layout (models/FastEGNN.py:28-99).
+ * att_* may be NULL without FEGNN_F_ATTENTION, gravity_* without FEGNN_F_GRAVITY. */
+typedef struct fegnn_layer_params {
+  const float *edge_w0, *edge_b0, *edge_w2, *edge_b2;         /* edge_mlp.{0,2}           [H,2H+1+Fe],[H],[H,H],[H] */
+  const float *edgev_w0, *edgev_b0, *edgev_w2, *edgev_b2;     /* edge_mlp_virtual.{0,2}   [H,2H+1+C],...            */
+  const float *cr_w0, *cr_b0, *cr_w2;                         /* coord_mlp_r.{0,2}        [H,H],[H],[1,H]           */
+  const float *crv_w0, *crv_b0, *crv_w2;                      /* coord_mlp_r_virtual                                 */
+  const float *cvv_w0, *cvv_b0, *cvv_w2;                      /* coord_mlp_v_virtual                                 */
+  const float *vel_w0, *vel_b0, *vel_w2, *vel_b2;             /* coord_mlp_vel.{0,2}      [H,H],[H],[1,H],[1]       */
+  const float *grav_w0, *grav_b0, *grav_w2, *grav_b2;         /* gravity_mlp.{0,2}                                   */
+  const float *node_w0, *node_b0, *node_w2, *node_b2;         /* node_mlp.{0,2}           [H,2H+H*C],[H],[H,H],[H]  */
+  const float *nodev_w0, *nodev_b0, *nodev_w2, *nodev_b2;     /* node_mlp_virtual.{0,2}   [H,2H],[H],[H,H],[H]      */
+  const float *att_w, *att_b, *attv_w, *attv_b;               /* att_mlp.0, att_mlp_virtual.0  [1,H],[1]            */
+} fegnn_layer_params;
+#define FEGNN_LAYER_NPTR 37
+
+/* Same member order; gradients are ACCUMULATED (+=) into these buffers, which the
+ * caller zero-fills once per backward.  A NULL member means "no gradient wanted". */
+typedef struct fegnn_layer_grads {
+  float *edge_w0, *edge_b0, *edge_w2, *edge_b2;
+  float *edgev_w0, *edgev_b0, *edgev_w2, *edgev_b2;
+  float *cr_w0, *cr_b0, *cr_w2;
+  float *crv_w0, *crv_b0, *crv_w2;
+  float *cvv_w0, *cvv_b0, *cvv_w2;
+  float *vel_w0, *vel_b0, *vel_w2, *vel_b2;
+  float *grav_w0, *grav_b0, *grav_w2, *grav_b2;
+  float *node_w0, *node_b0, *node_w2, *node_b2;
+  float *nodev_w0, *nodev_b0, *nodev_w2, *nodev_b2;
+  float *att_w, *att_b, *attv_w, *attv_b;
+} fegnn_layer_grads;
+
+/* Per-layer activations kept from forward for backward (all device, caller-owned;
+ * fegnn_layer_saved_floats() gives the size of one contiguous block and
+ * fegnn_layer_saved_bind() carves it). */
+typedef struct fegnn_layer_saved {
+  float *P, *Q, *Av, *Uh;   /* [N,H] [Nl,H] [N,H] [N,H] first-layer products of h        */
+  float *sv, *sg;           /* [N] phi_v(h), phi_g(h)                                     */
+  float *M, *Zc, *G1;       /* [B,C,C] [B,3,C] [B,C,H] per-graph terms                    */
+  float *msum, *tsum;       /* [N,H] [N,3] row sums of m_e and d_e*phi_x(m_e)             */
+  float *u;                 /* [N,C,H] real->virtual messages                             */
+  float *zh1;               /* [N,H] phi_h pre-activation                                 */
+  float *Dsum, *Usum;       /* [B,3,C] [B,C,H] per-graph partial sums (all-reduced when partitioned) */
+} fegnn_layer_saved;
+
+const char* fegnn_last_error(void);
+int fegnn_version(void);
+
+/* ------------------------------------------------------------------ graph prep
+ * Replaces, for the whole stack, what the reference redoes in every layer with
+ * int64 gathers / scatter_add (models/FastEGNN.py:182,210,283-294) and
+ * global_mean_pool's counting (:148,170,212).  Stable sort of edges by row
+ * (== torch.sort(row, stable=True)): perm, rowptr, sorted row/col as int32,
+ * gathered edge_attr, clamped inverse degrees and inverse graph sizes.          */
+size_t fegnn_graph_prep_workspace_bytes(int32_t N, int32_t E);
+int fegnn_graph_prep(int32_t N, int32_t E, int32_t B, int32_t Fe,
+                     const int64_t* edge_index /*[2,E]*/, const int64_t* data_batch /*[N]*/,
+                     const float* edge_attr /*[E,Fe] or NULL*/,
+                     int32_t* perm /*[E]*/, int32_t* rowptr /*[N+1]*/, int32_t* row /*[E]*/, int32_t* col /*[E]*/,
+                     int32_t* batch /*[N]*/, int32_t* gptr /*[B+1]*/, float* edge_attr_sorted /*[E,Fe]*/,
+                     float* dinv /*[N]*/, float* inv_nb /*[B]*/,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ phases of one layer (forward)
+ * Names follow oracle/staged.py, which spells the same pipeline out on the CPU.  */
+
+/* embedding_in (models/FastEGNN.py:271) and per-graph coordinate sums for xbar (:212). */
+int fegnn_embed_forward(int32_t N, int32_t Fin, const float* node_feat, const float* w /*[H,Fin]*/, const float* b,
+                        float* h, void* stream);
+int fegnn_embed_backward(int32_t N, int32_t Fin, const float* node_feat, const float* w, const float* gh,
+                         float* gw, float* gb, float* gnode_feat /*or NULL*/, void* stream);
+int fegnn_graph_xsum(int32_t N, int32_t B, const float* x, const int32_t* batch, float* xsum /*[B,3] zeroed here*/,
+                     void* stream);
+
+/* xbar, centred Gram M and G1 = V1s S_c + V1m M[:,c]        (:212-214, per-graph part of :112-115) */
+int fegnn_graph_pre_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                            const float* Z, const float* S, const float* xsum, fegnn_layer_saved* sv, void* stream);
+/* P,Q,Av,Uh and phi_v / phi_g heads: the h-dependent half of every first Linear (:104,115,139,142,162) */
+int fegnn_node_pre_forward(const fegnn_dims* d, const fegnn_layer_params* p, const float* h, fegnn_layer_saved* sv,
+                           void* stream);
+/* fused real-edge phase: gather, phi_e, phi_x, segment sums by row (:102-108,:125-129,:156) */
+int fegnn_edge_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                       fegnn_layer_saved* sv, void* stream);
+/* dense N x C real<->virtual phase + new coordinates + per-graph partial sums (:111-119,:133-150) */
+int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* x,
+                          const float* v, const float* Z, fegnn_layer_saved* sv, float* x_new /*[N,3]*/,
+                          float* xsum_new /*[B,3]*/, void* stream);
+/* phi_h (:153-166) */
+int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* h,
+                         fegnn_layer_saved* sv, float* h_new, void* stream);
+/* Z' and S' (:146-150,:168-177) */
+int fegnn_graph_post_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* Z,
+                             const float* S, const fegnn_layer_saved* sv, float* Z_new, float* S_new, void* stream);
+
+/* ------------------------------------------------------------------ phases of one layer (backward)
+ * Hand-written adjoints of the phases above; per-edge / per-(node,channel)
+ * activations are recomputed, never stored.                                     */
+int fegnn_graph_post_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                              fegnn_layer_grads* gr, const float* S, const fegnn_layer_saved* sv,
+                              const float* gZ_new, const float* gS_new,
+                              float* gZ /*[B,3,C] =*/, float* gS /*[B,C,H] =*/, float* gDsum /*[B,3,C] =*/,
+                              float* gUsum /*[B,C,H] =*/, void* stream);
+int fegnn_node_h_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                          fegnn_layer_grads* gr, const fegnn_layer_saved* sv, const float* gh_new,
+                          float* gzh1 /*[N,H] =*/, float* gm /*[N,H] =*/, float* gu /*[N,C,H] =*/, void* stream);
+int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                           fegnn_layer_grads* gr, const float* x, const float* v, const float* Z,
+                           const fegnn_layer_saved* sv, const float* gx_new /*[N,3]*/,
+                           const float* gxsum_next /*[B,3] or NULL*/, const float* gDsum, const float* gUsum,
+                           const float* gu /*[N,C,H] or NULL (last layer)*/,
+                           float* gAv /*[N,H] =*/, float* gG1 /*[B,C,H] zeroed here, +=*/, float* gx /*[Nl,3] zeroed here, owned rows =*/,
+                           float* gZ /*[B,3,C] +=*/, float* gsv /*[N] =*/, float* gsg /*[N] =*/, float* gt /*[N,3] =*/,
+                           void* stream);
+int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                        fegnn_layer_grads* gr, const float* x, const fegnn_layer_saved* sv,
+                        const float* gm /*[N,H] or NULL*/, const float* gt /*[N,3]*/,
+                        float* gP /*[N,H] zeroed here, +=*/, float* gQ /*[Nl,H] zeroed here, +=*/, float* gx /*[Nl,3] +=*/,
+                        void* stream);
+int fegnn_graph_pre_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p,
+                             fegnn_layer_grads* gr, const float* S, const fegnn_layer_saved* sv, const float* gG1,
+                             float* gS /*[B,C,H] +=*/, float* gZ /*[B,3,C] +=*/, float* gxsum /*[B,3] =*/, void* stream);
+int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fegnn_layer_grads* gr, const float* h,
+                            const float* gP, const float* gQ, const float* gAv, const float* gUh /*or NULL*/,
+                            const float* gsv, const float* gsg, float* gh /*[N,H] in: dL/dh' (residual), out: dL/dh*/,
+                            void* stream);
+
+/* ------------------------------------------------------------------ whole layer / whole stack
+ * fegnn_layer_forward == one E_GCL_vel.forward (:192-223) with S in [B,C,H];
+ * fegnn_model_forward == FastEGNN.forward (:265-276) after graph prep.
+ * Workspace layout is private; sizes come from the *_floats queries.            */
+size_t fegnn_layer_saved_floats(const fegnn_dims* d);
+int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out);
+size_t fegnn_model_workspace_floats(const fegnn_dims* d, int32_t L);
+size_t fegnn_model_backward_scratch_floats(const fegnn_dims* d);
+
+int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                        const fegnn_layer_params* layers_host /*[L]*/, const float* embed_w, const float* embed_b,
+                        const float* virtual_node_feat /*[1,H,C] reference layout*/,
+                        const float* node_feat /*[N,Fin]*/, const float* x0 /*[N,3]*/, const float* v /*[N,3]*/,
+                        const float* loc_mean /*[B,3,C]*/, float* x_out /*[N,3]*/, float* Z_out /*[B,3,C]*/,
+                        float* workspace, size_t workspace_floats, void* stream);
+int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                         const fegnn_layer_params* layers_host, fegnn_layer_grads* grads_host /*[L]*/,
+                         const float* embed_w, float* g_embed_w, float* g_embed_b, float* g_virtual_node_feat,
+                         const float* node_feat, const float* v,
+                         const float* gx_out /*[N,3]*/, const float* gZ_out /*[B,3,C]*/,
+                         float* g_x0 /*[N,3]*/, float* g_loc_mean /*[B,3,C]*/, float* g_node_feat /*[N,Fin] or NULL*/,
+                         const float* workspace, float* scratch, size_t scratch_floats, void* stream);
+
+/* ------------------------------------------------------------------ MMD regulariser
+ * utils/train.py:17-20,111-165 with the random sample made explicit:
+ * sample_idx[b*ns + s] is a GLOBAL node index (graph offset already added).
+ * loss = (1/(B C^2)) sum k(Z_bc,Z_bc') - (2/(B ns C)) sum k(x_s, Z_bc),
+ * k(p,q) = exp(-|p-q| / (2 sigma^2)).                                            */
+int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, const float* x /*[N,3]*/,
+                      const float* Z /*[B,3,C]*/, const int32_t* sample_idx, float* loss /*[1] zeroed here*/,
+                      void* stream);
+int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
+                       const int32_t* sample_idx, const float* gloss /*[1]*/, float* gx /*[N,3] zeroed here*/,
+                       float* gZ /*[B,3,C] =*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEGNN_H_ */

@@ -466,6 +466,7 @@ class StagedModel:
         gS = gx_out.new_zeros(g.B, C, H)
         gx, gZ = gx_out, gZ_out
         gxsum_next = gx_out.new_zeros(g.B, 3)
+        self.bsaved = [None] * self.L          # per-layer backward intermediates, for phase-level GPU tests
         for l in reversed(range(self.L)):
             w, sv, last, p = self.w[l], self.saved[l], l == self.L - 1, f"gcl_{l}"
             gxn = gx + gxsum_next[g.batch]            # x' also feeds the next layer's xbar
@@ -481,8 +482,12 @@ class StagedModel:
             f = node_pre_bwd(w, g, fl, sv["h"], d["gP"], d["gQ"], c["gAv"], b["gzh1"], c["gsv"], c.get("gsg"))
             if last:                                  # phi_h is dead in the last layer: its tensors get no grad
                 f["wg"].pop("U1h"), f["wg"].pop("e1")
+            lg: Dict[str, T] = {}
             for wg in (a["wg"], b["wg"], c["wg"], d["wg"], e["wg"], f["wg"]):
                 _scatter_wg(grads, p, wg, w, H, C, Fe)
+                _scatter_wg(lg, p, wg, w, H, C, Fe)
+            self.bsaved[l] = dict(gh_new=gh, gx_new=gx, gZ_new=gZ, gS_new=gS, gxsum_next=gxsum_next, gxn=gxn,
+                                  a=a, b=b, c=c, d=d, e=e, f=f, layer_grads=lg)
             gh = gh + f["gh"]
             gx = c["gx"] + d["gx"]
             gZ = a["gZ"] + c["gZ"] + e["gZ"]

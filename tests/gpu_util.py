@@ -1,0 +1,111 @@
+"""Helpers for the -m gpu parity tests (test infrastructure)."""
+import numpy as np
+import torch
+
+from oracle import fastegnn_oracle as orc
+from tests.helpers import oracle_run
+
+
+def make_graph_case(seed, sizes, deg, C, Fe=2, nf=2, L=4, gravity=None, attention=False, normalize=False,
+                    tanh=False, gain=1000.0, heavy_row=0, coord_scale=1.5):
+    """Seeded synthetic batch: unequal graphs, self-loops and duplicate edges allowed, some
+    isolated rows, optionally one row with `heavy_row` incident edges (spans several edge tiles)."""
+    g = torch.Generator().manual_seed(seed)
+    N, B = sum(sizes), len(sizes)
+    batch = torch.cat([torch.full((n,), b, dtype=torch.long) for b, n in enumerate(sizes)])
+    x = torch.randn(N, 3, generator=g) * coord_scale
+    v = torch.randn(N, 3, generator=g) * 0.5
+    node_feat = torch.rand(N, nf, generator=g)
+    rows, cols, off = [], [], 0
+    for n in sizes:
+        e = n * deg
+        r = torch.randint(0, max(n - 2, 1), (e,), generator=g) + off      # last two nodes of each graph: no row edges
+        c = torch.randint(0, n, (e,), generator=g) + off
+        rows.append(r)
+        cols.append(c)
+        off += n
+    if heavy_row:
+        rows.append(torch.full((heavy_row,), 1, dtype=torch.long))
+        cols.append(torch.randint(0, sizes[0], (heavy_row,), generator=g))
+    ei = torch.stack([torch.cat(rows), torch.cat(cols)])
+    perm = torch.randperm(ei.size(1), generator=g)
+    ei = ei[:, perm]
+    dist = (x[ei[0]] - x[ei[1]]).norm(dim=1, keepdim=True)
+    ea = torch.cat([dist] * Fe, dim=1) if Fe else torch.empty(ei.size(1), 0)
+    loc_mean = torch.stack([x[batch == b].mean(0) for b in range(B)]).unsqueeze(-1).repeat(1, 1, C)
+    loc_mean = loc_mean + 0.3 * torch.randn(B, 3, C, generator=g)
+    cfg = orc.OracleConfig(node_feat_nf=nf, edge_attr_nf=Fe, hidden_nf=64, virtual_channels=C, n_layers=L,
+                           attention=attention, normalize=normalize, tanh=tanh, gravity=gravity)
+    params = orc.make_params(cfg, seed + 1000)
+    if gain != 1.0:
+        orc.rescale_coord_heads(params, gain)
+    inp = dict(node_feat=node_feat, node_loc=x, node_vel=v, loc_mean=loc_mean, edge_attr=ea, edge_index=ei,
+               data_batch=batch, wx=torch.randn(N, 3, generator=g), wz=torch.randn(B, 3, C, generator=g))
+    return cfg, params, inp
+
+
+def build_gpu_model(cfg, params, dev="cuda:0"):
+    from fastegnn_b200 import FastEGNN
+    m = FastEGNN(node_feat_nf=cfg.node_feat_nf, node_attr_nf=0, edge_attr_nf=cfg.edge_attr_nf,
+                 hidden_nf=cfg.hidden_nf, virtual_channels=cfg.virtual_channels, device=dev, n_layers=cfg.n_layers,
+                 attention=cfg.attention, normalize=cfg.normalize, tanh=cfg.tanh, gravity=cfg.gravity)
+    m.load_state_dict({k: v.to(dev) for k, v in params.items()})
+    return m
+
+
+def gpu_run(cfg, params, inp, dev="cuda:0", want_grads=True):
+    m = build_gpu_model(cfg, params, dev)
+    g = {k: (None if v is None else v.to(dev)) for k, v in inp.items()}
+    leaf = {k: g[k].clone().requires_grad_(want_grads) for k in ("node_loc", "loc_mean", "node_feat")}
+    x, Z = m(node_feat=leaf["node_feat"], node_loc=leaf["node_loc"], node_vel=g["node_vel"],
+             edge_index=g["edge_index"], data_batch=g["data_batch"], loc_mean=leaf["loc_mean"],
+             edge_attr=g["edge_attr"])
+    res = dict(x=x.detach().cpu(), Z=Z.detach().cpu())
+    if want_grads:
+        ((x * g["wx"]).sum() + (Z * g["wz"]).sum()).backward()
+        res["gin"] = {k: t.grad.cpu() for k, t in leaf.items()}
+        res["gp"] = {k: (None if p.grad is None else p.grad.cpu()) for k, p in m.named_parameters()}
+    torch.cuda.synchronize()
+    return res
+
+
+def rel_err(a, ref):
+    a, ref = a.double(), ref.double()
+    return float((a - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+def compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=""):
+    """GPU result vs the fp64 oracle, with the fp32 oracle's own distance to fp64 alongside."""
+    p64 = {k: v.double() for k, v in params.items()}
+    i64 = {k: (v.double() if v is not None and v.is_floating_point() else v) for k, v in inp.items()}
+    r64 = oracle_run(cfg, p64, i64)
+    r32 = oracle_run(cfg, params, inp)
+    report, worst = [], 0.0
+
+    def chk(name, got, want64, want32, tol):
+        nonlocal worst
+        e_gpu = rel_err(got, want64)
+        e_ref = rel_err(want32, want64)
+        report.append(f"{label}{name}: gpu {e_gpu:.2e}  oracle32 {e_ref:.2e}")
+        ok = e_gpu <= tol
+        worst = max(worst, e_gpu / tol)
+        return ok
+
+    bad = []
+    for k in ("x", "Z"):
+        if not chk(k, res[k], r64[k], r32[k], tol_out):
+            bad.append(k)
+    for k in ("node_loc", "loc_mean", "node_feat"):
+        if not chk("gin." + k, res["gin"][k], r64["gin"][k], r32["gin"][k], tol_grad):
+            bad.append(k)
+    for k, g64 in r64["gp"].items():
+        if g64 is None:
+            if res["gp"][k] is not None:
+                bad.append(k + " (should have no grad)")
+            continue
+        if res["gp"][k] is None:
+            bad.append(k + " (missing grad)")
+            continue
+        if not chk("gp." + k, res["gp"][k], g64, r32["gp"][k], tol_grad):
+            bad.append(k)
+    return bad, report
