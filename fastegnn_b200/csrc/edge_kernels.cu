@@ -363,8 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd_kernel(EdgeArgs a) {
       const float inv = norm ? 1.f / v->snrm[tid] : 1.f;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        float gd = s * v->sgte[tid * 3 + k] * inv + gq2 * v->sd[tid * 3 + k];
-        if (r >= 0) atomicAdd(a.gx + (size_t)c * 3 + k, -gd);
+        // a self-loop adds +gd and -gd to the same node: skip both (with normalize, 1/nrm is 1e8 there and
+        // the two halves would only cancel to rounding)
+        float gd = r == c ? 0.f : s * v->sgte[tid * 3 + k] * inv + gq2 * v->sd[tid * 3 + k];
+        if (r >= 0 && r != c) atomicAdd(a.gx + (size_t)c * 3 + k, -gd);
         bool tail;
         float tot = warp_segsum(r >= 0 ? gd : 0.f, r, lane, tail);
         if (tail && r >= 0) atomicAdd(a.gx + (size_t)r * 3 + k, tot);

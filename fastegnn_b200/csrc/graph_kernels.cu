@@ -27,16 +27,16 @@ struct GraphArgs {
 
 constexpr int kPerThread = (FEGNN_MAX_C * kH + kThreads - 1) / kThreads;
 
-struct GraphSmem {
-  float xbar[3];
+struct __align__(16) GraphSmem {
+  float a[FEGNN_MAX_C * kH];     // S / at                 (float4-accessed arrays first: 16-byte aligned)
+  float b[FEGNN_MAX_C * kH];     // Um / gzt1 / gG1
+  float c[FEGNN_MAX_C * kH];     // dsilu(zt1) / at
+  float d[FEGNN_MAX_C * kH];     // gzt2
   float Zc[3 * FEGNN_MAX_C];
   float M[FEGNN_MAX_C * FEGNN_MAX_C];
   float gM[FEGNN_MAX_C * FEGNN_MAX_C];
   float gZc[3 * FEGNN_MAX_C];
-  float a[FEGNN_MAX_C * kH];     // S / at
-  float b[FEGNN_MAX_C * kH];     // Um / gzt1 / gG1
-  float c[FEGNN_MAX_C * kH];     // dsilu(zt1) / at
-  float d[FEGNN_MAX_C * kH];     // gzt2
+  float xbar[4];
 };
 
 __global__ void __launch_bounds__(kThreads) graph_pre_fwd_kernel(GraphArgs a) {

@@ -28,8 +28,18 @@ def test_golden_vectors_from_reference(name):
     res = gpu_run(cfg, params, inp)
     assert rel_err(res["x"], torch.from_numpy(arr["out_x"])) < TOL_OUT
     assert rel_err(res["Z"], torch.from_numpy(arr["out_Z"])) < TOL_OUT
+    # The golden gradients are the reference's own fp32 autograd.  With normalize=True a self-loop
+    # contributes +g/1e-8 and -g/1e-8 to the same node (models/FastEGNN.py:186), which the reference
+    # cancels only to rounding (c1_flags: its gin.node_loc is 3.9e-2 from the fp64 value); the CUDA path
+    # drops the pair exactly.  So the golden's own distance to the fp64 oracle is added to the tolerance,
+    # and the fp64 oracle is checked at the plain tolerance.
+    p64 = {k: v.double() for k, v in params.items()}
+    i64 = {k: (v.double() if v.is_floating_point() else v) for k, v in inp.items()}
+    r64 = oracle_run(cfg, p64, i64)
     for k in ("node_loc", "loc_mean", "node_feat"):
-        assert rel_err(res["gin"][k], torch.from_numpy(arr[f"gin_{k}"])) < TOL_GRAD, k
+        gold = torch.from_numpy(arr[f"gin_{k}"])
+        assert rel_err(res["gin"][k], r64["gin"][k]) < TOL_GRAD, k
+        assert rel_err(res["gin"][k], gold) < TOL_GRAD + rel_err(gold, r64["gin"][k]), k
     none = sorted(k for k, g in res["gp"].items() if g is None)
     assert none == sorted(meta["grad_none"])          # last layer's node_mlp / node_mlp_virtual: no gradient
     for k, dig in meta["grad_digest"].items():
