@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- FastEGNN layer path on B200: layer fwd+bwd edges/s and train steps/s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE
+JSON line from rank 0.  A step is one full training step of the reference's loop
+(utils/train.py:49-170) on one batch of the workload: 4-layer FastEGNN forward, MSE + weight*MMD,
+backward, Adam step.  `value` = (edges x layers processed by all ranks) / (max-over-ranks device time),
+inputs resident in HBM; `e2e` = the same with pinned HOST inputs copied in and the loss read back
+inside the timed region.
+
+Workloads (BASELINE.json configs):
+  water3d   (default, config 4) 8 000 uniform particles, radius graph with mean degree ~25
+            (E ~ 2e5 directed edges, ordered by ascending length), C=3, gravity [0,-1,0], B=1.
+  nbody100  (config 2) 100 graphs x 100 particles, shortest 50% of all ordered pairs.
+  large     (config 5 shape, scaled by --nodes) uniform cloud, mean degree 30, C=8.
+With N>1 ranks every rank trains on its own whole graphs (weak scaling) and weight gradients are
+all-reduced over NCCL once per step (SURVEY.md 5.1 mode 1).
+
+`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops in the
+reference's op order, all host threads) on the same workload and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, LAYERS = 64, 4
+
+
+# ----------------------------------------------------------------------------- workloads
+def radius_graph_np(pts: np.ndarray, r: float):
+    from scipy.spatial import cKDTree
+    pairs = cKDTree(pts).query_pairs(r, output_type="ndarray")           # i < j
+    row = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    col = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    return row, col
+
+
+def make_cloud(n: int, mean_deg: float, C: int, seed: int, gravity, r: float = 0.035, vel_std: float = 0.01):
+    """Uniform points in a cube sized so that radius r gives `mean_deg` neighbours
+    (datasets/simulation/dataset.py:80); edges ordered by ascending length like cutoff_edge (:96-101)."""
+    rng = np.random.default_rng(seed)
+    rho = mean_deg / (4.0 / 3.0 * math.pi * r ** 3)
+    side = (n / rho) ** (1.0 / 3.0)
+    x = (rng.random((n, 3)) * side).astype(np.float32)
+    row, col = radius_graph_np(x.astype(np.float64), r)
+    length = np.linalg.norm(x[row] - x[col], axis=1)
+    order = np.argsort(length, kind="stable")
+    row, col, length = row[order], col[order], length[order].astype(np.float32)
+    v = (rng.standard_normal((n, 3)) * vel_std).astype(np.float32)
+    q = rng.choice([-1.0, 1.0], size=n).astype(np.float32)
+    node_feat = np.stack([np.linalg.norm(v, axis=1), q / np.abs(q).max()], axis=1).astype(np.float32)
+    loc_t = (x + v + rng.standard_normal((n, 3)).astype(np.float32) * 1e-3).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return dict(node_feat=t(node_feat), loc_0=t(x), vel_0=t(v), loc_t=t(loc_t),
+                edge_index=t(np.stack([row, col]).astype(np.int64)),
+                edge_attr=t(np.stack([length, length], axis=1)),                 # utils/train.py:41-43
+                batch=torch.zeros(n, dtype=torch.int64),
+                loc_mean=t(x.mean(0, keepdims=True).T[None].repeat(C, axis=2).astype(np.float32)),
+                n_graphs=1, C=C, gravity=gravity, sizes=[n])
+
+
+def make_nbody(n: int, B: int, cutoff: float, C: int, seed: int):
+    """datagen/system.py:21-39 initial conditions + datasets/nbody/dataset.py:102-113 edge selection."""
+    rng = np.random.default_rng(seed)
+    sigma = (n / 5.0) ** (1.0 / 3.0) + 0.1
+    xs, vs, nfs, rows, cols, eas, lms = [], [], [], [], [], [], []
+    keep = int(n * (n - 1) * (1 - cutoff))
+    for b in range(B):
+        x = (rng.standard_normal((n, 3)) * sigma).astype(np.float32)
+        v = rng.standard_normal((n, 3)).astype(np.float32)
+        v = (v / np.linalg.norm(v, axis=1, keepdims=True) * 0.5).astype(np.float32)
+        q = rng.choice([-1.0, 1.0], size=n).astype(np.float32)
+        d = np.linalg.norm(x[:, None] - x[None], axis=2)
+        np.fill_diagonal(d, 1e18)
+        idx = np.argsort(d.reshape(-1), kind="stable")[:keep]
+        r, c = idx // n, idx % n
+        ln = d.reshape(-1)[idx].astype(np.float32)
+        xs.append(x); vs.append(v); nfs.append(np.stack([np.linalg.norm(v, axis=1), q], 1).astype(np.float32))
+        rows.append(r + b * n); cols.append(c + b * n); eas.append(np.stack([ln, ln], 1))
+        lms.append(x.mean(0, keepdims=True).T.repeat(C, axis=1))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    x = np.concatenate(xs)
+    v = np.concatenate(vs)
+    return dict(node_feat=t(np.concatenate(nfs)), loc_0=t(x), vel_0=t(v), loc_t=t((x + v).astype(np.float32)),
+                edge_index=t(np.stack([np.concatenate(rows), np.concatenate(cols)]).astype(np.int64)),
+                edge_attr=t(np.concatenate(eas).astype(np.float32)),
+                batch=torch.arange(B).repeat_interleave(n), loc_mean=t(np.stack(lms).astype(np.float32)),
+                n_graphs=B, C=C, gravity=None, sizes=[n] * B)
+
+
+def make_workload(name: str, seed: int, nodes: int):
+    if name == "water3d":
+        return make_cloud(nodes or 8000, 25.0, 3, seed, [0, -1, 0]), dict(sigma=1.0, weight=0.01, sample=3)
+    if name == "nbody100":
+        return make_nbody(100, 100, 0.5, 3, seed), dict(sigma=1.5, weight=0.01, sample=3)
+    if name == "large":
+        return make_cloud(nodes or 1_000_000, 30.0, 8, seed, None), dict(sigma=1.0, weight=0.01, sample=3)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def sample_indices(sizes, ns, gen):
+    """Global node indices of the reference's per-graph torch.randperm(n_b)[:ns] (utils/train.py:131,152)."""
+    out, off = [], 0
+    for n in sizes:
+        out.append(torch.randperm(n, generator=gen)[:ns] + off)
+        off += n
+    return torch.stack(out).to(torch.int32)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 6 or not p[0].isdigit():
+                continue
+            sm.append(int(p[0])); mx = int(p[1])
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def oracle_step_fn(data, hp):
+    """The reference's training step (utils/train.py:49-170) on the CPU restatement of the model."""
+    from oracle import fastegnn_oracle as orc
+    cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=2, hidden_nf=H, virtual_channels=data["C"], n_layers=LAYERS,
+                           gravity=data["gravity"])
+    params = {k: v.clone().requires_grad_(True) for k, v in orc.make_params(cfg, 0).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=5e-4, weight_decay=1e-12)
+    gen = torch.Generator().manual_seed(0)
+    ns = min(hp["sample"] * data["C"], min(data["sizes"]))
+    offs = np.concatenate([[0], np.cumsum(data["sizes"])[:-1]])
+
+    def step():
+        opt.zero_grad()
+        x, Z = orc.fastegnn_forward(params, cfg, data["node_feat"], data["loc_0"], data["vel_0"], data["edge_index"],
+                                    data["batch"], data["loc_mean"], data["edge_attr"])
+        loss = torch.nn.functional.mse_loss(x, data["loc_t"])
+        idx = sample_indices(data["sizes"], ns, gen).long()
+        local = [idx[b] - int(offs[b]) for b in range(len(data["sizes"]))]
+        loss = loss + hp["weight"] * orc.mmd_loss(x, Z, data["batch"], hp["sigma"], local)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu(step, warmup, steps):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts)
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="water3d", choices=["water3d", "nbody100", "large"])
+    ap.add_argument("--nodes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-phases", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    data, hp = make_workload(args.workload, seed=rank, nodes=args.nodes)
+    E, N, B, C = int(data["edge_index"].size(1)), int(data["loc_0"].size(0)), data["n_graphs"], data["C"]
+    config = dict(workload=f"{args.workload}: N={N} nodes, E={E} directed edges, B={B} graph(s), C={C}, L={LAYERS}, "
+                           f"H={H}, gravity={data['gravity']}; step = fwd + MSE + {hp['weight']}*MMD + bwd + Adam",
+                  l2="flushed (256 MiB write) before every timed step",
+                  parallelism=f"{world} rank(s), whole graphs per rank, weight-gradient all-reduce per step"
+                  if world > 1 else "1 rank")
+    metric = "layer fwd+bwd edges/sec (full train step: fwd+MSE+MMD+bwd+Adam), Water-3D shape"
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(cores)
+        step = oracle_step_fn(data, hp)
+        t = time_cpu(step, max(1, min(args.warmup, 2)), max(1, min(args.steps, 5)))
+        val = E * LAYERS / t
+        line = dict(impl="reference", metric=metric, value=val, unit="edges/s", n_gpus=args.gpus,
+                    steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)), ms_per_step=t * 1e3,
+                    steps_per_sec=1.0 / t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", config=config,
+                    cpu_baseline=dict(value=val, unit="edges/s", cores=cores, kind="port",
+                                      sample="the full workload, one training step per timed step (oracle/ restates "
+                                             "the reference's torch op chain; the reference itself needs "
+                                             "torch_geometric, absent on this box)"),
+                    e2e=dict(value=val, unit="edges/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from fastegnn_b200 import FastEGNN, mmd_loss
+    from fastegnn_b200 import _lib
+
+    torch.manual_seed(0)
+    model = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=H, virtual_channels=C, device=dev,
+                     n_layers=LAYERS, gravity=data["gravity"])
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-12)
+    params = [p for p in model.parameters()]
+    gen = torch.Generator().manual_seed(0)
+    ns = min(hp["sample"] * C, min(data["sizes"]))
+    keys = ("node_feat", "loc_0", "vel_0", "loc_t", "edge_index", "edge_attr", "batch", "loc_mean")
+    host = {k: data[k].pin_memory() for k in keys}
+    dev_in = {k: host[k].to(dev) for k in keys}
+    idx_host = sample_indices(data["sizes"], ns, gen).pin_memory()
+    idx_dev = idx_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def allreduce_grads():
+        grads = [p.grad for p in params if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
+
+    def train_step(t, idx):
+        opt.zero_grad(set_to_none=True)
+        x, Z = model(node_feat=t["node_feat"], node_loc=t["loc_0"], node_vel=t["vel_0"], edge_index=t["edge_index"],
+                     data_batch=t["batch"], loc_mean=t["loc_mean"], edge_attr=t["edge_attr"])
+        loss = torch.nn.functional.mse_loss(x, t["loc_t"]) + hp["weight"] * mmd_loss(x, Z, idx, hp["sigma"])
+        loss.backward()
+        if world > 1:
+            allreduce_grads()
+        opt.step()
+        return loss
+
+    def e2e_step():
+        t = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        idx = idx_host.to(dev, non_blocking=True)
+        return train_step(t, idx).item()                      # device->host read of the loss
+
+    def timed(fn, steps):
+        """Per-step CUDA events on the launching (current) stream, L2 flushed before each step."""
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs) / steps     # ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        train_step(dev_in, idx_dev)
+        e2e_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.fegnn_launch_count()
+    barrier()
+    ms = timed(lambda: train_step(dev_in, idx_dev), args.steps)
+    barrier()
+    launches = _lib.lib.fegnn_launch_count() - launches0
+    ms_e2e = timed(e2e_step, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ee = torch.tensor([E], device=dev, dtype=torch.float64)
+        dist.all_reduce(ee)
+        ms, ms_e2e, E_all = float(tt[0]), float(tt[1]), float(ee[0])
+    else:
+        E_all = float(E)
+
+    if rank == 0:
+        h2d = sum(host[k].numel() * host[k].element_size() for k in keys) + idx_host.numel() * 4
+        line = dict(metric=metric, value=E_all * LAYERS / (ms * 1e-3), unit="edges/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms, steps_per_sec=1e3 / ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clocks,
+                    e2e=dict(value=E_all * LAYERS / (ms_e2e * 1e-3), unit="edges/s", ms_per_step=ms_e2e,
+                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                    gpu_launches=int(launches))
+        if not args.no_phases:
+            line.update(phase_profile(model, dev_in, dev, data, E, N, B, C, flush))
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(cores)
+            t_cpu = time_cpu(oracle_step_fn(data, hp), 1, 3)
+            line["cpu_baseline"] = dict(value=E * LAYERS / t_cpu, unit="edges/s", cores=cores, kind="port",
+                                        ms_per_step=t_cpu * 1e3,
+                                        sample="the full workload: 1 warm-up + 3 timed training steps of oracle/ "
+                                               "(CPU restatement of the reference's torch op chain)")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def phase_profile(model, t, dev, data, E, N, B, C, flush):
+    """CUDA-event time of every phase of layer 0 (one C-ABI call each), and the roofline of the
+    dominant kernel (edge backward)."""
+    import ctypes as Ct
+    from fastegnn_b200 import _lib as L
+    from fastegnn_b200.layer_fn import LayerPhases
+    from fastegnn_b200.ops import CsrGraph, layer_ptrs, make_dims
+    lib = L.lib
+    st = torch.cuda.current_stream().cuda_stream
+    graph = CsrGraph(t["edge_index"], t["batch"], t["edge_attr"], B)
+    flags = L.F_GRAVITY if data["gravity"] is not None else 0
+    dims = make_dims(N, N, E, B, C, 2, flags, data["gravity"])
+    named = dict(model.named_parameters())
+    ptrs = layer_ptrs(named, "gcl_0")
+    ph = LayerPhases(dims, graph, ptrs, dev)
+    h = torch.nn.functional.linear(t["node_feat"], model.embedding_in.weight, model.embedding_in.bias).detach()
+    x, v, Z = t["loc_0"], t["vel_0"], t["loc_mean"]
+    S = model.virtual_node_feat.detach()[0].T.contiguous().unsqueeze(0).repeat(B, 1, 1).contiguous()
+    xsum = torch.zeros(B, 3, device=dev).index_add_(0, t["batch"], x)
+    e32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+    gviews = {k: torch.zeros_like(p) for k, p in named.items() if k.startswith("gcl_0.")}
+    gr = layer_ptrs(gviews, "gcl_0")
+    pd, pg, pp, ps, pgr = Ct.byref(dims), Ct.byref(graph.c), Ct.byref(ptrs), Ct.byref(ph.saved.c), Ct.byref(gr)
+    x_new, xsum_new, h_new, Z_new, S_new = e32(N, 3), e32(B, 3), e32(N, H), e32(B, 3, C), e32(B, C, H)
+    gZ, gS, gDsum, gUsum = e32(B, 3, C), e32(B, C, H), e32(B, 3, C), e32(B, C, H)
+    gh, gzh1, gm, gu = torch.randn(N, H, device=dev), e32(N, H), e32(N, H), e32(N, C, H)
+    gxn, gAv, gG1, gx, gsv, gsg, gt = torch.randn(N, 3, device=dev), e32(N, H), e32(B, C, H), e32(N, 3), e32(N), e32(N), e32(N, 3)
+    gP, gQ, gxs = e32(N, H), e32(N, H), e32(B, 3)
+    gZn, gSn = torch.randn(B, 3, C, device=dev), torch.randn(B, C, H, device=dev)
+    p = L.ptr
+    calls = [
+        ("graph_prep", lambda: CsrGraph(t["edge_index"], t["batch"], t["edge_attr"], B)),
+        ("graph_pre_fwd", lambda: lib.fegnn_graph_pre_forward(pd, pg, pp, p(Z), p(S), p(xsum), ps, st)),
+        ("node_pre_fwd", lambda: lib.fegnn_node_pre_forward(pd, pp, p(h), ps, st)),
+        ("edge_fwd", lambda: lib.fegnn_edge_forward(pd, pg, pp, p(x), ps, st)),
+        ("virtual_fwd", lambda: lib.fegnn_virtual_forward(pd, pg, pp, p(x), p(v), p(Z), ps, p(x_new), p(xsum_new), st)),
+        ("node_h_fwd", lambda: lib.fegnn_node_h_forward(pd, pg, pp, p(h), ps, p(h_new), st)),
+        ("graph_post_fwd", lambda: lib.fegnn_graph_post_forward(pd, pg, pp, p(Z), p(S), ps, p(Z_new), p(S_new), st)),
+        ("graph_post_bwd", lambda: lib.fegnn_graph_post_backward(pd, pg, pp, pgr, p(S), ps, p(gZn), p(gSn), p(gZ), p(gS),
+                                                                 p(gDsum), p(gUsum), st)),
+        ("node_h_bwd", lambda: lib.fegnn_node_h_backward(pd, pg, pp, pgr, ps, p(gh), p(gzh1), p(gm), p(gu), st)),
+        ("virtual_bwd", lambda: lib.fegnn_virtual_backward(pd, pg, pp, pgr, p(x), p(v), p(Z), ps, p(gxn), None, p(gDsum),
+                                                           p(gUsum), p(gu), p(gAv), p(gG1), p(gx), p(gZ), p(gsv), p(gsg),
+                                                           p(gt), st)),
+        ("edge_bwd", lambda: lib.fegnn_edge_backward(pd, pg, pp, pgr, p(x), ps, p(gm), p(gt), p(gP), p(gQ), p(gx), st)),
+        ("graph_pre_bwd", lambda: lib.fegnn_graph_pre_backward(pd, pg, pp, pgr, p(S), ps, p(gG1), p(gS), p(gZ), p(gxs), st)),
+        ("node_pre_bwd", lambda: lib.fegnn_node_pre_backward(pd, pp, pgr, p(h), p(gP), p(gQ), p(gAv), p(gzh1), p(gsv),
+                                                             p(gsg), p(gh), st)),
+    ]
+    out = {}
+    for name, fn in calls:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        out[name] = round(sum(ts) / len(ts), 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    which = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if "bf16_tflops" in peaks else "fallback 1590"
+    flop = 6 * 2 * H * H * E       # recompute 2 + dgrad 2 + wgrad 2 GEMMs of [E,64]x[64,64]
+    t_s = out["edge_bwd"] * 1e-3
+    ach = flop / t_s / 1e12
+    roof = dict(kernel="edge_bwd_kernel (one launch = all E edges of one layer; timed with its two output memsets)",
+                bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None,
+                peak_source=which,
+                note="fp32 FMA formulation this round: the fp32 pipe's nominal peak is 74 TFLOP/s "
+                     f"(frac of that: {ach / 74.0:.3f}); algorithmic flops = 6 GEMMs x 2*64*64 per edge")
+    return dict(roofline=roof, phases_ms_layer0=out)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,7 @@ _PD, _PG, _PP, _PS = C.POINTER(Dims), C.POINTER(Graph), C.POINTER(LayerPtrs), C.
 SIGNATURES = {
     "fegnn_last_error": (C.c_char_p, []),
     "fegnn_version": (C.c_int, []),
+    "fegnn_launch_count": (C.c_ulonglong, []),
     "fegnn_graph_prep_workspace_bytes": (C.c_size_t, [i32, i32]),
     "fegnn_graph_prep": (C.c_int, [i32, i32, i32, i32] + [vp] * 12 + [vp, C.c_size_t, vp]),
     "fegnn_embed_forward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),

@@ -150,6 +150,7 @@ extern "C" {
 
 const char* fegnn_last_error(void) { return g_err; }
 int fegnn_version(void) { return 100; }
+unsigned long long fegnn_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------ graph prep
 size_t fegnn_graph_prep_workspace_bytes(int32_t N, int32_t E) { return graph_prep_workspace_bytes(N, E); }
@@ -462,7 +463,7 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   CK(cudaMemcpyAsync(w.x[0], x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(w.Z[0], loc_mean, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
   if (B > 0) {
-    broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, w.Sx[0]);
+    broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, w.Sx[0]); ++g_launches;
     CK(cudaGetLastError());
   }
   TRY(fegnn_graph_xsum(d->N, d->B, w.x[0], g->batch, w.xsum[0], stream));
@@ -528,13 +529,13 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     cur ^= 1;
   }
   if (N > 0) {
-    final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, st>>>(d->N, gx_new, gxsum_next, g->batch, g_x0);
+    final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, st>>>(d->N, gx_new, gxsum_next, g->batch, g_x0); ++g_launches;
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(g_loc_mean, gZ_new, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
   TRY(fegnn_embed_backward(d->N, Fin, node_feat, embed_w, s.gh, g_embed_w, g_embed_b, g_node_feat, stream));
   if (B > 0) {
-    reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf);
+    reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf); ++g_launches;
     CK(cudaGetLastError());
   }
   return 0;

@@ -215,8 +215,7 @@ __device__ __forceinline__ void load_tile(float* __restrict__ T, const float* __
   }
 }
 
-struct Launch {
-  static int sm_count();
-};
+// Number of kernels this library has launched (host counter; read through fegnn_launch_count()).
+inline unsigned long long g_launches = 0;
 
 }  // namespace fegnn

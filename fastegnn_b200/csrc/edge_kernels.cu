@@ -402,7 +402,7 @@ cudaError_t launch_edge_fwd(const EdgeArgs& a, int sms, cudaStream_t st) {
   int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
   int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
-  edge_fwd_kernel<<<grid, kThreads, kEdgeFwdSmem, st>>>(a);
+  edge_fwd_kernel<<<grid, kThreads, kEdgeFwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_edge_bwd(const EdgeArgs& a, int sms, cudaStream_t st) {
@@ -415,7 +415,7 @@ cudaError_t launch_edge_bwd(const EdgeArgs& a, int sms, cudaStream_t st) {
   int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
   int grid = ntiles < sms ? ntiles : sms;
-  edge_bwd_kernel<<<grid, kThreads, kEdgeBwdSmem, st>>>(a);
+  edge_bwd_kernel<<<grid, kThreads, kEdgeBwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 

@@ -287,22 +287,22 @@ __global__ void __launch_bounds__(kThreads) graph_pre_bwd_kernel(GraphArgs a) {
 
 cudaError_t launch_graph_pre_fwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_pre_fwd_kernel<<<a.B, kThreads, 0, st>>>(a);
+  graph_pre_fwd_kernel<<<a.B, kThreads, 0, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_post_fwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_post_fwd_kernel<<<a.B, kThreads, 0, st>>>(a);
+  graph_post_fwd_kernel<<<a.B, kThreads, 0, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_post_bwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_post_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a);
+  graph_post_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_pre_bwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_pre_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a);
+  graph_pre_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 

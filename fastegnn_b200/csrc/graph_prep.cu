@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(256) scan_apply(const int* __restrict__ in, in
 static cudaError_t exclusive_scan(const int* in, int n, int* out, int* total, int* sums, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   int nb = (n + kScanChunk - 1) / kScanChunk;
-  scan_block_sums<<<nb, 256, 0, st>>>(in, n, sums);
-  scan_sums<<<1, 1024, 0, st>>>(sums, nb);
-  scan_apply<<<nb, 256, 0, st>>>(in, n, sums, out, total);
+  scan_block_sums<<<nb, 256, 0, st>>>(in, n, sums); ++g_launches;
+  scan_sums<<<1, 1024, 0, st>>>(sums, nb); ++g_launches;
+  scan_apply<<<nb, 256, 0, st>>>(in, n, sums, out, total); ++g_launches;
   return cudaGetLastError();
 }
 
@@ -255,12 +255,12 @@ cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, c
   // counts -> rowptr, gptr, reciprocals
   if ((e = cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(gptr, 0, sizeof(int) * ((size_t)B + 1), st)) != cudaSuccess) return e;
-  if (E > 0) count_rows_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, edge_index, rowptr);
-  if (N > 0) batch_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, data_batch, batch, gptr);
+  if (E > 0) { count_rows_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, edge_index, rowptr); ++g_launches; }
+  if (N > 0) { batch_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, data_batch, batch, gptr); ++g_launches; }
   if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums, st)) != cudaSuccess) return e;
   if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums, st)) != cudaSuccess) return e;
-  if (N > 0) recip_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, rowptr, dinv);
-  if (B > 0) recip_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, gptr, inv_nb);
+  if (N > 0) { recip_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, rowptr, dinv); ++g_launches; }
+  if (B > 0) { recip_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, gptr, inv_nb); ++g_launches; }
   if (E == 0) return cudaGetLastError();
   // radix sort (row, edge id)
   int bits = 1;
@@ -274,18 +274,20 @@ cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, c
     const int shift = 8 * p;
     if (p == 0) radix_hist_kernel<true><<<G, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, G, hist);
     else radix_hist_kernel<false><<<G, kSortThreads, 0, st>>>(E, shift, nullptr, kin, G, hist);
+    ++g_launches;
     if ((e = exclusive_scan(hist, 256 * G, hist, nullptr, sums, st)) != cudaSuccess) return e;
     if (p == 0)
       radix_scatter_kernel<true><<<G, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, nullptr, G, hist, kout, vout);
     else
       radix_scatter_kernel<false><<<G, kSortThreads, 0, st>>>(E, shift, nullptr, kin, vin, G, hist, kout, vout);
+    ++g_launches;
     kin = kout;
     vin = vout;
     kout = (kout == keysA) ? keysB : keysA;
     vout = (vout == valsA) ? valsB : valsA;
   }
   finalize_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, Fe, kin, vin, edge_index + E, edge_attr, perm, row, col,
-                                                    ea_sorted);
+                                                    ea_sorted); ++g_launches;
   return cudaGetLastError();
 }
 

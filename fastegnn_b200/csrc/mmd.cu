@@ -87,14 +87,14 @@ cudaError_t launch_mmd_fwd(int B, int C, int ns, float sigma, const float* x, co
                            float* loss, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
   if (e != cudaSuccess || B == 0) return e;
-  mmd_fwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, loss);
+  mmd_fwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, loss); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_mmd_bwd(int N, int B, int C, int ns, float sigma, const float* x, const float* Z, const int* idx,
                            const float* gloss, float* gx, float* gZ, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)N, st);
   if (e != cudaSuccess || B == 0) return e;
-  mmd_bwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, gloss, gx, gZ);
+  mmd_bwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, gloss, gx, gZ); ++g_launches;
   return cudaGetLastError();
 }
 

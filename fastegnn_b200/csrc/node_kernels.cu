@@ -456,18 +456,18 @@ cudaError_t launch_embed_fwd(int N, int Fin, const float* nf, const float* w, co
                              cudaStream_t st) {
   if (N == 0) return cudaSuccess;
   size_t total = (size_t)N * kH;
-  embed_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, Fin, nf, w, b, h);
+  embed_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, Fin, nf, w, b, h); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_embed_bwd(int N, int Fin, const float* nf, const float* w, const float* gh, float* gw, float* gb,
                              float* gnf, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
-  embed_bwd_kernel<<<(N + kEmbedChunk - 1) / kEmbedChunk, kThreads, 0, st>>>(N, Fin, nf, w, gh, gw, gb, gnf);
+  embed_bwd_kernel<<<(N + kEmbedChunk - 1) / kEmbedChunk, kThreads, 0, st>>>(N, Fin, nf, w, gh, gw, gb, gnf); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_xsum(int N, const float* x, const int* batch, float* xsum, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
-  graph_xsum_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, x, batch, xsum);
+  graph_xsum_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, x, batch, xsum); ++g_launches;
   return cudaGetLastError();
 }
 
@@ -485,28 +485,28 @@ cudaError_t launch_node_pre_fwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   FEGNN_SET_SMEM(node_pre_fwd_kernel, kNodePreFwdSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_pre_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreFwdSmem, st>>>(a);
+  node_pre_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreFwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_pre_bwd_kernel, kNodePreBwdSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_pre_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreBwdSmem, st>>>(a);
+  node_pre_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreBwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_h_fwd_kernel, kNodeHSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_h_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a);
+  node_h_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_h_bwd_kernel, kNodeHSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_h_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a);
+  node_h_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 

@@ -565,7 +565,7 @@ cudaError_t launch_virtual_fwd(const VirtArgs& a, int sms, cudaStream_t st) {
   int ntiles = (a.N + TN - 1) / TN;
   if (ntiles == 0) return cudaSuccess;
   int grid = ntiles < sms ? ntiles : sms;
-  virtual_fwd_kernel<<<grid, kThreads, kVirtFwdSmem, st>>>(a);
+  virtual_fwd_kernel<<<grid, kThreads, kVirtFwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_virtual_bwd(const VirtArgs& a, int sms, cudaStream_t st) {
@@ -579,7 +579,7 @@ cudaError_t launch_virtual_bwd(const VirtArgs& a, int sms, cudaStream_t st) {
   int ntiles = (a.N + TN - 1) / TN;
   if (ntiles == 0) return cudaSuccess;
   int grid = ntiles < sms ? ntiles : sms;
-  virtual_bwd_kernel<<<grid, kThreads, kVirtBwdSmem, st>>>(a);
+  virtual_bwd_kernel<<<grid, kThreads, kVirtBwdSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 

@@ -114,6 +114,8 @@ typedef struct fegnn_layer_saved {
 
 const char* fegnn_last_error(void);
 int fegnn_version(void);
+/* kernels launched by this library so far in this process (host-side counter; bench.py reports it) */
+unsigned long long fegnn_launch_count(void);
 
 /* ------------------------------------------------------------------ graph prep
  * Replaces, for the whole stack, what the reference redoes in every layer with
