@@ -407,6 +407,18 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
                                                              p(gsg), p(gh), st)),
     ]
     out = {}
+
+    def with_mode(phase, mode, fn):
+        def run():
+            old = L.get_mode(phase)
+            L.set_mode(phase, mode)
+            try:
+                return fn()
+            finally:
+                L.set_mode(phase, old)
+        return run
+    edge_fwd_fn = dict(calls)["edge_fwd"]
+    calls += [(f"edge_fwd[mode={m}]", with_mode("edge_forward", m, edge_fwd_fn)) for m in (0, 1, 3)]
     for name, fn in calls:
         for _ in range(3):
             fn()

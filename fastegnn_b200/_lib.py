@@ -92,6 +92,8 @@ SIGNATURES = {
     "fegnn_last_error": (C.c_char_p, []),
     "fegnn_version": (C.c_int, []),
     "fegnn_launch_count": (C.c_ulonglong, []),
+    "fegnn_set_mode": (C.c_int, [C.c_char_p, C.c_int]),
+    "fegnn_get_mode": (C.c_int, [C.c_char_p]),
     "fegnn_graph_prep_workspace_bytes": (C.c_size_t, [i32, i32]),
     "fegnn_graph_prep": (C.c_int, [i32, i32, i32, i32] + [vp] * 12 + [vp, C.c_size_t, vp]),
     "fegnn_embed_forward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),
@@ -125,10 +127,25 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+def set_mode(phase: str, mode: int) -> None:
+    """0 = fp32 FMA kernels, 1 = tcgen05 TF32, 3 = tcgen05 3xTF32 (see fegnn_set_mode in fegnn.h)."""
+    check(lib.fegnn_set_mode(phase.encode(), int(mode)), "fegnn_set_mode")
+
+
+def get_mode(phase: str) -> int:
+    return int(lib.fegnn_get_mode(phase.encode()))
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib.fegnn_last_error().decode("utf-8", "replace")
         raise FegnnError(f"{what or 'fegnn'} failed with code {rc}: {msg}")
+
+
+for _phase in ("edge_forward",):
+    _env = os.environ.get("FEGNN_MODE_" + _phase.upper())
+    if _env is not None:
+        set_mode(_phase, int(_env))
 
 
 def ptr(t):

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "edge_kernels.cu"
+#include "edge_tc.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "mmd.cu"
@@ -40,6 +41,9 @@ int fail(int code, const char* fmt, ...) {
     int rc__ = (expr);       \
     if (rc__ != 0) return rc__; \
   } while (0)
+
+// 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32, 3 = tcgen05 3xTF32 (fp32-grade)
+int g_edge_fwd_mode = 3;
 
 int sm_count() {
   static int sms = 0;
@@ -151,6 +155,19 @@ extern "C" {
 const char* fegnn_last_error(void) { return g_err; }
 int fegnn_version(void) { return 100; }
 unsigned long long fegnn_launch_count(void) { return g_launches; }
+int fegnn_set_mode(const char* phase, int mode) {
+  if (phase == nullptr) return fail(FEGNN_EINVAL, "phase is null");
+  if (strcmp(phase, "edge_forward") == 0) {
+    if (mode != 0 && mode != 1 && mode != 3) return fail(FEGNN_EINVAL, "edge_forward mode must be 0, 1 or 3");
+    g_edge_fwd_mode = mode;
+    return 0;
+  }
+  return fail(FEGNN_EINVAL, "unknown phase '%s'", phase);
+}
+int fegnn_get_mode(const char* phase) {
+  if (phase != nullptr && strcmp(phase, "edge_forward") == 0) return g_edge_fwd_mode;
+  return -1;
+}
 
 // ------------------------------------------------------------------ graph prep
 size_t fegnn_graph_prep_workspace_bytes(int32_t N, int32_t E) { return graph_prep_workspace_bytes(N, E); }
@@ -221,7 +238,10 @@ int fegnn_edge_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_la
   a.msum = sv->msum; a.tsum = sv->tsum;
   CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
   CK(cudaMemsetAsync(sv->tsum, 0, sizeof(float) * 3 * (size_t)d->N, S(stream)));
-  CK(launch_edge_fwd(a, sm_count(), S(stream)));
+  const int mode = d->Fe <= kTcMaxFe ? g_edge_fwd_mode : 0;
+  if (mode == 3) CK(launch_edge_fwd_tc<3>(a, sm_count(), S(stream)));
+  else if (mode == 1) CK(launch_edge_fwd_tc<1>(a, sm_count(), S(stream)));
+  else CK(launch_edge_fwd(a, sm_count(), S(stream)));
   return 0;
 }
 

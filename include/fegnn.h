@@ -116,6 +116,10 @@ const char* fegnn_last_error(void);
 int fegnn_version(void);
 /* kernels launched by this library so far in this process (host-side counter; bench.py reports it) */
 unsigned long long fegnn_launch_count(void);
+/* Arithmetic mode of a phase: 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32 tiles, 3 = tcgen05
+ * error-compensated 3xTF32 tiles (fp32-grade).  phase: "edge_forward".  Process-wide. */
+int fegnn_set_mode(const char* phase, int mode);
+int fegnn_get_mode(const char* phase);
 
 /* ------------------------------------------------------------------ graph prep
  * Replaces, for the whole stack, what the reference redoes in every layer with

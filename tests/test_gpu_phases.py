@@ -202,3 +202,39 @@ def test_phases(name, layer):
             fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
     bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
     assert not bad, bad
+
+
+# tolerance of the tensor-core modes of the fused edge forward (relative to each tensor's max):
+#   3 = 3xTF32 error-compensated tiles -> fp32-grade;  1 = single-pass TF32 (10-bit mantissa operands)
+EDGE_MODE_TOL = {0: 3e-5, 3: 3e-5, 1: 4e-3}
+
+
+@pytest.mark.parametrize("mode", [0, 3, 1])
+@pytest.mark.parametrize("name", list(PHASE_CASES))
+def test_edge_forward_modes(name, mode):
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"], cfg.gravity)
+    ptrs = s["layer_ptrs"](s["gparams"], "gcl_0")
+    sv = s["SavedBlock"](dims, dev)
+    S_ = sm.saved[0]
+    sv.view("P", (N, H)).copy_(_g(S_["npre"]["P"], dev))
+    sv.view("Q", (N, H)).copy_(_g(S_["npre"]["Q"], dev))
+    x = _g(S_["x"], dev)
+    old = L.get_mode("edge_forward")
+    try:
+        L.set_mode("edge_forward", mode)
+        L.check(lib.fegnn_edge_forward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), L.ptr(x), C.byref(sv.c), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("edge_forward", old)
+    e_m = rel_err(sv.view("msum", (N, H)).cpu(), S_["e"]["msum"])
+    e_t = rel_err(sv.view("tsum", (N, 3)).cpu(), S_["e"]["tsum"])
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/edge_fwd_mode{mode}_{name}.txt", "w") as fh:
+        fh.write(f"mode {mode} {name}: msum {e_m:.3e} tsum {e_t:.3e}\n")
+    assert e_m <= EDGE_MODE_TOL[mode] and e_t <= EDGE_MODE_TOL[mode], (e_m, e_t)
