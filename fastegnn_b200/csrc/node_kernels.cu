@@ -21,7 +21,7 @@ __global__ void embed_fwd_kernel(int N, int Fin, const float* __restrict__ nf, c
   h[idx] = acc;
 }
 
-constexpr int kEmbedChunk = 1024;
+constexpr int kEmbedChunk = 128;
 __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, const float* __restrict__ nf,
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ gh, float* __restrict__ gw,
@@ -83,65 +83,66 @@ struct NodePreArgs {
 };
 
 constexpr int kNodePreBlocks = 6;   // P, Q, Av, Uh, vel, grav
-constexpr size_t kNodePreFwdSmem = (kNodePreBlocks * kWFloats + kTileFloats + 4 * kH) * sizeof(float);
+constexpr size_t kNodePreFwdSmem = (kWFloats + kTileFloats + 2 * kH) * sizeof(float);
 
-__global__ void __launch_bounds__(kThreads, 1) node_pre_fwd_kernel(NodePreArgs a) {
+// Work item = (node tile, weight block).  The grid is a multiple of the number of active blocks, so a
+// CTA always meets the same block and stages its 64x64 weight once; small N still fills the GPU
+// (N = 8000 -> 63 tiles x 6 blocks = 378 CTAs instead of 63).
+__device__ __forceinline__ int node_pre_block_id(int k, bool last, bool grav) {
+  // k-th ACTIVE block -> block id (0 P, 1 Q, 2 Av, 3 Uh, 4 vel, 5 grav)
+  if (last && k >= 3) ++k;
+  (void)grav;
+  return k;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) node_pre_fwd_kernel(NodePreArgs a, int nactive) {
   extern __shared__ __align__(16) float smem[];
-  float* Wb = smem;                               // 6 resident weight tiles
-  float* T0 = Wb + kNodePreBlocks * kWFloats;     // h tile
-  float* vec = T0 + kTileFloats;                  // [0]=vel_b0 [1]=vel_w2 [2]=grav_b0 [3]=grav_w2
+  float* Ws = smem;
+  float* T0 = Ws + kWFloats;
+  float* vec = T0 + kTileFloats;     // head blocks: [0] first-layer bias, [1] output weight
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
-  stage_weight(Wb + 0 * kWFloats, a.edge_w0, a.ld1, 0, 1);
-  stage_weight(Wb + 1 * kWFloats, a.edge_w0, a.ld1, kH, 1);
-  stage_weight(Wb + 2 * kWFloats, a.edgev_w0, a.ldv, 0, 1);
-  if (!last) stage_weight(Wb + 3 * kWFloats, a.node_w0, a.ldn, 0, 1);
-  stage_weight(Wb + 4 * kWFloats, a.vel_w0, kH, 0, 1);
-  stage_vec(vec + 0 * kH, a.vel_b0, kH);
-  stage_vec(vec + 1 * kH, a.vel_w2, kH);
-  if (grav) {
-    stage_weight(Wb + 5 * kWFloats, a.grav_w0, kH, 0, 1);
-    stage_vec(vec + 2 * kH, a.grav_b0, kH);
-    stage_vec(vec + 3 * kH, a.grav_w2, kH);
+  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav);
+  const int cta = blockIdx.x / nactive, nctas = gridDim.x / nactive;
+  const float* wsrc = blk <= 1 ? a.edge_w0 : blk == 2 ? a.edgev_w0 : blk == 3 ? a.node_w0 : blk == 4 ? a.vel_w0 : a.grav_w0;
+  const int ld = blk <= 1 ? a.ld1 : blk == 2 ? a.ldv : blk == 3 ? a.ldn : kH;
+  stage_weight(Ws, wsrc, ld, blk == 1 ? kH : 0, 1);
+  if (blk >= 4) {
+    stage_vec(vec, blk == 4 ? a.vel_b0 : a.grav_b0, kH);
+    stage_vec(vec + kH, blk == 4 ? a.vel_w2 : a.grav_w2, kH);
   }
   const int ntiles = (a.N + kTM - 1) / kTM;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = cta; tile < ntiles; tile += nctas) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
     load_tile(T0, a.h + (size_t)i0 * kH, kH, nvalid);
     __syncthreads();
-#pragma unroll 1
-    for (int blk = 0; blk < kNodePreBlocks; ++blk) {
-      if (blk == 3 && last) continue;
-      if (blk == 5 && !grav) continue;
-      float acc[kRT][4];
-      zero_acc(acc);
-      gemm_nt(acc, T0, Wb + blk * kWFloats, ty, tx);
-      if (blk < 4) {
-        const float* bias = blk == 0 ? a.edge_b0 : blk == 2 ? a.edgev_b0 : blk == 3 ? a.node_b0 : nullptr;
-        float* out = blk == 0 ? a.P : blk == 1 ? a.Q : blk == 2 ? a.Av : a.Uh;
-        float4 bb = make_float4(0, 0, 0, 0);
-        if (bias != nullptr) bb = *reinterpret_cast<const float4*>(bias + tx * 4);
+    float acc[kRT][4];
+    zero_acc(acc);
+    gemm_nt(acc, T0, Ws, ty, tx);
+    if (blk < 4) {
+      const float* bias = blk == 0 ? a.edge_b0 : blk == 2 ? a.edgev_b0 : blk == 3 ? a.node_b0 : nullptr;
+      float* out = blk == 0 ? a.P : blk == 1 ? a.Q : blk == 2 ? a.Av : a.Uh;
+      float4 bb = make_float4(0, 0, 0, 0);
+      if (bias != nullptr) bb = *reinterpret_cast<const float4*>(bias + tx * 4);
 #pragma unroll
-        for (int i = 0; i < kRT; ++i) {
-          const int r = ty * kRT + i;
-          if (r < nvalid)
-            *reinterpret_cast<float4*>(out + (size_t)(i0 + r) * kH + tx * 4) =
-                make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
-        }
-      } else {
-        const float* bvec = vec + (blk == 4 ? 0 : 2) * kH;
-        const float4 bb = *reinterpret_cast<const float4*>(bvec + tx * 4);
-        const float4 w = *reinterpret_cast<const float4*>(bvec + kH + tx * 4);
-        const float b2 = blk == 4 ? a.vel_b2[0] : a.grav_b2[0];
-        float* out = blk == 4 ? a.sv : a.sg;
+      for (int i = 0; i < kRT; ++i) {
+        const int r = ty * kRT + i;
+        if (r < nvalid)
+          *reinterpret_cast<float4*>(out + (size_t)(i0 + r) * kH + tx * 4) =
+              make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+      }
+    } else {
+      const float4 bb = *reinterpret_cast<const float4*>(vec + tx * 4);
+      const float4 w = *reinterpret_cast<const float4*>(vec + kH + tx * 4);
+      const float b2 = blk == 4 ? a.vel_b2[0] : a.grav_b2[0];
+      float* out = blk == 4 ? a.sv : a.sg;
 #pragma unroll
-        for (int i = 0; i < kRT; ++i) {
-          const int r = ty * kRT + i;
-          float s = rowsum16(silu_f(acc[i][0] + bb.x) * w.x + silu_f(acc[i][1] + bb.y) * w.y +
-                             silu_f(acc[i][2] + bb.z) * w.z + silu_f(acc[i][3] + bb.w) * w.w);
-          if (tx == 0 && r < nvalid) out[i0 + r] = s + b2;
-        }
+      for (int i = 0; i < kRT; ++i) {
+        const int r = ty * kRT + i;
+        float s = rowsum16(silu_f(acc[i][0] + bb.x) * w.x + silu_f(acc[i][1] + bb.y) * w.y +
+                           silu_f(acc[i][2] + bb.z) * w.z + silu_f(acc[i][3] + bb.w) * w.w);
+        if (tx == 0 && r < nvalid) out[i0 + r] = s + b2;
       }
     }
   }
@@ -177,92 +178,81 @@ __device__ __forceinline__ void bias_flush(const float (&bs)[4], float* __restri
 
 constexpr size_t kNodePreBwdSmem = (kWFloats + 2 * kTileFloats + 2 * kH) * sizeof(float);
 
-// gh (in: dL/dh' of the residual, out: dL/dh) += sum over blocks G_blk W_blk ; dW_blk += G_blk^T h
-__global__ void __launch_bounds__(kThreads, 1) node_pre_bwd_kernel(NodePreArgs a) {
+// gh (in: dL/dh' of the residual, out: dL/dh) += G_blk W_blk ; dW_blk += G_blk^T h.
+// Work item = (node tile, block) as in the forward; gh is accumulated with red.global.add.v4.f32.
+__global__ void __launch_bounds__(kThreads, 2) node_pre_bwd_kernel(NodePreArgs a, int nactive) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
   float* Th = Ws + kWFloats;
   float* TG = Th + kTileFloats;
   float* vec = TG + kTileFloats;   // [0] = first-layer bias of a head, [1] = its output weight
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const bool grav = a.flags & FEGNN_F_GRAVITY;
+  const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.gUh == nullptr;
+  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav);
+  const int cta = blockIdx.x / nactive, nctas = gridDim.x / nactive;
   const int ntiles = (a.N + kTM - 1) / kTM;
-#pragma unroll 1
-  for (int blk = 0; blk < kNodePreBlocks; ++blk) {
-    const float* G = blk == 0 ? a.gP : blk == 1 ? a.gQ : blk == 2 ? a.gAv : blk == 3 ? a.gUh : nullptr;
-    if (blk == 3 && a.gUh == nullptr) continue;
-    if (blk == 5 && !grav) continue;
-    const bool head = blk >= 4;
-    const float* wsrc = blk <= 1 ? a.edge_w0 : blk == 2 ? a.edgev_w0 : blk == 3 ? a.node_w0
-                        : blk == 4 ? a.vel_w0 : a.grav_w0;
-    const int ld = blk <= 1 ? a.ld1 : blk == 2 ? a.ldv : blk == 3 ? a.ldn : kH;
-    const int off = blk == 1 ? kH : 0;
-    float* gw = blk <= 1 ? a.g_edge_w0 : blk == 2 ? a.g_edgev_w0 : blk == 3 ? a.g_node_w0
-                : blk == 4 ? a.g_vel_w0 : a.g_grav_w0;
-    float* gb = blk == 0 ? a.g_edge_b0 : blk == 2 ? a.g_edgev_b0 : blk == 3 ? a.g_node_b0
-                : blk == 4 ? a.g_vel_b0 : blk == 5 ? a.g_grav_b0 : nullptr;
-    const float* gs = blk == 4 ? a.gsv : a.gsg;
+  const float* G = blk == 0 ? a.gP : blk == 1 ? a.gQ : blk == 2 ? a.gAv : blk == 3 ? a.gUh : nullptr;
+  const bool head = blk >= 4;
+  const float* wsrc = blk <= 1 ? a.edge_w0 : blk == 2 ? a.edgev_w0 : blk == 3 ? a.node_w0 : blk == 4 ? a.vel_w0 : a.grav_w0;
+  const int ld = blk <= 1 ? a.ld1 : blk == 2 ? a.ldv : blk == 3 ? a.ldn : kH;
+  const int off = blk == 1 ? kH : 0;
+  float* gw = blk <= 1 ? a.g_edge_w0 : blk == 2 ? a.g_edgev_w0 : blk == 3 ? a.g_node_w0 : blk == 4 ? a.g_vel_w0 : a.g_grav_w0;
+  float* gb = blk == 0 ? a.g_edge_b0 : blk == 2 ? a.g_edgev_b0 : blk == 3 ? a.g_node_b0
+              : blk == 4 ? a.g_vel_b0 : blk == 5 ? a.g_grav_b0 : nullptr;
+  const float* gs = blk == 4 ? a.gsv : a.gsg;
+  stage_weight(Ws, wsrc, ld, off, 1);
+  if (head) {
+    stage_vec(vec, blk == 4 ? a.vel_b0 : a.grav_b0, kH);
+    stage_vec(vec + kH, blk == 4 ? a.vel_w2 : a.grav_w2, kH);
+  }
+  float wg[4][4], bs[4] = {0, 0, 0, 0}, cw2[4] = {0, 0, 0, 0};
+  float cb2 = 0.f;
+  zero_wg(wg);
+  for (int tile = cta; tile < ntiles; tile += nctas) {
+    const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
-    stage_weight(Ws, wsrc, ld, off, 1);
+    load_tile(Th, a.h + (size_t)i0 * kH, kH, nvalid);
+    if (!head) load_tile(TG, G + (size_t)i0 * kH, kH, nvalid);
+    __syncthreads();
+    float acc[kRT][4];
     if (head) {
-      stage_vec(vec, blk == 4 ? a.vel_b0 : a.grav_b0, kH);
-      stage_vec(vec + kH, blk == 4 ? a.vel_w2 : a.grav_w2, kH);
-    }
-    float wg[4][4], bs[4] = {0, 0, 0, 0}, cw2[4] = {0, 0, 0, 0};
-    float cb2 = 0.f;
-    zero_wg(wg);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
-      __syncthreads();
-      load_tile(Th, a.h + (size_t)i0 * kH, kH, nvalid);
-      if (!head) load_tile(TG, G + (size_t)i0 * kH, kH, nvalid);
-      __syncthreads();
-      float acc[kRT][4];
-      if (head) {
-        // recompute z = W h + b ; G = gs_i * w2 * silu'(z)
-        zero_acc(acc);
-        gemm_nt(acc, Th, Ws, ty, tx);
-        const float4 bb = *reinterpret_cast<const float4*>(vec + tx * 4);
-        const float4 w2 = *reinterpret_cast<const float4*>(vec + kH + tx * 4);
-#pragma unroll
-        for (int i = 0; i < kRT; ++i) {
-          const int r = ty * kRT + i;
-          const float g = r < nvalid ? gs[i0 + r] : 0.f;
-          float av[4], dv[4];
-          silu_grad_f(acc[i][0] + bb.x, av[0], dv[0]); silu_grad_f(acc[i][1] + bb.y, av[1], dv[1]);
-          silu_grad_f(acc[i][2] + bb.z, av[2], dv[2]); silu_grad_f(acc[i][3] + bb.w, av[3], dv[3]);
-          *reinterpret_cast<float4*>(TG + r * kH + tx * 4) =
-              make_float4(g * w2.x * dv[0], g * w2.y * dv[1], g * w2.z * dv[2], g * w2.w * dv[3]);
-          cw2[0] = fmaf(g, av[0], cw2[0]); cw2[1] = fmaf(g, av[1], cw2[1]);
-          cw2[2] = fmaf(g, av[2], cw2[2]); cw2[3] = fmaf(g, av[3], cw2[3]);
-          if (tx == 0) cb2 += g;
-        }
-        __syncthreads();
-      }
+      // recompute z = W h + b ; G = gs_i * w2 * silu'(z)
+      zero_acc(acc);
+      gemm_nt(acc, Th, Ws, ty, tx);
+      const float4 bb = *reinterpret_cast<const float4*>(vec + tx * 4);
+      const float4 w2 = *reinterpret_cast<const float4*>(vec + kH + tx * 4);
 #pragma unroll
       for (int i = 0; i < kRT; ++i) {
         const int r = ty * kRT + i;
-        float4 g0 = make_float4(0, 0, 0, 0);
-        if (r < nvalid) g0 = *reinterpret_cast<const float4*>(a.gh + (size_t)(i0 + r) * kH + tx * 4);
-        acc[i][0] = g0.x; acc[i][1] = g0.y; acc[i][2] = g0.z; acc[i][3] = g0.w;
+        const float g = r < nvalid ? gs[i0 + r] : 0.f;
+        float av[4], dv[4];
+        silu_grad_f(acc[i][0] + bb.x, av[0], dv[0]); silu_grad_f(acc[i][1] + bb.y, av[1], dv[1]);
+        silu_grad_f(acc[i][2] + bb.z, av[2], dv[2]); silu_grad_f(acc[i][3] + bb.w, av[3], dv[3]);
+        *reinterpret_cast<float4*>(TG + r * kH + tx * 4) =
+            make_float4(g * w2.x * dv[0], g * w2.y * dv[1], g * w2.z * dv[2], g * w2.w * dv[3]);
+        cw2[0] = fmaf(g, av[0], cw2[0]); cw2[1] = fmaf(g, av[1], cw2[1]);
+        cw2[2] = fmaf(g, av[2], cw2[2]); cw2[3] = fmaf(g, av[3], cw2[3]);
+        if (tx == 0) cb2 += g;
       }
-      gemm_nn(acc, TG, Ws, ty, tx);
+      __syncthreads();
+    }
+    zero_acc(acc);
+    gemm_nn(acc, TG, Ws, ty, tx);
 #pragma unroll
-      for (int i = 0; i < kRT; ++i) {
-        const int r = ty * kRT + i;
-        if (r < nvalid)
-          *reinterpret_cast<float4*>(a.gh + (size_t)(i0 + r) * kH + tx * 4) =
-              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      }
-      wgrad_acc_bias(wg, bs, TG, Th, kTM);
+    for (int i = 0; i < kRT; ++i) {
+      const int r = ty * kRT + i;
+      if (r < nvalid)
+        atomicAdd(reinterpret_cast<float4*>(a.gh + (size_t)(i0 + r) * kH + tx * 4),
+                  make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
-    wgrad_flush(wg, gw, ld, off, 1);
-    bias_flush(bs, gb);
-    if (head) {
-      colsum_flush(cw2, blk == 4 ? a.g_vel_w2 : a.g_grav_w2, 1, tx);
-      float* gb2 = blk == 4 ? a.g_vel_b2 : a.g_grav_b2;
-      if (tx == 0 && gb2 != nullptr) atomicAdd(gb2, cb2);
-    }
+    wgrad_acc_bias(wg, bs, TG, Th, kTM);
+  }
+  wgrad_flush(wg, gw, ld, off, 1);
+  bias_flush(bs, gb);
+  if (head) {
+    colsum_flush(cw2, blk == 4 ? a.g_vel_w2 : a.g_grav_w2, 1, tx);
+    float* gb2 = blk == 4 ? a.g_vel_b2 : a.g_grav_b2;
+    if (tx == 0 && gb2 != nullptr) atomicAdd(gb2, cb2);
   }
 }
 
@@ -481,18 +471,28 @@ cudaError_t launch_graph_xsum(int N, const float* x, const int* batch, float* xs
     }                                                                                                        \
   } while (0)
 
+static inline int node_pre_grid(int ntiles, int nactive, int sms) {
+  int per = (2 * sms) / nactive;            // CTAs per block id at 2 CTAs/SM
+  if (per < 1) per = 1;
+  if (per > ntiles) per = ntiles;
+  return per * nactive;
+}
 cudaError_t launch_node_pre_fwd(const NodePreArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_pre_fwd_kernel, kNodePreFwdSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_pre_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreFwdSmem, st>>>(a); ++g_launches;
+  const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
+  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - (grav ? 0 : 0);
+  node_pre_fwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreFwdSmem, st>>>(a, nactive); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_pre_bwd_kernel, kNodePreBwdSmem);
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_pre_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodePreBwdSmem, st>>>(a); ++g_launches;
+  const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.gUh == nullptr;
+  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0);
+  node_pre_bwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreBwdSmem, st>>>(a, nactive); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {

@@ -62,14 +62,18 @@ class LayerPhases:
         return h_new, x_new, Z_new, S_new, xsum_new
 
     # ---- backward
-    def backward(self, grads: L.LayerPtrs, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks=None):
-        """gh_new is consumed in place (becomes dL/dh).  Returns (gh, gx, gZ, gS, gxsum)."""
+    def backward(self, grads: L.LayerPtrs, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks=None,
+                 graph_grads: Optional[L.LayerPtrs] = None):
+        """gh_new is consumed in place (becomes dL/dh).  Returns (gh, gx, gZ, gS, gxsum).
+        graph_grads: weight-gradient table for the per-graph phases (replicated when partitioned, so
+        only one rank passes real pointers); defaults to `grads`."""
         d, g, p, sv, st = self.d, self.g, self.p, self.saved, _stream()
         N, Nl, B, Cc = d.N, d.Nl, d.B, d.C
         pd, pg, pp, ps, pgr = self.pd, C.byref(g.c), C.byref(p), C.byref(sv.c), C.byref(grads)
+        pgg = pgr if graph_grads is None else C.byref(graph_grads)
         gZ, gS = self._e(B, 3, Cc), self._e(B, Cc, L.H)
         gDsum, gUsum = self._e(B, 3, Cc), self._e(B, Cc, L.H)
-        L.check(lib.fegnn_graph_post_backward(pd, pg, pp, pgr, L.ptr(S), ps, L.ptr(gZ_new), L.ptr(gS_new), L.ptr(gZ),
+        L.check(lib.fegnn_graph_post_backward(pd, pg, pp, pgg, L.ptr(S), ps, L.ptr(gZ_new), L.ptr(gS_new), L.ptr(gZ),
                                               L.ptr(gS), L.ptr(gDsum), L.ptr(gUsum), st), "graph_post_backward")
         gzh1 = gm = gu = None
         if not self.last:
@@ -78,17 +82,20 @@ class LayerPhases:
                                               st), "node_h_backward")
         gAv, gG1, gx = self._e(N, L.H), self._e(B, Cc, L.H), self._e(Nl, 3)
         gsv, gsg, gt = self._e(N), self._e(N), self._e(N, 3)
+        # partitioned: the virtual phase adds only this rank's share of dZ -> keep it apart until it is all-reduced
+        gZ_part = gZ if hooks is None else torch.zeros(B, 3, Cc, device=self.dev, dtype=torch.float32)
         L.check(lib.fegnn_virtual_backward(pd, pg, pp, pgr, L.ptr(x), L.ptr(v), L.ptr(Z), ps, L.ptr(gx_new),
                                            L.ptr(gxsum_next), L.ptr(gDsum), None if self.last else L.ptr(gUsum),
-                                           L.ptr(gu), L.ptr(gAv), L.ptr(gG1), L.ptr(gx), L.ptr(gZ), L.ptr(gsv),
+                                           L.ptr(gu), L.ptr(gAv), L.ptr(gG1), L.ptr(gx), L.ptr(gZ_part), L.ptr(gsv),
                                            L.ptr(gsg), L.ptr(gt), st), "virtual_backward")
         gP, gQ = self._e(N, L.H), self._e(Nl, L.H)
         L.check(lib.fegnn_edge_backward(pd, pg, pp, pgr, L.ptr(x), ps, L.ptr(gm), L.ptr(gt), L.ptr(gP), L.ptr(gQ),
                                         L.ptr(gx), st), "edge_backward")
         if hooks is not None:
-            hooks.after_edge_backward(self, gQ, gx, gG1, gZ)   # reverse halo (sum) + all-reduce of gG1 / gZ partials
+            hooks.after_edge_backward(self, gQ, gx, gG1, gZ_part)   # reverse halo (sum) + all-reduce of dG1 / dZ shares
+            gZ.add_(gZ_part)
         gxsum = self._e(B, 3)
-        L.check(lib.fegnn_graph_pre_backward(pd, pg, pp, pgr, L.ptr(S), ps, L.ptr(gG1), L.ptr(gS), L.ptr(gZ),
+        L.check(lib.fegnn_graph_pre_backward(pd, pg, pp, pgg, L.ptr(S), ps, L.ptr(gG1), L.ptr(gS), L.ptr(gZ),
                                              L.ptr(gxsum), st), "graph_pre_backward")
         L.check(lib.fegnn_node_pre_backward(pd, pp, pgr, L.ptr(h), L.ptr(gP), L.ptr(gQ), L.ptr(gAv), L.ptr(gzh1),
                                             L.ptr(gsv), L.ptr(gsg), L.ptr(gh_new), st), "node_pre_backward")

@@ -1,0 +1,107 @@
+"""Multi-GPU parity check of the spatially partitioned path (run under torchrun, one rank per GPU):
+the slab-partitioned forward/backward must reproduce the single-GPU result of the same module on the
+same graph -- owned rows of x', replicated Z', input gradients and (after the all-reduce) every weight
+gradient.  Launched by tests/test_gpu_partitioned.py; also usable by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from bench import make_cloud
+    from fastegnn_b200 import FastEGNN
+    from fastegnn_b200.partitioned import PartitionedFastEGNN, SlabPlan
+    from oracle import fastegnn_oracle as orc
+
+    C, n = int(os.environ.get("CHECK_C", "3")), int(os.environ.get("CHECK_N", "3000"))
+    grav = [0, -1, 0] if C == 3 else None
+    data = make_cloud(n, 14.0, C, seed=5, gravity=grav)
+    g = torch.Generator().manual_seed(1)
+    data["loc_mean"] = data["loc_mean"] + 0.01 * torch.randn(data["loc_mean"].shape, generator=g)
+    wx = torch.randn(n, 3, generator=g)
+    wz = torch.randn(1, 3, C, generator=g)
+    torch.manual_seed(3)
+    model = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=64, virtual_channels=C, device=dev,
+                     n_layers=3, gravity=grav)
+    sd = model.state_dict()
+    orc.rescale_coord_heads(sd, 300.0)        # make the coordinate path visible (default init has gain 1e-3)
+    model.load_state_dict(sd)
+
+    # ---- single-GPU result of the same module (every rank computes it on its own GPU)
+    t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    x0 = t["loc_0"].clone().requires_grad_(True)
+    lm = t["loc_mean"].clone().requires_grad_(True)
+    xr, Zr = model(node_feat=t["node_feat"], node_loc=x0, node_vel=t["vel_0"], edge_index=t["edge_index"],
+                   data_batch=t["batch"], loc_mean=lm, edge_attr=t["edge_attr"])
+    ((xr * wx.to(dev)).sum() + (Zr * wz.to(dev)).sum()).backward()
+    ref_grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()}
+    ref_gx0, ref_glm = x0.grad.clone(), lm.grad.clone()
+    model.zero_grad(set_to_none=True)
+
+    # ---- partitioned
+    plan = SlabPlan(data["loc_0"].numpy(), data["edge_index"].numpy(), world)
+    loc = plan.localize(rank, dict(node_feat=data["node_feat"].numpy(), loc_0=data["loc_0"].numpy(),
+                                   vel_0=data["vel_0"].numpy(), wx=wx.numpy()),
+                        dict(edge_attr=data["edge_attr"].numpy()))
+    lt = {k: torch.from_numpy(v).to(dev) for k, v in loc.items()}
+    runner = PartitionedFastEGNN(model, plan, rank, dev)
+    N = runner.comm.N
+    xl = lt["loc_0"].clone().requires_grad_(True)
+    lm2 = t["loc_mean"].clone().requires_grad_(True)
+    xo, Zo = runner(lt["node_feat"], xl, lt["vel_0"], lt["edge_index"], lm2, lt["edge_attr"], n_global=n)
+    loss = (xo * lt["wx"][:N]).sum()
+    if rank == 0:                      # Z-only loss terms live on one rank (the total loss is the sum over ranks)
+        loss = loss + (Zo * wz.to(dev)).sum()
+    else:
+        loss = loss + 0.0 * Zo.sum()
+    loss.backward()
+    runner.allreduce_gradients()
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+    owned = torch.from_numpy(plan.parts[rank]["owned"]).to(dev)
+    errs = dict(x=rel(xo, xr.detach()[owned]), Z=rel(Zo, Zr.detach()), gx0=rel(xl.grad[:N], ref_gx0[owned]),
+                gloc_mean=rel(lm2.grad, ref_glm))
+    worst_w = 0.0
+    bad_none = []
+    for k, p in model.named_parameters():
+        if ref_grads[k] is None:
+            if p.grad is not None:
+                bad_none.append(k)
+            continue
+        e = rel(p.grad, ref_grads[k])
+        errs["w:" + k] = e
+        worst_w = max(worst_w, e)
+    tol_out, tol_grad = 2e-5, 3e-4
+    ok = (errs["x"] < tol_out and errs["Z"] < tol_out and errs["gx0"] < tol_grad and errs["gloc_mean"] < tol_grad and
+          worst_w < tol_grad and not bad_none)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_w{world}_c{C}_rank{rank}.txt"), "w") as f:
+        f.write(f"world {world} rank {rank} N_owned {N} halo {runner.comm.Nl - N} ok {ok}\n")
+        for k in ("x", "Z", "gx0", "gloc_mean"):
+            f.write(f"{k}: {errs[k]:.3e}\n")
+        f.write(f"worst weight grad: {worst_w:.3e}\n")
+        for k, e in errs.items():
+            if k.startswith("w:") and e > tol_grad:
+                f.write(f"FAIL {k}: {e:.3e}\n")
+    print(f"rank {rank}: ok={ok} x {errs['x']:.2e} Z {errs['Z']:.2e} gx0 {errs['gx0']:.2e} glm {errs['gloc_mean']:.2e} "
+          f"w {worst_w:.2e} halo {runner.comm.Nl - N}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

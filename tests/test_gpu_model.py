@@ -39,7 +39,7 @@ def test_golden_vectors_from_reference(name):
     for k in ("node_loc", "loc_mean", "node_feat"):
         gold = torch.from_numpy(arr[f"gin_{k}"])
         assert rel_err(res["gin"][k], r64["gin"][k]) < TOL_GRAD, k
-        assert rel_err(res["gin"][k], gold) < TOL_GRAD + rel_err(gold, r64["gin"][k]), k
+        assert rel_err(res["gin"][k], gold) < TOL_GRAD + 1.1 * rel_err(gold, r64["gin"][k]), k
     none = sorted(k for k, g in res["gp"].items() if g is None)
     assert none == sorted(meta["grad_none"])          # last layer's node_mlp / node_mlp_virtual: no gradient
     for k, dig in meta["grad_digest"].items():
