@@ -13,8 +13,11 @@ Workloads (BASELINE.json configs):
             (E ~ 2e5 directed edges, ordered by ascending length), C=3, gravity [0,-1,0], B=1.
   nbody100  (config 2) 100 graphs x 100 particles, shortest 50% of all ordered pairs.
   large     (config 5 shape, scaled by --nodes) uniform cloud, mean degree 30, C=8.
-With N>1 ranks every rank trains on its own whole graphs (weak scaling) and weight gradients are
-all-reduced over NCCL once per step (SURVEY.md 5.1 mode 1).
+With N>1 ranks: water3d / nbody100 (whole small graphs, as the reference batches them) go one batch per
+rank with a single weight-gradient all-reduce per step (--mode dp, SURVEY.md 5.1 mode 1, weak scaling);
+`--workload large` is ONE graph spatially partitioned into N slabs (--mode partitioned, mode 2): halo
+exchange of (Q_j, x_j) and an all-reduce of the per-graph virtual-node sums per layer (strong scaling).
+`--mode partitioned` can be forced for water3d too (then 8 000 nodes per rank, weak).
 
 `--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops in the
 reference's op order, all host threads) on the same workload and prints the same line shape.
@@ -210,6 +213,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="water3d", choices=["water3d", "nbody100", "large"])
     ap.add_argument("--nodes", type=int, default=0)
+    ap.add_argument("--mode", default="auto", choices=["auto", "dp", "partitioned"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
     args = ap.parse_args()
@@ -218,13 +223,27 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
-    data, hp = make_workload(args.workload, seed=rank, nodes=args.nodes)
+    mode = args.mode
+    if mode == "auto":
+        # small / batched graphs (configs 1-4) go whole to the ranks; one big graph (config 5) is partitioned
+        mode = "partitioned" if world > 1 and args.impl == "b200" and args.workload == "large" else "dp"
+    part = mode == "partitioned" and world > 1
+    if part:
+        nodes = args.nodes or (8000 * world if args.workload == "water3d" else 0)
+        data, hp = make_workload(args.workload, seed=0, nodes=nodes)          # every rank builds the same global graph
+    else:
+        data, hp = make_workload(args.workload, seed=rank, nodes=args.nodes)
     E, N, B, C = int(data["edge_index"].size(1)), int(data["loc_0"].size(0)), data["n_graphs"], data["C"]
-    config = dict(workload=f"{args.workload}: N={N} nodes, E={E} directed edges, B={B} graph(s), C={C}, L={LAYERS}, "
-                           f"H={H}, gravity={data['gravity']}; step = fwd + MSE + {hp['weight']}*MMD + bwd + Adam",
-                  l2="flushed (256 MiB write) before every timed step",
-                  parallelism=f"{world} rank(s), whole graphs per rank, weight-gradient all-reduce per step"
-                  if world > 1 else "1 rank")
+    scaling = "weak" if not (part and args.workload == "large") else "strong"
+    par = "1 rank"
+    if world > 1:
+        par = (f"{world} ranks, ONE graph in {world} slabs: halo exchange + per-graph all-reduce per layer, "
+               "weight-gradient all-reduce per step") if part else \
+              f"{world} ranks, whole graphs per rank, weight-gradient all-reduce per step"
+    config = dict(workload=f"{args.workload}: N={N} nodes, E={E} directed edges{' (global)' if part else ''}, "
+                           f"B={B} graph(s), C={C}, L={LAYERS}, H={H}, gravity={data['gravity']}; "
+                           f"step = fwd + MSE + {hp['weight']}*MMD + bwd + Adam",
+                  l2="flushed (256 MiB write) before every timed step", parallelism=par)
     metric = "layer fwd+bwd edges/sec (full train step: fwd+MSE+MMD+bwd+Adam), Water-3D shape"
     cores = os.cpu_count() or 1
 
@@ -237,7 +256,7 @@ def main():
         val = E * LAYERS / t
         line = dict(impl="reference", metric=metric, value=val, unit="edges/s", n_gpus=args.gpus,
                     steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)), ms_per_step=t * 1e3,
-                    steps_per_sec=1.0 / t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    steps_per_sec=1.0 / t, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f32",
                     data="synthetic", config=config,
                     cpu_baseline=dict(value=val, unit="edges/s", cores=cores, kind="port",
                                       sample="the full workload, one training step per timed step (oracle/ restates "
@@ -259,16 +278,37 @@ def main():
     torch.manual_seed(0)
     model = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=H, virtual_channels=C, device=dev,
                      n_layers=LAYERS, gravity=data["gravity"])
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-12)
+    use_graph = not args.no_graph and world == 1     # NCCL collectives are kept out of graph capture
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-12, capturable=use_graph)
     params = [p for p in model.parameters()]
     gen = torch.Generator().manual_seed(0)
     ns = min(hp["sample"] * C, min(data["sizes"]))
     keys = ("node_feat", "loc_0", "vel_0", "loc_t", "edge_index", "edge_attr", "batch", "loc_mean")
-    host = {k: data[k].pin_memory() for k in keys}
+    idx_all = sample_indices(data["sizes"], ns, gen)                         # [B, ns] global node ids
+    runner, n_own, svv, srv = None, N, 1.0, 1.0
+    if part:
+        from fastegnn_b200.partitioned import PartitionedFastEGNN, SlabPlan
+        plan = SlabPlan(data["loc_0"].numpy(), data["edge_index"].numpy(), world)
+        loc = plan.localize(rank, dict(node_feat=data["node_feat"].numpy(), loc_0=data["loc_0"].numpy(),
+                                       vel_0=data["vel_0"].numpy(), loc_t=data["loc_t"].numpy()),
+                            dict(edge_attr=data["edge_attr"].numpy()))
+        runner = PartitionedFastEGNN(model, plan, rank, dev)
+        n_own = runner.comm.N
+        local = {k: torch.from_numpy(v) for k, v in loc.items()}
+        local["loc_mean"] = data["loc_mean"]
+        local["batch"] = torch.zeros(n_own, dtype=torch.int64)
+        mine = [int(plan.local_id[g]) for g in idx_all[0].tolist() if plan.owner[g] == rank]
+        idx_all = torch.tensor([mine], dtype=torch.int32).reshape(1, len(mine))
+        svv, srv = (1.0 if rank == 0 else 0.0), len(mine) / float(ns)
+        data_local = local
+    else:
+        data_local = data
+    host = {k: data_local[k].pin_memory() for k in keys}
     dev_in = {k: host[k].to(dev) for k in keys}
-    idx_host = sample_indices(data["sizes"], ns, gen).pin_memory()
+    idx_host = idx_all.pin_memory()
     idx_dev = idx_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    n_glob = N
 
     def allreduce_grads():
         grads = [p.grad for p in params if p.grad is not None]
@@ -279,19 +319,63 @@ def main():
 
     def train_step(t, idx):
         opt.zero_grad(set_to_none=True)
-        x, Z = model(node_feat=t["node_feat"], node_loc=t["loc_0"], node_vel=t["vel_0"], edge_index=t["edge_index"],
-                     data_batch=t["batch"], loc_mean=t["loc_mean"], edge_attr=t["edge_attr"])
-        loss = torch.nn.functional.mse_loss(x, t["loc_t"]) + hp["weight"] * mmd_loss(x, Z, idx, hp["sigma"])
-        loss.backward()
-        if world > 1:
-            allreduce_grads()
+        if part:
+            x, Z = runner(t["node_feat"], t["loc_0"], t["vel_0"], t["edge_index"], t["loc_mean"], t["edge_attr"],
+                          n_global=n_glob)
+            # MSE over ALL nodes and the MMD term, written as a sum of rank-local shares
+            loss = ((x - t["loc_t"][:n_own]) ** 2).sum() / (3.0 * n_glob) + \
+                hp["weight"] * mmd_loss(x, Z, idx, hp["sigma"], svv, srv)
+            loss.backward()
+            runner.allreduce_gradients()
+        else:
+            x, Z = model(node_feat=t["node_feat"], node_loc=t["loc_0"], node_vel=t["vel_0"],
+                         edge_index=t["edge_index"], data_batch=t["batch"], loc_mean=t["loc_mean"],
+                         edge_attr=t["edge_attr"])
+            loss = torch.nn.functional.mse_loss(x, t["loc_t"]) + hp["weight"] * mmd_loss(x, Z, idx, hp["sigma"])
+            loss.backward()
+            if world > 1:
+                allreduce_grads()
         opt.step()
         return loss
 
+    # ---- the whole step (graph prep, 4-layer fwd, losses, bwd, collectives, Adam) as ONE CUDA graph:
+    #      the C ABI never allocates or synchronises, so every launch of a step is capturable.
+    graph_state = dict(g=None, loss=None, why=None)
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    train_step(dev_in, idx_dev)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.lib.fegnn_launch_count()
+            with torch.cuda.graph(g):
+                graph_state["loss"] = train_step(dev_in, idx_dev)
+            graph_state["per_step"] = int(_lib.lib.fegnn_launch_count() - c0)   # kernels of this library in the graph
+            graph_state["g"] = g
+        except Exception as exc:                                  # pragma: no cover - reported in the JSON line
+            graph_state.update(g=None, why=f"{type(exc).__name__}: {exc}"[:300])
+            torch.cuda.synchronize()
+
+    def resident_step():
+        if graph_state["g"] is not None:
+            graph_state["g"].replay()
+            return graph_state["loss"]
+        return train_step(dev_in, idx_dev)
+
     def e2e_step():
+        if graph_state["g"] is not None:
+            for k in keys:                                        # pinned host -> the graph's static inputs
+                dev_in[k].copy_(host[k], non_blocking=True)
+            idx_dev.copy_(idx_host, non_blocking=True)
+            graph_state["g"].replay()
+            return graph_state["loss"].item()                     # device->host read of the loss
         t = {k: host[k].to(dev, non_blocking=True) for k in keys}
         idx = idx_host.to(dev, non_blocking=True)
-        return train_step(t, idx).item()                      # device->host read of the loss
+        return train_step(t, idx).item()
 
     def timed(fn, steps):
         """Per-step CUDA events on the launching (current) stream, L2 flushed before each step."""
@@ -312,7 +396,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        train_step(dev_in, idx_dev)
+        resident_step()
         e2e_step()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -320,9 +404,11 @@ def main():
         sampler.start()
     launches0 = _lib.lib.fegnn_launch_count()
     barrier()
-    ms = timed(lambda: train_step(dev_in, idx_dev), args.steps)
+    ms = timed(resident_step, args.steps)
     barrier()
     launches = _lib.lib.fegnn_launch_count() - launches0
+    if graph_state["g"] is not None:
+        launches = graph_state["per_step"] * args.steps          # replayed from the captured graph
     ms_e2e = timed(e2e_step, args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -331,19 +417,21 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ee = torch.tensor([E], device=dev, dtype=torch.float64)
         dist.all_reduce(ee)
-        ms, ms_e2e, E_all = float(tt[0]), float(tt[1]), float(ee[0])
+        ms, ms_e2e, E_all = float(tt[0]), float(tt[1]), (float(E) if part else float(ee[0]))
     else:
         E_all = float(E)
 
     if rank == 0:
         h2d = sum(host[k].numel() * host[k].element_size() for k in keys) + idx_host.numel() * 4
         line = dict(metric=metric, value=E_all * LAYERS / (ms * 1e-3), unit="edges/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=ms, steps_per_sec=1e3 / ms, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=ms, steps_per_sec=1e3 / ms, higher_is_better=True, scaling=scaling,
                     vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clocks,
                     e2e=dict(value=E_all * LAYERS / (ms_e2e * 1e-3), unit="edges/s", ms_per_step=ms_e2e,
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
-                    gpu_launches=int(launches))
-        if not args.no_phases:
+                    gpu_launches=int(launches), cuda_graph=graph_state["g"] is not None)
+        if graph_state["why"]:
+            line["cuda_graph_error"] = graph_state["why"]
+        if not args.no_phases and not part:
             line.update(phase_profile(model, dev_in, dev, data, E, N, B, C, flush))
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(cores)

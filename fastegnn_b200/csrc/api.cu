@@ -562,17 +562,19 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
 }
 
 // ------------------------------------------------------------------ MMD
-int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
-                      const int32_t* sample_idx, float* loss, void* stream) {
-  RQ(B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 1 && sigma > 0.f && loss && (B == 0 || (x && Z && sample_idx)));
-  CK(launch_mmd_fwd(B, C, ns, sigma, x, Z, sample_idx, loss, S(stream)));
+int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, float scale_vv, float scale_rv, const float* x,
+                      const float* Z, const int32_t* sample_idx, float* loss, void* stream) {
+  RQ(B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 0 && sigma > 0.f && loss && (B == 0 || Z));
+  RQ(B == 0 || ns == 0 || (x && sample_idx));
+  CK(launch_mmd_fwd(B, C, ns, sigma, scale_vv, scale_rv, x, Z, sample_idx, loss, S(stream)));
   return 0;
 }
-int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
-                       const int32_t* sample_idx, const float* gloss, float* gx, float* gZ, void* stream) {
-  RQ(N >= 0 && B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 1 && sigma > 0.f && gloss && gx && gZ);
-  RQ(B == 0 || (x && Z && sample_idx));
-  CK(launch_mmd_bwd(N, B, C, ns, sigma, x, Z, sample_idx, gloss, gx, gZ, S(stream)));
+int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float scale_vv, float scale_rv,
+                       const float* x, const float* Z, const int32_t* sample_idx, const float* gloss, float* gx,
+                       float* gZ, void* stream) {
+  RQ(N >= 0 && B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 0 && sigma > 0.f && gloss && gx && gZ);
+  RQ(B == 0 || (Z && (ns == 0 || (x && sample_idx))));
+  CK(launch_mmd_bwd(N, B, C, ns, sigma, scale_vv, scale_rv, x, Z, sample_idx, gloss, gx, gZ, S(stream)));
   return 0;
 }
 

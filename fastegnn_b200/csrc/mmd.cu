@@ -9,11 +9,11 @@
 
 namespace fegnn {
 
-__global__ void __launch_bounds__(128) mmd_fwd_kernel(int B, int C, int ns, float inv2s2, const float* __restrict__ x,
+__global__ void __launch_bounds__(128) mmd_fwd_kernel(int B, int C, int ns, float inv2s2, float svv, float srv, const float* __restrict__ x,
                                                       const float* __restrict__ Z, const int* __restrict__ idx,
                                                       float* __restrict__ loss) {
   const int b = blockIdx.x;
-  const float cvv = 1.f / ((float)B * C * C), crv = 2.f / ((float)B * ns * C);
+  const float cvv = svv / ((float)B * C * C), crv = ns > 0 ? srv * 2.f / ((float)B * ns * C) : 0.f;
   float acc = 0.f;
   for (int p = threadIdx.x; p < C * C + ns * C; p += blockDim.x) {
     float px, py, pz, w;
@@ -38,14 +38,14 @@ __global__ void __launch_bounds__(128) mmd_fwd_kernel(int B, int C, int ns, floa
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc);
 }
 
-__global__ void __launch_bounds__(128) mmd_bwd_kernel(int B, int C, int ns, float inv2s2, const float* __restrict__ x,
+__global__ void __launch_bounds__(128) mmd_bwd_kernel(int B, int C, int ns, float inv2s2, float svv, float srv, const float* __restrict__ x,
                                                       const float* __restrict__ Z, const int* __restrict__ idx,
                                                       const float* __restrict__ gloss, float* __restrict__ gx,
                                                       float* __restrict__ gZ) {
   __shared__ float gz[3 * FEGNN_MAX_C];
   const int b = blockIdx.x;
   const float gl = gloss[0];
-  const float cvv = gl / ((float)B * C * C), crv = 2.f * gl / ((float)B * ns * C);
+  const float cvv = svv * gl / ((float)B * C * C), crv = ns > 0 ? srv * 2.f * gl / ((float)B * ns * C) : 0.f;
   if (threadIdx.x < 3 * C) gz[threadIdx.x] = 0.f;
   __syncthreads();
   for (int p = threadIdx.x; p < C * C + ns * C; p += blockDim.x) {
@@ -83,18 +83,18 @@ __global__ void __launch_bounds__(128) mmd_bwd_kernel(int B, int C, int ns, floa
   if (threadIdx.x < 3 * C) gZ[(size_t)b * 3 * C + threadIdx.x] = gz[threadIdx.x];
 }
 
-cudaError_t launch_mmd_fwd(int B, int C, int ns, float sigma, const float* x, const float* Z, const int* idx,
+cudaError_t launch_mmd_fwd(int B, int C, int ns, float sigma, float svv, float srv, const float* x, const float* Z, const int* idx,
                            float* loss, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
   if (e != cudaSuccess || B == 0) return e;
-  mmd_fwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, loss); ++g_launches;
+  mmd_fwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), svv, srv, x, Z, idx, loss); ++g_launches;
   return cudaGetLastError();
 }
-cudaError_t launch_mmd_bwd(int N, int B, int C, int ns, float sigma, const float* x, const float* Z, const int* idx,
+cudaError_t launch_mmd_bwd(int N, int B, int C, int ns, float sigma, float svv, float srv, const float* x, const float* Z, const int* idx,
                            const float* gloss, float* gx, float* gZ, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)N, st);
   if (e != cudaSuccess || B == 0) return e;
-  mmd_bwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), x, Z, idx, gloss, gx, gZ); ++g_launches;
+  mmd_bwd_kernel<<<B, 128, 0, st>>>(B, C, ns, 1.f / (2.f * sigma * sigma), svv, srv, x, Z, idx, gloss, gx, gZ); ++g_launches;
   return cudaGetLastError();
 }
 

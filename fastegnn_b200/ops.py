@@ -109,37 +109,40 @@ class SavedBlock:
 # ----------------------------------------------------------------------------- MMD
 class _MmdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, Z, sample_idx, sigma):
+    def forward(ctx, x, Z, sample_idx, sigma, scale_vv, scale_rv):
         _require_cuda(x, "node_loc")
         x = x.contiguous()
         Z = Z.contiguous()
         B, _, C_ = Z.shape
         ns = sample_idx.size(1)
         loss = torch.empty(1, device=x.device, dtype=torch.float32)
-        L.check(lib.fegnn_mmd_forward(B, C_, ns, float(sigma), L.ptr(x), L.ptr(Z), L.ptr(sample_idx), L.ptr(loss),
-                                      _stream()), "fegnn_mmd_forward")
+        L.check(lib.fegnn_mmd_forward(B, C_, ns, float(sigma), float(scale_vv), float(scale_rv), L.ptr(x), L.ptr(Z),
+                                      L.ptr(sample_idx), L.ptr(loss), _stream()), "fegnn_mmd_forward")
         ctx.save_for_backward(x, Z, sample_idx)
-        ctx.sigma = float(sigma)
+        ctx.cfg = (float(sigma), float(scale_vv), float(scale_rv))
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         x, Z, idx = ctx.saved_tensors
         B, _, C_ = Z.shape
+        sigma, svv, srv = ctx.cfg
         gx = torch.empty_like(x)
         gZ = torch.empty_like(Z)
         gl = g.reshape(1).contiguous().float()
-        L.check(lib.fegnn_mmd_backward(x.size(0), B, C_, idx.size(1), ctx.sigma, L.ptr(x), L.ptr(Z), L.ptr(idx),
+        L.check(lib.fegnn_mmd_backward(x.size(0), B, C_, idx.size(1), sigma, svv, srv, L.ptr(x), L.ptr(Z), L.ptr(idx),
                                        L.ptr(gl), L.ptr(gx), L.ptr(gZ), _stream()), "fegnn_mmd_backward")
-        return gx, gZ, None, None
+        return gx, gZ, None, None, None, None
 
 
-def mmd_loss(node_loc: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx: torch.Tensor, sigma: float):
+def mmd_loss(node_loc: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx: torch.Tensor, sigma: float,
+             scale_vv: float = 1.0, scale_rv: float = 1.0):
     """l_vv - l_rv of utils/train.py:111-165 in one launch.
 
     node_loc [N,3]; virtual_node_loc [B,3,C] exactly as FastEGNN.forward returns it (the
     reference permutes it to [B,C,3] at :113); sample_idx int32 [B, ns] of GLOBAL node
-    indices (graph offset + the reference's torch.randperm(n_b)[:ns])."""
+    indices (graph offset + the reference's torch.randperm(n_b)[:ns]).  scale_vv / scale_rv weight the
+    two terms (1, 1 = the reference; the partitioned path splits the sum over ranks, see fegnn.h)."""
     if sample_idx.dtype != torch.int32:
         sample_idx = sample_idx.to(torch.int32)
-    return _MmdFn.apply(node_loc, virtual_node_loc, sample_idx.contiguous(), sigma)
+    return _MmdFn.apply(node_loc, virtual_node_loc, sample_idx.contiguous(), sigma, scale_vv, scale_rv)

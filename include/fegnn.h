@@ -225,14 +225,16 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
 /* ------------------------------------------------------------------ MMD regulariser
  * utils/train.py:17-20,111-165 with the random sample made explicit:
  * sample_idx[b*ns + s] is a GLOBAL node index (graph offset already added).
- * loss = (1/(B C^2)) sum k(Z_bc,Z_bc') - (2/(B ns C)) sum k(x_s, Z_bc),
- * k(p,q) = exp(-|p-q| / (2 sigma^2)).                                            */
-int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, const float* x /*[N,3]*/,
-                      const float* Z /*[B,3,C]*/, const int32_t* sample_idx, float* loss /*[1] zeroed here*/,
-                      void* stream);
-int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, const float* x, const float* Z,
-                       const int32_t* sample_idx, const float* gloss /*[1]*/, float* gx /*[N,3] zeroed here*/,
-                       float* gZ /*[B,3,C] =*/, void* stream);
+ * loss = scale_vv * (1/(B C^2)) sum k(Z_bc,Z_bc') - scale_rv * (2/(B ns C)) sum k(x_s, Z_bc),
+ * k(p,q) = exp(-|p-q| / (2 sigma^2)).  scale_vv = scale_rv = 1 is the reference; the partitioned
+ * path evaluates the Z-only term on one rank (scale_vv = 0 elsewhere) and weights each rank's share of
+ * the samples (scale_rv = ns_local / ns_total; ns == 0 is allowed).                                   */
+int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, float scale_vv, float scale_rv,
+                      const float* x /*[N,3]*/, const float* Z /*[B,3,C]*/, const int32_t* sample_idx,
+                      float* loss /*[1] zeroed here*/, void* stream);
+int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float scale_vv, float scale_rv,
+                       const float* x, const float* Z, const int32_t* sample_idx, const float* gloss /*[1]*/,
+                       float* gx /*[N,3] zeroed here*/, float* gZ /*[B,3,C] =*/, void* stream);
 
 #ifdef __cplusplus
 }
