@@ -132,6 +132,16 @@ def set_mode(phase: str, mode: int) -> None:
     check(lib.fegnn_set_mode(phase.encode(), int(mode)), "fegnn_set_mode")
 
 
+def set_precision(name: str) -> None:
+    """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase runs on
+    tcgen05 TF32 tiles, forward and backward (stated tolerance).  "tf32x3": TF32 backward, 3xTF32
+    (fp32-grade) forward."""
+    table = {"fp32": (0, 0), "tf32": (1, 1), "tf32x3": (3, 1)}
+    fwd, bwd = table[name]
+    set_mode("edge_forward", fwd)
+    set_mode("edge_backward", bwd)
+
+
 def get_mode(phase: str) -> int:
     return int(lib.fegnn_get_mode(phase.encode()))
 
@@ -142,7 +152,9 @@ def check(rc: int, what: str = "") -> None:
         raise FegnnError(f"{what or 'fegnn'} failed with code {rc}: {msg}")
 
 
-for _phase in ("edge_forward",):
+if os.environ.get("FEGNN_PRECISION"):
+    set_precision(os.environ["FEGNN_PRECISION"])
+for _phase in ("edge_forward", "edge_backward"):
     _env = os.environ.get("FEGNN_MODE_" + _phase.upper())
     if _env is not None:
         set_mode(_phase, int(_env))

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "edge_kernels.cu"
 #include "edge_tc.cu"
+#include "edge_tc_bwd.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "mmd.cu"
@@ -43,7 +44,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32, 3 = tcgen05 3xTF32 (fp32-grade)
-int g_edge_fwd_mode = 3;
+int g_edge_fwd_mode = 1;
+// 0 = fp32 FMA kernel, 1 = tcgen05 single-pass TF32
+int g_edge_bwd_mode = 1;
 
 int sm_count() {
   static int sms = 0;
@@ -162,10 +165,16 @@ int fegnn_set_mode(const char* phase, int mode) {
     g_edge_fwd_mode = mode;
     return 0;
   }
+  if (strcmp(phase, "edge_backward") == 0) {
+    if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "edge_backward mode must be 0 or 1");
+    g_edge_bwd_mode = mode;
+    return 0;
+  }
   return fail(FEGNN_EINVAL, "unknown phase '%s'", phase);
 }
 int fegnn_get_mode(const char* phase) {
   if (phase != nullptr && strcmp(phase, "edge_forward") == 0) return g_edge_fwd_mode;
+  if (phase != nullptr && strcmp(phase, "edge_backward") == 0) return g_edge_bwd_mode;
   return -1;
 }
 
@@ -350,7 +359,9 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
   CK(cudaMemsetAsync(gP, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
   CK(cudaMemsetAsync(gQ, 0, sizeof(float) * kH * (size_t)d->Nl, S(stream)));
-  CK(launch_edge_bwd(a, sm_count(), S(stream)));
+  const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
+  if (g_edge_bwd_mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
+  else CK(launch_edge_bwd(a, sm_count(), S(stream)));
   return 0;
 }
 

@@ -64,6 +64,8 @@ __device__ __forceinline__ void edge_load_geometry(const EdgeArgs& a, EdgeSmemVe
       d2 = a.x[(size_t)r * 3 + 2] - a.x[(size_t)c * 3 + 2];
       q = d0 * d0 + d1 * d1 + d2 * d2;
       for (int f = 0; f < a.Fe; ++f) v->sea[t * FEGNN_MAX_FE + f] = a.ea[(size_t)e * a.Fe + f];
+    } else {
+      for (int f = 0; f < a.Fe; ++f) v->sea[t * FEGNN_MAX_FE + f] = 0.f;   // padded rows multiply into column sums
     }
     v->srow[t] = r;
     v->scol[t] = c;

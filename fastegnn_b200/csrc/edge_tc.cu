@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
           d0 *= inv; d1 *= inv; d2 *= inv;
         }
         for (int f = 0; f < a.Fe; ++f) v->sea[t * kTcMaxFe + f] = a.ea[(size_t)e * a.Fe + f];
+      } else {
+        for (int f = 0; f < a.Fe; ++f) v->sea[t * kTcMaxFe + f] = 0.f;
       }
       v->srow[t] = r;
       v->scol[t] = c;

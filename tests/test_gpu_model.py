@@ -8,24 +8,28 @@ import pytest
 import torch
 
 from oracle import fastegnn_oracle as orc
-from tests.gpu_util import build_gpu_model, compare_with_oracles, gpu_run, make_graph_case, rel_err
+from tests.gpu_util import (TOLERANCES, build_gpu_model, compare_with_oracles, gpu_run, make_graph_case, precision,
+                            rel_err)
 from tests.helpers import GOLDEN, H64_CASES, case_inputs, case_params, load_case, oracle_run
 
 pytestmark = pytest.mark.gpu
 
-# fp32 tolerances, relative to the largest entry of each tensor.  The CUDA path sums in a
-# different order than ATen (split first Linear, tile-wise segment sums) and uses ex2.approx
-# in SiLU; observed errors are ~1e-6 (outputs) and ~1e-5 (gradients), the fp32 oracle itself
-# sits at ~1e-6 from the fp64 oracle.
-TOL_OUT, TOL_GRAD = 2e-5, 2e-4
+# Tolerances are relative to the largest entry of each tensor and depend on the arithmetic mode
+# (tests/gpu_util.py TOLERANCES).  In fp32 mode the CUDA path only sums in a different order than ATen
+# (split first Linear, tile-wise segment sums) and uses ex2.approx in SiLU: observed ~1e-7 (outputs) and
+# ~1e-6 (gradients), the same distance the fp32 oracle has from the fp64 oracle.
+TOL_OUT, TOL_GRAD = TOLERANCES["fp32"]
+PRECISIONS = ["fp32", "tf32x3", "tf32"]
 
 
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("name", H64_CASES)
-def test_golden_vectors_from_reference(name):
+def test_golden_vectors_from_reference(name, prec):
     meta, arr = load_case(name)
     cfg, params = case_params(meta["case"])
     inp = case_inputs(arr)
-    res = gpu_run(cfg, params, inp)
+    with precision(prec) as (TOL_OUT, TOL_GRAD):
+        res = gpu_run(cfg, params, inp)
     assert rel_err(res["x"], torch.from_numpy(arr["out_x"])) < TOL_OUT
     assert rel_err(res["Z"], torch.from_numpy(arr["out_Z"])) < TOL_OUT
     # The golden gradients are the reference's own fp32 autograd.  With normalize=True a self-loop
@@ -42,10 +46,18 @@ def test_golden_vectors_from_reference(name):
         assert rel_err(res["gin"][k], gold) < TOL_GRAD + 1.1 * rel_err(gold, r64["gin"][k]), k
     none = sorted(k for k, g in res["gp"].items() if g is None)
     assert none == sorted(meta["grad_none"])          # last layer's node_mlp / node_mlp_virtual: no gradient
+    for k, g64 in r64["gp"].items():
+        if g64 is not None:
+            assert rel_err(res["gp"][k], g64) < (TOL_GRAD if prec == "fp32" else 5 * TOL_GRAD), k
     for k, dig in meta["grad_digest"].items():
+        if cfg.normalize:
+            break       # the reference's own fp32 gradients carry the self-loop cancellation noise (see above)
         g = res["gp"][k].double().flatten()
         scale = dig["l2"] + 1e-30
-        assert abs(float(g.norm()) - dig["l2"]) <= 5e-4 * scale, k
+        # TF32 modes: on these 20-40 node fixtures a few gradient tensors are sums with strong cancellation and move
+        # by several per cent in norm under 10-bit operand rounding; the per-entry check below (relative to the
+        # tensor's norm) is the stated tolerance, the norm itself gets 5x of it.
+        assert abs(float(g.norm()) - dig["l2"]) <= (5e-4 if prec == "fp32" else 5 * TOL_GRAD) * scale, k
         np.testing.assert_allclose(g[dig["idx"]].numpy(), np.array(dig["val"]), rtol=0, atol=TOL_GRAD * scale,
                                    err_msg=k)
 
@@ -62,19 +74,25 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("name", list(CASES))
-def test_seeded_batches_against_oracle(name):
+def test_seeded_batches_against_oracle(name, prec):
     cfg, params, inp = make_graph_case(**CASES[name])
-    res = gpu_run(cfg, params, inp)
-    bad, report = compare_with_oracles(cfg, params, inp, res, TOL_OUT, TOL_GRAD, label=name + " ")
+    with precision(prec) as (tol_out, tol_grad):
+        res = gpu_run(cfg, params, inp)
+    bad, report = compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=f"{name} [{prec}] ")
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/parity_{name}.txt", "w") as f:
+    with open(f"gpurun_out/parity_{prec}_{name}.txt", "w") as f:
         f.write("\n".join(report) + "\n")
     assert not bad, (bad, [r for r in report if any(b in r for b in bad)])
 
 
-def test_equivariance_property():
-    """equivariant_test.py:18-62 with seeds: FastEGNN(G R + t) == FastEGNN(G) R + t, atol 1e-4."""
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_equivariance_property(prec):
+    """equivariant_test.py:18-62 with seeds: FastEGNN(G R + t) == FastEGNN(G) R + t, atol 1e-4 -- in every
+    arithmetic mode (the MLP inputs are invariants, so TF32 operand rounding does not break equivariance)."""
+    from fastegnn_b200 import _lib
+    _lib.set_precision(prec)
     dev = "cuda:0"
     for seed in range(4):
         g = torch.Generator().manual_seed(seed)
@@ -101,7 +119,11 @@ def test_equivariance_property():
             return out.detach().cpu()
         a = run(x, v) @ R + t
         b = run(x @ R + t, v @ R)
-        assert torch.allclose(a, b, atol=1e-4), float((a - b).abs().max())
+        ok = torch.allclose(a, b, atol=1e-4)
+        if not ok:
+            _lib.set_precision("tf32")
+        assert ok, float((a - b).abs().max())
+    _lib.set_precision("tf32")
 
 
 def test_graph_prep_is_bit_exact_stable_sort():
@@ -150,6 +172,15 @@ def test_mmd_matches_reference_block():
 
 def test_layer_level_api_matches_oracle_layer():
     """E_GCL_vel.forward (the unit the layer metric is quoted on), S in the reference's [B,H,C] layout."""
+    from fastegnn_b200 import _lib
+    _lib.set_precision("fp32")
+    try:
+        _layer_level_check()
+    finally:
+        _lib.set_precision("tf32")
+
+
+def _layer_level_check():
     dev = "cuda:0"
     cfg, params, inp = make_graph_case(seed=9, sizes=[150, 160], deg=9, C=3, L=1, gravity=[0, -1, 0])
     m = build_gpu_model(cfg, params, dev)
@@ -190,7 +221,17 @@ def test_layer_level_api_matches_oracle_layer():
 
 
 def test_training_step_through_adam_matches_oracle():
-    """Two optimizer steps (MSE + weight * MMD, Adam as in main_*.py) track the oracle."""
+    """Two optimizer steps (MSE + weight * MMD, Adam as in main_*.py) track the oracle (fp32 mode: Adam's
+    normalised update turns tiny gradient differences into O(lr) weight differences)."""
+    from fastegnn_b200 import _lib
+    _lib.set_precision("fp32")
+    try:
+        _adam_check()
+    finally:
+        _lib.set_precision("tf32")
+
+
+def _adam_check():
     from fastegnn_b200 import mmd_loss
     dev = "cuda:0"
     cfg, params, inp = make_graph_case(seed=21, sizes=[60] * 4, deg=8, C=3, gain=1.0)

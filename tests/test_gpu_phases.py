@@ -56,6 +56,16 @@ def _chk(errs, name, got, want, tol):
 @pytest.mark.parametrize("name", list(PHASE_CASES))
 @pytest.mark.parametrize("layer", [0, 1])
 def test_phases(name, layer):
+    """Every phase on the fp32 FMA kernels (the tensor-core modes of the edge phase have their own tests below)."""
+    from fastegnn_b200 import _lib
+    _lib.set_precision("fp32")
+    try:
+        _phases(name, layer)
+    finally:
+        _lib.set_precision("tf32")
+
+
+def _phases(name, layer):
     s = _setup(name)
     L, lib = s["L"], s["L"].lib
     cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
@@ -238,3 +248,60 @@ def test_edge_forward_modes(name, mode):
     with open(f"gpurun_out/edge_fwd_mode{mode}_{name}.txt", "w") as fh:
         fh.write(f"mode {mode} {name}: msum {e_m:.3e} tsum {e_t:.3e}\n")
     assert e_m <= EDGE_MODE_TOL[mode] and e_t <= EDGE_MODE_TOL[mode], (e_m, e_t)
+
+
+EDGE_BWD_TOL = {0: (3e-5, 2e-4), 1: (6e-3, 6e-3)}     # (per-node outputs, weight gradients), relative to tensor max
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
+@pytest.mark.parametrize("layer", [0, 1])
+def test_edge_backward_modes(name, mode, layer):
+    """fegnn_edge_backward alone (fp32 FMA kernel vs tcgen05 TF32 kernel) against staged.edge_bwd."""
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    l = layer
+    last = l == cfg.n_layers - 1
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"] | (L.F_LAST if last else 0), cfg.gravity)
+    prefix = f"gcl_{l}"
+    ptrs = s["layer_ptrs"](s["gparams"], prefix)
+    sv = s["SavedBlock"](dims, dev)
+    S_, bs = sm.saved[l], sm.bsaved[l]
+    sv.view("P", (N, H)).copy_(_g(S_["npre"]["P"], dev))
+    sv.view("Q", (N, H)).copy_(_g(S_["npre"]["Q"], dev))
+    x = _g(S_["x"], dev)
+    gviews = {k: torch.zeros_like(p) for k, p in s["gparams"].items() if k.startswith(prefix + ".")}
+    gr = s["layer_ptrs"](gviews, prefix)
+    b, c, d_ = bs["b"], bs["c"], bs["d"]
+    gm_x, gt_x = _g(b["gm"], dev), _g(c["gt"], dev)
+    gP = torch.empty(N, H, device=dev)
+    gQ = torch.empty(N, H, device=dev)
+    gx_acc = torch.zeros(N, 3, device=dev)
+    old = L.get_mode("edge_backward")
+    try:
+        L.set_mode("edge_backward", mode)
+        L.check(lib.fegnn_edge_backward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), C.byref(gr), L.ptr(x),
+                                        C.byref(sv.c), None if last else L.ptr(gm_x), L.ptr(gt_x), L.ptr(gP),
+                                        L.ptr(gQ), L.ptr(gx_acc), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("edge_backward", old)
+    tol, tol_w = EDGE_BWD_TOL[mode]
+    errs = []
+    _chk(errs, "gP", gP, d_["gP"], tol)
+    _chk(errs, "gQ", gQ, d_["gQ"], tol)
+    _chk(errs, "gx", gx_acc, d_["gx"], tol)
+    want = {}
+    staged._scatter_wg(want, prefix, d_["wg"], sm.w[l], 64, Cc, cfg.edge_attr_nf)
+    for k, wv in want.items():
+        _chk(errs, "wgrad." + k, gviews[k], wv, tol_w)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/edge_bwd_mode{mode}_{name}_l{l}.txt", "w") as fh:
+        for n_, e, t in errs:
+            fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
+    assert not bad, bad
