@@ -39,9 +39,25 @@ struct __align__(16) GraphSmem {
   float xbar[4];
 };
 
+// 64x64 weight block of a reference-layout matrix -> shared memory, row stride 65 (conflict-free both for
+// "thread n walks row n" and "thread k walks column k").  All 16 loads of a thread are independent.
+constexpr int kWPad = kH + 1;
+constexpr int kWPadFloats = kH * kWPad;
+__device__ __forceinline__ void stage_plain(float* __restrict__ Wsm, const float* __restrict__ g, int ld, int off) {
+#pragma unroll 16
+  for (int i = threadIdx.x; i < kWFloats; i += kThreads) {
+    const int n = i >> 6, k = i & 63;
+    Wsm[n * kWPad + k] = g[(size_t)n * ld + off + k];
+  }
+}
+constexpr size_t kGraphSmemBytes = sizeof(GraphSmem) + 3 * kWPadFloats * sizeof(float);
+
 __global__ void __launch_bounds__(kThreads) graph_pre_fwd_kernel(GraphArgs a) {
-  __shared__ GraphSmem s;
+  extern __shared__ __align__(16) unsigned char graph_smem_raw[];
+  GraphSmem& s = *reinterpret_cast<GraphSmem*>(graph_smem_raw);
+  float* V1s = reinterpret_cast<float*>(graph_smem_raw + sizeof(GraphSmem));
   const int b = blockIdx.x, C = a.C, tid = threadIdx.x;
+  stage_plain(V1s, a.wv1, a.ldv, kH);
   if (tid < 3) s.xbar[tid] = a.xsum[b * 3 + tid] * a.inv_nb[b];
   for (int i = tid; i < C * kH; i += kThreads) s.a[i] = a.S[(size_t)b * C * kH + i];
   __syncthreads();
@@ -60,20 +76,28 @@ __global__ void __launch_bounds__(kThreads) graph_pre_fwd_kernel(GraphArgs a) {
   __syncthreads();
   for (int o = tid; o < C * kH; o += kThreads) {
     const int c = o >> 6, n = o & 63;
-    const float* wrow = a.wv1 + (size_t)n * a.ldv;
     float acc = 0.f;
-    for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], wrow[kH + k], acc);
-    for (int d = 0; d < C; ++d) acc = fmaf(wrow[2 * kH + 1 + d], s.M[d * C + c], acc);
+#pragma unroll 16
+    for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], V1s[n * kWPad + k], acc);
+    const float* wrow = a.wv1 + (size_t)n * a.ldv + 2 * kH + 1;
+    for (int d = 0; d < C; ++d) acc = fmaf(wrow[d], s.M[d * C + c], acc);
     a.G1[(size_t)b * C * kH + o] = acc;
   }
 }
 
 __global__ void __launch_bounds__(kThreads) graph_post_fwd_kernel(GraphArgs a) {
-  __shared__ GraphSmem s;
+  extern __shared__ __align__(16) unsigned char graph_smem_raw[];
+  GraphSmem& s = *reinterpret_cast<GraphSmem*>(graph_smem_raw);
+  float* T1s = reinterpret_cast<float*>(graph_smem_raw + sizeof(GraphSmem));
+  float* T1a = T1s + kWPadFloats;
+  float* T2 = T1a + kWPadFloats;
   const int b = blockIdx.x, C = a.C, tid = threadIdx.x;
   const float inb = a.inv_nb[b];
   if (tid < 3 * C) a.Z_new[(size_t)b * 3 * C + tid] = a.Z[(size_t)b * 3 * C + tid] + a.Dsum[(size_t)b * 3 * C + tid] * inb;
   if (a.flags & FEGNN_F_LAST) return;
+  stage_plain(T1s, a.nodev_w0, 2 * kH, 0);
+  stage_plain(T1a, a.nodev_w0, 2 * kH, kH);
+  stage_plain(T2, a.nodev_w2, kH, 0);
   for (int i = tid; i < C * kH; i += kThreads) {
     s.a[i] = a.S[(size_t)b * C * kH + i];
     s.b[i] = a.Usum[(size_t)b * C * kH + i] * inb;
@@ -81,18 +105,19 @@ __global__ void __launch_bounds__(kThreads) graph_post_fwd_kernel(GraphArgs a) {
   __syncthreads();
   for (int o = tid; o < C * kH; o += kThreads) {
     const int c = o >> 6, n = o & 63;
-    const float* wrow = a.nodev_w0 + (size_t)n * 2 * kH;
     float acc = a.nodev_b0[n];
-    for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], wrow[k], acc);
-    for (int k = 0; k < kH; ++k) acc = fmaf(s.b[c * kH + k], wrow[kH + k], acc);
+#pragma unroll 16
+    for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], T1s[n * kWPad + k], acc);
+#pragma unroll 16
+    for (int k = 0; k < kH; ++k) acc = fmaf(s.b[c * kH + k], T1a[n * kWPad + k], acc);
     s.c[o] = silu_f(acc);
   }
   __syncthreads();
   for (int o = tid; o < C * kH; o += kThreads) {
     const int c = o >> 6, n = o & 63;
-    const float* wrow = a.nodev_w2 + (size_t)n * kH;
     float acc = a.nodev_b2[n];
-    for (int k = 0; k < kH; ++k) acc = fmaf(s.c[c * kH + k], wrow[k], acc);
+#pragma unroll 16
+    for (int k = 0; k < kH; ++k) acc = fmaf(s.c[c * kH + k], T2[n * kWPad + k], acc);
     a.S_new[(size_t)b * C * kH + o] = s.a[o] + acc;
   }
 }
@@ -115,9 +140,18 @@ __device__ __forceinline__ void small_outer_acc(float (&wg)[4][4], const float* 
 }
 
 __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
-  __shared__ GraphSmem s;
+  extern __shared__ __align__(16) unsigned char graph_smem_raw[];
+  GraphSmem& s = *reinterpret_cast<GraphSmem*>(graph_smem_raw);
+  float* T1s = reinterpret_cast<float*>(graph_smem_raw + sizeof(GraphSmem));
+  float* T1a = T1s + kWPadFloats;
+  float* T2 = T1a + kWPadFloats;
   const int C = a.C, tid = threadIdx.x;
   const bool last = a.flags & FEGNN_F_LAST;
+  if (!last) {
+    stage_plain(T1s, a.nodev_w0, 2 * kH, 0);
+    stage_plain(T1a, a.nodev_w0, 2 * kH, kH);
+    stage_plain(T2, a.nodev_w2, kH, 0);
+  }
   float wgT2[4][4], wgT1s[4][4], wgT1a[4][4];
   zero_wg(wgT2); zero_wg(wgT1s); zero_wg(wgT1a);
   float bf1 = 0.f, bf2 = 0.f;   // thread n < 64 owns the bias sums of column n
@@ -150,10 +184,11 @@ __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
       dts[q] = 0.f;
       if (o < C * kH) {
         const int c = o >> 6, n = o & 63;
-        const float* wrow = a.nodev_w0 + (size_t)n * 2 * kH;
         float acc = a.nodev_b0[n];
-        for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], wrow[k], acc);
-        for (int k = 0; k < kH; ++k) acc = fmaf(s.b[c * kH + k], wrow[kH + k], acc);
+#pragma unroll 16
+        for (int k = 0; k < kH; ++k) acc = fmaf(s.a[c * kH + k], T1s[n * kWPad + k], acc);
+#pragma unroll 16
+        for (int k = 0; k < kH; ++k) acc = fmaf(s.b[c * kH + k], T1a[n * kWPad + k], acc);
         float at, dt;
         silu_grad_f(acc, at, dt);
         s.c[o] = at;
@@ -173,7 +208,8 @@ __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
       if (o < C * kH) {
         const int c = o >> 6, k = o & 63;
         float acc = 0.f;
-        for (int n = 0; n < kH; ++n) acc = fmaf(s.d[c * kH + n], a.nodev_w2[(size_t)n * kH + k], acc);
+#pragma unroll 16
+        for (int n = 0; n < kH; ++n) acc = fmaf(s.d[c * kH + n], T2[n * kWPad + k], acc);
         gz[q] = acc * dts[q];
       }
     }
@@ -192,10 +228,11 @@ __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
     for (int o = tid; o < C * kH; o += kThreads) {
       const int c = o >> 6, k = o & 63;
       float accs = s.d[o], accu = 0.f;
+#pragma unroll 16
       for (int n = 0; n < kH; ++n) {
         const float g = s.c[c * kH + n];
-        accs = fmaf(g, a.nodev_w0[(size_t)n * 2 * kH + k], accs);
-        accu = fmaf(g, a.nodev_w0[(size_t)n * 2 * kH + kH + k], accu);
+        accs = fmaf(g, T1s[n * kWPad + k], accs);
+        accu = fmaf(g, T1a[n * kWPad + k], accu);
       }
       a.gS[(size_t)b * C * kH + o] = accs;
       a.gUsum[(size_t)b * C * kH + o] = accu * inb;
@@ -213,8 +250,11 @@ __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
 }
 
 __global__ void __launch_bounds__(kThreads) graph_pre_bwd_kernel(GraphArgs a) {
-  __shared__ GraphSmem s;
+  extern __shared__ __align__(16) unsigned char graph_smem_raw[];
+  GraphSmem& s = *reinterpret_cast<GraphSmem*>(graph_smem_raw);
+  float* V1s = reinterpret_cast<float*>(graph_smem_raw + sizeof(GraphSmem));
   const int C = a.C, tid = threadIdx.x;
+  stage_plain(V1s, a.wv1, a.ldv, kH);
   float wgV1s[4][4];
   zero_wg(wgV1s);
   float gV1m[kPerThread];
@@ -246,7 +286,8 @@ __global__ void __launch_bounds__(kThreads) graph_pre_bwd_kernel(GraphArgs a) {
     for (int o = tid; o < C * kH; o += kThreads) {
       const int c = o >> 6, k = o & 63;
       float acc = 0.f;
-      for (int n = 0; n < kH; ++n) acc = fmaf(s.b[c * kH + n], a.wv1[(size_t)n * a.ldv + kH + k], acc);
+#pragma unroll 16
+      for (int n = 0; n < kH; ++n) acc = fmaf(s.b[c * kH + n], V1s[n * kWPad + k], acc);
       a.gS[(size_t)b * C * kH + o] += acc;
     }
     // gM[d][c] = sum_n V1m[n][d] gG1[c][n]
@@ -285,24 +326,38 @@ __global__ void __launch_bounds__(kThreads) graph_pre_bwd_kernel(GraphArgs a) {
   }
 }
 
+#define FEGNN_GRAPH_SMEM(kernel)                                                                              \
+  do {                                                                                                       \
+    static bool done_ = false;                                                                               \
+    if (!done_) {                                                                                            \
+      cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphSmemBytes); \
+      if (e_ != cudaSuccess) return e_;                                                                      \
+      done_ = true;                                                                                          \
+    }                                                                                                        \
+  } while (0)
+
 cudaError_t launch_graph_pre_fwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_pre_fwd_kernel<<<a.B, kThreads, 0, st>>>(a); ++g_launches;
+  FEGNN_GRAPH_SMEM(graph_pre_fwd_kernel);
+  graph_pre_fwd_kernel<<<a.B, kThreads, kGraphSmemBytes, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_post_fwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_post_fwd_kernel<<<a.B, kThreads, 0, st>>>(a); ++g_launches;
+  FEGNN_GRAPH_SMEM(graph_post_fwd_kernel);
+  graph_post_fwd_kernel<<<a.B, kThreads, kGraphSmemBytes, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_post_bwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_post_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a); ++g_launches;
+  FEGNN_GRAPH_SMEM(graph_post_bwd_kernel);
+  graph_post_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, kGraphSmemBytes, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_pre_bwd(const GraphArgs& a, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  graph_pre_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, 0, st>>>(a); ++g_launches;
+  FEGNN_GRAPH_SMEM(graph_pre_bwd_kernel);
+  graph_pre_bwd_kernel<<<a.B < 32 ? a.B : 32, kThreads, kGraphSmemBytes, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 

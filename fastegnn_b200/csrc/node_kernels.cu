@@ -285,45 +285,50 @@ __device__ __forceinline__ void load_tile_rowscaled(float* __restrict__ T, const
 
 constexpr size_t kNodeHSmem = (kWFloats + 2 * kTileFloats) * sizeof(float);
 
-__global__ void __launch_bounds__(kThreads, 1) node_h_fwd_kernel(NodeHArgs a) {
+// zh1 += [Uh +] W_blk A_blk for one (node tile, K-block) work item; zh1 is zero-filled by the launcher and
+// accumulated with red.global.add.v4.f32 (block 0 = message mean + the h term Uh, block 1+c = u[:,c,:]).
+__global__ void __launch_bounds__(kThreads, 2) node_h_z_kernel(NodeHArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;
+  float* T0 = Ws + kWFloats;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int nblk = a.C + 1;
+  const int blk = blockIdx.x % nblk, cta = blockIdx.x / nblk, nctas = gridDim.x / nblk;
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
+  else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
+  for (int tile = cta; tile < ntiles; tile += nctas) {
+    const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
+    __syncthreads();
+    if (blk == 0) load_tile_rowscaled(T0, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
+    else load_tile(T0, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
+    __syncthreads();
+    float acc[kRT][4];
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      const int r = ty * kRT + i;
+      float4 g0 = make_float4(0, 0, 0, 0);
+      if (blk == 0 && r < nvalid) g0 = *reinterpret_cast<const float4*>(a.Uh + (size_t)(i0 + r) * kH + tx * 4);
+      acc[i][0] = g0.x; acc[i][1] = g0.y; acc[i][2] = g0.z; acc[i][3] = g0.w;
+    }
+    gemm_nt(acc, T0, Ws, ty, tx);
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      const int r = ty * kRT + i;
+      if (r < nvalid)
+        atomicAdd(reinterpret_cast<float4*>(a.zh1 + (size_t)(i0 + r) * kH + tx * 4),
+                  make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  }
+}
+
+// h' = h + U2 silu(zh1) + e2
+__global__ void __launch_bounds__(kThreads, 2) node_h_out_kernel(NodeHArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
   float* T0 = Ws + kWFloats;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int ntiles = (a.N + kTM - 1) / kTM;
-  // zh1 = Uh + U1a mmean + sum_c U1u_c u_c     (accumulated in place in zh1, block by block)
-#pragma unroll 1
-  for (int blk = 0; blk <= a.C; ++blk) {
-    __syncthreads();
-    if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
-    else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
-      __syncthreads();
-      if (blk == 0) load_tile_rowscaled(T0, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
-      else load_tile(T0, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
-      __syncthreads();
-      const float* init = blk == 0 ? a.Uh : a.zh1;
-      float acc[kRT][4];
-#pragma unroll
-      for (int i = 0; i < kRT; ++i) {
-        const int r = ty * kRT + i;
-        float4 g0 = make_float4(0, 0, 0, 0);
-        if (r < nvalid) g0 = *reinterpret_cast<const float4*>(init + (size_t)(i0 + r) * kH + tx * 4);
-        acc[i][0] = g0.x; acc[i][1] = g0.y; acc[i][2] = g0.z; acc[i][3] = g0.w;
-      }
-      gemm_nt(acc, T0, Ws, ty, tx);
-#pragma unroll
-      for (int i = 0; i < kRT; ++i) {
-        const int r = ty * kRT + i;
-        if (r < nvalid)
-          *reinterpret_cast<float4*>(a.zh1 + (size_t)(i0 + r) * kH + tx * 4) =
-              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      }
-    }
-  }
-  // h' = h + U2 silu(zh1) + e2
-  __syncthreads();
   stage_weight(Ws, a.node_w2, kH, 0, 1);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
@@ -355,88 +360,93 @@ __global__ void __launch_bounds__(kThreads, 1) node_h_fwd_kernel(NodeHArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) node_h_bwd_kernel(NodeHArgs a) {
+// backward pass 1: gzh1 = (gh' U2) * silu'(zh1) ; dU2 += gh'^T silu(zh1) ; de2 += sum gh'
+__global__ void __launch_bounds__(kThreads, 2) node_h_bwd1_kernel(NodeHArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
   float* T0 = Ws + kWFloats;
   float* T1 = T0 + kTileFloats;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int ntiles = (a.N + kTM - 1) / kTM;
-  // pass 1: gzh1 = (gh' U2) * silu'(zh1) ; dU2 += gh'^T silu(zh1) ; de2 += sum gh'
-  {
-    stage_weight(Ws, a.node_w2, kH, 0, 1);
-    float wg[4][4], bs[4] = {0, 0, 0, 0};
-    zero_wg(wg);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
-      __syncthreads();
-      load_tile(T0, a.gh_new + (size_t)i0 * kH, kH, nvalid);
-      for (int i = tid; i < kTM * 16; i += kThreads) {
-        int r = i >> 4, c4 = i & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nvalid) {
-          v = *reinterpret_cast<const float4*>(a.zh1 + (size_t)(i0 + r) * kH + c4 * 4);
-          v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
-        }
-        *reinterpret_cast<float4*>(T1 + r * kH + c4 * 4) = v;
-      }
-      __syncthreads();
-      float acc[kRT][4];
-      zero_acc(acc);
-      gemm_nn(acc, T0, Ws, ty, tx);
-#pragma unroll
-      for (int i = 0; i < kRT; ++i) {
-        const int r = ty * kRT + i;
-        if (r < nvalid) {
-          float4 z = *reinterpret_cast<const float4*>(a.zh1 + (size_t)(i0 + r) * kH + tx * 4);
-          float av, d0, d1, d2, d3;
-          silu_grad_f(z.x, av, d0); silu_grad_f(z.y, av, d1); silu_grad_f(z.z, av, d2); silu_grad_f(z.w, av, d3);
-          *reinterpret_cast<float4*>(a.gzh1 + (size_t)(i0 + r) * kH + tx * 4) =
-              make_float4(acc[i][0] * d0, acc[i][1] * d1, acc[i][2] * d2, acc[i][3] * d3);
-        }
-      }
-      wgrad_acc_bias(wg, bs, T0, T1, kTM);
-    }
-    wgrad_flush(wg, a.g_node_w2, kH, 0, 1);
-    bias_flush(bs, a.g_node_b2);
-  }
-  // pass 2 .. 2+C: block 0 = U1a (message mean), block 1+c = U1u_c (virtual message of channel c)
-#pragma unroll 1
-  for (int blk = 0; blk <= a.C; ++blk) {
+  stage_weight(Ws, a.node_w2, kH, 0, 1);
+  float wg[4][4], bs[4] = {0, 0, 0, 0};
+  zero_wg(wg);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
-    if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
-    else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
-    float wg[4][4];
-    zero_wg(wg);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
-      __syncthreads();
-      load_tile(T0, a.gzh1 + (size_t)i0 * kH, kH, nvalid);
-      if (blk == 0) load_tile_rowscaled(T1, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
-      else load_tile(T1, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
-      __syncthreads();
-      float acc[kRT][4];
-      zero_acc(acc);
-      gemm_nn(acc, T0, Ws, ty, tx);
+    load_tile(T0, a.gh_new + (size_t)i0 * kH, kH, nvalid);
+    for (int i = tid; i < kTM * 16; i += kThreads) {
+      int r = i >> 4, c4 = i & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nvalid) {
+        v = *reinterpret_cast<const float4*>(a.zh1 + (size_t)(i0 + r) * kH + c4 * 4);
+        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+      }
+      *reinterpret_cast<float4*>(T1 + r * kH + c4 * 4) = v;
+    }
+    __syncthreads();
+    float acc[kRT][4];
+    zero_acc(acc);
+    gemm_nn(acc, T0, Ws, ty, tx);
 #pragma unroll
-      for (int i = 0; i < kRT; ++i) {
-        const int r = ty * kRT + i;
-        if (r < nvalid) {
-          if (blk == 0) {
-            const float s = a.dinv[i0 + r];
-            *reinterpret_cast<float4*>(a.gm + (size_t)(i0 + r) * kH + tx * 4) =
-                make_float4(acc[i][0] * s, acc[i][1] * s, acc[i][2] * s, acc[i][3] * s);
-          } else {
-            *reinterpret_cast<float4*>(a.gu + ((size_t)(i0 + r) * a.C + (blk - 1)) * kH + tx * 4) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-          }
+    for (int i = 0; i < kRT; ++i) {
+      const int r = ty * kRT + i;
+      if (r < nvalid) {
+        float4 z = *reinterpret_cast<const float4*>(a.zh1 + (size_t)(i0 + r) * kH + tx * 4);
+        float av, d0, d1, d2, d3;
+        silu_grad_f(z.x, av, d0); silu_grad_f(z.y, av, d1); silu_grad_f(z.z, av, d2); silu_grad_f(z.w, av, d3);
+        *reinterpret_cast<float4*>(a.gzh1 + (size_t)(i0 + r) * kH + tx * 4) =
+            make_float4(acc[i][0] * d0, acc[i][1] * d1, acc[i][2] * d2, acc[i][3] * d3);
+      }
+    }
+    wgrad_acc_bias(wg, bs, T0, T1, kTM);
+  }
+  wgrad_flush(wg, a.g_node_w2, kH, 0, 1);
+  bias_flush(bs, a.g_node_b2);
+}
+
+// backward pass 2, one (node tile, K-block) work item: block 0 -> gm and dU1a, block 1+c -> gu[:,c,:] and dU1u_c
+__global__ void __launch_bounds__(kThreads, 2) node_h_bwd2_kernel(NodeHArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;
+  float* T0 = Ws + kWFloats;
+  float* T1 = T0 + kTileFloats;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int nblk = a.C + 1;
+  const int blk = blockIdx.x % nblk, cta = blockIdx.x / nblk, nctas = gridDim.x / nblk;
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
+  else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
+  float wg[4][4];
+  zero_wg(wg);
+  for (int tile = cta; tile < ntiles; tile += nctas) {
+    const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
+    __syncthreads();
+    load_tile(T0, a.gzh1 + (size_t)i0 * kH, kH, nvalid);
+    if (blk == 0) load_tile_rowscaled(T1, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
+    else load_tile(T1, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
+    __syncthreads();
+    float acc[kRT][4];
+    zero_acc(acc);
+    gemm_nn(acc, T0, Ws, ty, tx);
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+      const int r = ty * kRT + i;
+      if (r < nvalid) {
+        if (blk == 0) {
+          const float sc = a.dinv[i0 + r];
+          *reinterpret_cast<float4*>(a.gm + (size_t)(i0 + r) * kH + tx * 4) =
+              make_float4(acc[i][0] * sc, acc[i][1] * sc, acc[i][2] * sc, acc[i][3] * sc);
+        } else {
+          *reinterpret_cast<float4*>(a.gu + ((size_t)(i0 + r) * a.C + (blk - 1)) * kH + tx * 4) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
       }
-      wgrad_acc(wg, T0, T1, kTM);
     }
-    if (blk == 0) wgrad_flush(wg, a.g_node_w0, a.ldn, kH, 1);
-    else wgrad_flush(wg, a.g_node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
+    wgrad_acc(wg, T0, T1, kTM);
   }
+  if (blk == 0) wgrad_flush(wg, a.g_node_w0, a.ldn, kH, 1);
+  else wgrad_flush(wg, a.g_node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
 }
 
 // ------------------------------------------------------------------------------------------- launchers
@@ -496,17 +506,37 @@ cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
-  FEGNN_SET_SMEM(node_h_fwd_kernel, kNodeHSmem);
+  FEGNN_SET_SMEM(node_h_z_kernel, kNodeHSmem);
+  {
+    static bool done2_ = false;
+    if (!done2_) {
+      cudaError_t e_ = cudaFuncSetAttribute(node_h_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeHSmem);
+      if (e_ != cudaSuccess) return e_;
+      done2_ = true;
+    }
+  }
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_h_fwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  cudaError_t e = cudaMemsetAsync(a.zh1, 0, sizeof(float) * kH * (size_t)a.N, st);
+  if (e != cudaSuccess) return e;
+  node_h_z_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  node_h_out_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
-  FEGNN_SET_SMEM(node_h_bwd_kernel, kNodeHSmem);
+  FEGNN_SET_SMEM(node_h_bwd1_kernel, kNodeHSmem);
+  {
+    static bool done2_ = false;
+    if (!done2_) {
+      cudaError_t e_ = cudaFuncSetAttribute(node_h_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeHSmem);
+      if (e_ != cudaSuccess) return e_;
+      done2_ = true;
+    }
+  }
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_h_bwd_kernel<<<persistent_grid(ntiles, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  node_h_bwd1_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  node_h_bwd2_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   return cudaGetLastError();
 }
 
