@@ -13,10 +13,11 @@
 // row-major ones, so no MN-major descriptors are needed.  Thread (warp, lane) owns edge row
 // (warp&3)*32+lane (= its TMEM lane) and the 32 columns of half (warp>>2); column sums (bias and
 // vector gradients) use a 31-shuffle transpose-reduce per warp; row-segment sums (gP) walk the tile.
-// silu'(z1) is recomputed in the last epilogue from a re-gather of P[row], Q[col] (L2-resident).
+// silu'(z1) is kept as an fp16 tile from the assembly for the last epilogue (TF32-grade anyway).
 // attention=True layers use the fp32 FMA kernel.
 #include "common.cuh"
 #include "umma.cuh"
+#include <cuda_fp16.h>
 
 namespace fegnn {
 
@@ -37,7 +38,8 @@ struct EdgeTcBwdSmem {
   static constexpr int off_X1 = off_X0 + kT; // a1 -> g3 -> g2 -> gz1      [128][64]
   static constexpr int off_X2 = off_X1 + kT; // m  -> g3^T -> g2^T
   static constexpr int off_X3 = off_X2 + kT; // m^T                        [64][128]
-  static constexpr int off_vec = off_X3 + kT;
+  static constexpr int off_D1 = off_X3 + kT; // silu'(z1) as fp16 [128][64], 16-byte chunks swizzled by (row & 7)
+  static constexpr int off_vec = off_D1 + kTM * kH * 2;
   static constexpr size_t bytes = off_vec + sizeof(EdgeTcBwdVec) + 1024;
 };
 
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
   uint8_t* X1 = smem + SM::off_X1;
   uint8_t* X2 = smem + SM::off_X2;
   uint8_t* X3 = smem + SM::off_X3;
+  uint8_t* D1 = smem + SM::off_D1;
   uint32_t phase = 0;
   bool first_tile = true;
   // per-thread column accumulators (column half*32+lane, rows of this warp's quarter), flushed at the end
@@ -239,14 +242,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
               z0 = fmaf(ef, wf.x, z0); z1 = fmaf(ef, wf.y, z1); z2 = fmaf(ef, wf.z, z2); z3 = fmaf(ef, wf.w, z3);
             }
           }
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ri[j] >= 0) o = make_float4(tc_silu<1>(z0), tc_silu<1>(z1), tc_silu<1>(z2), tc_silu<1>(z3));
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f), od = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ri[j] >= 0) {
+            tc_silu_grad(z0, o.x, od.x); tc_silu_grad(z1, o.y, od.y);
+            tc_silu_grad(z2, o.z, od.z); tc_silu_grad(z3, o.w, od.w);
+          }
           *reinterpret_cast<float4*>(X1 + umma::tile_chunk_off(rr, l16, kTM)) = o;
-          // transposed: rows n = 4*l16 .. +3, column e = rr
-          *reinterpret_cast<float*>(X0 + umma::tile_off(4 * l16 + 0, rr, kH)) = o.x;
-          *reinterpret_cast<float*>(X0 + umma::tile_off(4 * l16 + 1, rr, kH)) = o.y;
-          *reinterpret_cast<float*>(X0 + umma::tile_off(4 * l16 + 2, rr, kH)) = o.z;
-          *reinterpret_cast<float*>(X0 + umma::tile_off(4 * l16 + 3, rr, kH)) = o.w;
+          // silu'(z1) kept as fp16 for the last epilogue: row rr, 8-byte slot l16 of the swizzled 128-byte row
+          __half2 h01 = __floats2half2_rn(od.x, od.y), h23 = __floats2half2_rn(od.z, od.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h01);
+          pk.y = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(D1 + rr * 128 + ((((l16 >> 1) ^ (rr & 7)) << 4) | ((l16 & 1) << 3))) = pk;
         }
       }
     }
@@ -257,6 +264,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
       umma::fence_after();
       tc_gemm(tmem + 0, sX1, kTM, sW2, kH, 8, idesc128, false);             // G1
       umma::commit(&v->bar[0]);
+    }
+    // a1^T -> X0 while G1 runs: each thread re-reads its own row segment (read-only on X1) and writes it
+    // edge-transposed (conflict-free: lanes are consecutive edges)
+    {
+      const uint32_t ebase = (uint32_t)((row >> 5) * (kH * 128) + ((row & 3) << 2) + half * 4096);
+      const int ech = (row & 31) >> 2;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 q4 = *reinterpret_cast<const float4*>(X1 + umma::tile_chunk_off(row, half * 8 + ch, kTM));
+        const float vv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = ch * 4 + k;
+          *reinterpret_cast<float*>(X0 + ebase + (j >> 3) * 1024 + (j & 7) * 128 + ((ech ^ (j & 7)) << 4)) = vv[k];
+        }
+      }
     }
     umma::mbar_wait(&v->bar[0], phase);
     umma::fence_after();
@@ -362,29 +385,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
       float gq = 0.f;
       if (r >= 0) {
         const int c = v->scol[row];
-        const float q = v->sq[row];
-        const float4* Pr = reinterpret_cast<const float4*>(a.P + (size_t)r * kH + half * 32);
-        const float4* Qc = reinterpret_cast<const float4*>(a.Q + (size_t)c * kH + half * 32);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const float4 p = Pr[ch], qq = Qc[ch];
-          float z[4] = {p.x + qq.x, p.y + qq.y, p.z + qq.z, p.w + qq.w};
+        for (int c16 = 0; c16 < 4; ++c16) {          // 16-byte chunks (8 halves) of this thread's 64-byte d1 segment
+          const uint4 pk = *reinterpret_cast<const uint4*>(D1 + row * 128 + (((half * 4 + c16) ^ (row & 7)) << 4));
+          const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int n = half * 32 + ch * 4 + k;
-            z[k] = fmaf(q, v->wq[n], z[k]);
-#pragma unroll
-            for (int f = 0; f < kTcMaxFe; ++f)
-              if (f < a.Fe) z[k] = fmaf(v->sea[row * kTcMaxFe + f], v->Wa[f * kH + n], z[k]);
-            float a1, d1;
-            tc_silu_grad(z[k], a1, d1);
-            const float g = g1v[ch * 4 + k] * d1;
-            g1v[ch * 4 + k] = g;
-            gq = fmaf(g, v->wq[n], gq);
+            const float2 dd = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            const int j = c16 * 8 + k * 2;
+            g1v[j] *= dd.x;
+            g1v[j + 1] *= dd.y;
+            gq = fmaf(g1v[j], v->wq[half * 32 + j], gq);
+            gq = fmaf(g1v[j + 1], v->wq[half * 32 + j + 1], gq);
           }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
           atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + half * 32 + ch * 4),
                     make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
-        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) g1v[j] = 0.f;
