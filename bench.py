@@ -278,7 +278,9 @@ def main():
     torch.manual_seed(0)
     model = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=H, virtual_channels=C, device=dev,
                      n_layers=LAYERS, gravity=data["gravity"])
-    use_graph = not args.no_graph and world == 1     # NCCL collectives are kept out of graph capture
+    # one rank or whole graphs per rank: the step (incl. the weight-gradient all-reduce, which NCCL lets a stream
+    # capture record) is ONE CUDA graph; the partitioned path keeps its per-layer collectives eager
+    use_graph = not args.no_graph and not part
     opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-12, capturable=use_graph)
     params = [p for p in model.parameters()]
     gen = torch.Generator().manual_seed(0)

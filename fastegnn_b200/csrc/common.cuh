@@ -44,9 +44,31 @@ __device__ __forceinline__ int wswz(int n, int k) { return n * kH + ((((k >> 2) 
 // element (n,k) = g[n*ld + off + k*kstride]
 __device__ __forceinline__ void stage_weight(float* __restrict__ Ws, const float* __restrict__ g, int ld, int off,
                                              int kstride) {
-  for (int i = threadIdx.x; i < kWFloats; i += kThreads) {
-    int n = i >> 6, k = i & 63;
-    Ws[wswz(n, k)] = g[(size_t)n * ld + off + (size_t)k * kstride];
+  // Every load of a thread is issued before the first store (one global-memory round trip per tile, not 16).
+  if (kstride == 1 && ((ld | off) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    float4 w[kWFloats / 4 / kThreads];
+#pragma unroll
+    for (int j = 0; j < kWFloats / 4 / kThreads; ++j) {
+      const int i = threadIdx.x + j * kThreads, n = i >> 4, c = i & 15;
+      w[j] = *reinterpret_cast<const float4*>(g + (size_t)n * ld + off + c * 4);
+    }
+#pragma unroll
+    for (int j = 0; j < kWFloats / 4 / kThreads; ++j) {
+      const int i = threadIdx.x + j * kThreads, n = i >> 4, c = i & 15;
+      *reinterpret_cast<float4*>(Ws + n * kH + ((c ^ ((n >> 2) & 7)) << 2)) = w[j];
+    }
+    return;
+  }
+  float w[kWFloats / kThreads];
+#pragma unroll
+  for (int j = 0; j < kWFloats / kThreads; ++j) {
+    const int i = threadIdx.x + j * kThreads, n = i >> 6, k = i & 63;
+    w[j] = g[(size_t)n * ld + off + (size_t)k * kstride];
+  }
+#pragma unroll
+  for (int j = 0; j < kWFloats / kThreads; ++j) {
+    const int i = threadIdx.x + j * kThreads, n = i >> 6, k = i & 63;
+    Ws[wswz(n, k)] = w[j];
   }
 }
 __device__ __forceinline__ void stage_vec(float* __restrict__ s, const float* __restrict__ g, int n, int stride = 1) {
@@ -140,6 +162,13 @@ __device__ __forceinline__ void wgrad_flush(const float (&wg)[4][4], float* __re
                                             int kstride) {
   if (dst == nullptr) return;
   const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;
+  if (kstride == 1 && ((ld | off) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)      // one red.global.add.v4.f32 per 4 consecutive k
+      atomicAdd(reinterpret_cast<float4*>(dst + (size_t)(tn * 4 + jn) * ld + off + tk * 4),
+                make_float4(wg[jn][0], wg[jn][1], wg[jn][2], wg[jn][3]));
+    return;
+  }
 #pragma unroll
   for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
@@ -164,8 +193,38 @@ __device__ __forceinline__ float warpsum(float v) {
 // reduced over the 16 ty-threads with atomics at kernel end.
 __device__ __forceinline__ void colsum_flush(const float (&cs)[4], float* __restrict__ dst, int stride, int tx) {
   if (dst == nullptr) return;
+  // the two half-warps of a warp hold the same columns (ty even / odd): add them first
 #pragma unroll
-  for (int j = 0; j < 4; ++j) atomicAdd(dst + (size_t)(tx * 4 + j) * stride, cs[j]);
+  for (int j = 0; j < 4; ++j) {
+    const float v = cs[j] + __shfl_xor_sync(0xffffffffu, cs[j], 16);
+    if ((threadIdx.x & 16) == 0) atomicAdd(dst + (size_t)(tx * 4 + j) * stride, v);
+  }
+}
+
+// Shared-memory form for kernels with many column-sum vectors: vector v of every thread is stashed in
+// scratch[v][ty][64] (NV * 1024 floats), then 64 threads per vector add the 16 ty-partials and issue ONE atomic per
+// column and CTA.  All threads must call; a __syncthreads() is needed before scratch is reused.
+struct ColsumDst {
+  float* dst;
+  int stride;
+};
+__device__ __forceinline__ void colsum_stash(float* __restrict__ scratch, int v, const float (&cs)[4]) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  *reinterpret_cast<float4*>(scratch + v * (16 * kH) + ty * kH + tx * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+}
+template <int NV>
+__device__ __forceinline__ void colsum_emit(const float* __restrict__ scratch, const ColsumDst (&d)[NV]) {
+  __syncthreads();
+  const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if ((v & 3) == grp && d[v].dst != nullptr) {
+      float sum = 0.f;
+#pragma unroll
+      for (int ty = 0; ty < 16; ++ty) sum += scratch[v * (16 * kH) + ty * kH + col];
+      atomicAdd(d[v].dst + (size_t)col * d[v].stride, sum);
+    }
+  }
 }
 
 // Segmented inclusive sum inside a warp over lanes with equal, contiguous keys.

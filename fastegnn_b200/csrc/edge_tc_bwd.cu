@@ -480,14 +480,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
     umma::tmem_ld32(tlane + 256, w);
     if (lane < 16 && a.g_W3 != nullptr) {
       const int n = quarter * 16 + lane;
+      float* dst = a.g_W3 + (size_t)n * kH + half * 32;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(a.g_W3 + (size_t)n * kH + half * 32 + j, w[j]);
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, w[j]);
+      }
     }
     umma::tmem_ld32(tlane + 320, w);
     if (lane < 16 && a.g_W2 != nullptr) {
       const int n = quarter * 16 + lane;
+      float* dst = a.g_W2 + (size_t)n * kH + half * 32;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(a.g_W2 + (size_t)n * kH + half * 32 + j, w[j]);
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, w[j]);
+      }
     }
     const int n = half * 32 + lane;
     if (a.g_w4 != nullptr) atomicAdd(a.g_w4 + n, c_w4);

@@ -542,14 +542,15 @@ __global__ void __launch_bounds__(kThreads, 1) virtual_bwd_kernel(VirtArgs a) {
   wgrad_flush(wgV2, a.g_V2, kH, 0, 1);
   wgrad_flush(wgWxv, a.g_Wxv, kH, 0, 1);
   wgrad_flush(wgWX, a.g_WX, kH, 0, 1);
-  colsum_flush(cwxv, a.g_wxv, 1, tx);
-  colsum_flush(cbxv, a.g_bxv, 1, tx);
-  colsum_flush(cwX, a.g_wX, 1, tx);
-  colsum_flush(cbX, a.g_bX, 1, tx);
-  colsum_flush(cc2, a.g_c2, 1, tx);
-  if (a.g_wv1 != nullptr) colsum_flush(cvr, a.g_wv1 + 2 * kH, a.ldv, tx);
+  {
+    __syncthreads();                       // T0 is free: every tile is finished
+    colsum_stash(T0, 0, cwxv); colsum_stash(T0, 1, cbxv); colsum_stash(T0, 2, cwX); colsum_stash(T0, 3, cbX);
+    colsum_stash(T0, 4, cc2); colsum_stash(T0, 5, cvr); colsum_stash(T0, 6, cwav);
+    const ColsumDst dsts[7] = {{a.g_wxv, 1}, {a.g_bxv, 1}, {a.g_wX, 1}, {a.g_bX, 1}, {a.g_c2, 1},
+                               {a.g_wv1 != nullptr ? a.g_wv1 + 2 * kH : nullptr, a.ldv}, {att ? a.g_wav : nullptr, 1}};
+    colsum_emit<7>(T0, dsts);
+  }
   if (att) {
-    colsum_flush(cwav, a.g_wav, 1, tx);
     if (tx == 0 && a.g_bav != nullptr) atomicAdd(a.g_bav, cbav);
   }
 }
