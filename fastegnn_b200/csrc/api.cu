@@ -9,6 +9,7 @@
 #include "edge_kernels.cu"
 #include "edge_tc.cu"
 #include "edge_tc_bwd.cu"
+#include "edge_tc_bwd2.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "mmd.cu"
@@ -166,7 +167,7 @@ int fegnn_set_mode(const char* phase, int mode) {
     return 0;
   }
   if (strcmp(phase, "edge_backward") == 0) {
-    if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "edge_backward mode must be 0 or 1");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 4) return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2 or 4");
     g_edge_bwd_mode = mode;
     return 0;
   }
@@ -360,7 +361,9 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   CK(cudaMemsetAsync(gP, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
   CK(cudaMemsetAsync(gQ, 0, sizeof(float) * kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
-  if (g_edge_bwd_mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
+  if (g_edge_bwd_mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
+  else if (g_edge_bwd_mode == 4 && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
+  else if (g_edge_bwd_mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
   else CK(launch_edge_bwd(a, sm_count(), S(stream)));
   return 0;
 }
