@@ -136,7 +136,7 @@ def set_precision(name: str) -> None:
     """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase runs on
     tcgen05 TF32 tiles, forward and backward (stated tolerance).  "tf32x3": TF32 backward, 3xTF32
     (fp32-grade) forward."""
-    table = {"fp32": (0, 0), "tf32": (1, 1), "tf32x3": (3, 1)}
+    table = {"fp32": (0, 0), "tf32": (1, 4), "tf32x3": (3, 4)}
     fwd, bwd = table[name]
     set_mode("edge_forward", fwd)
     set_mode("edge_backward", bwd)

@@ -46,8 +46,9 @@ int fail(int code, const char* fmt, ...) {
 
 // 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32, 3 = tcgen05 3xTF32 (fp32-grade)
 int g_edge_fwd_mode = 1;
-// 0 = fp32 FMA kernel, 1 = tcgen05 single-pass TF32
-int g_edge_bwd_mode = 1;
+// 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands
+// and MN-major weight-gradient operands (256 / 512 threads per tile)
+int g_edge_bwd_mode = 4;
 
 int sm_count() {
   static int sms = 0;

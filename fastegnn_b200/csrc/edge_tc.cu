@@ -86,11 +86,11 @@ __device__ __forceinline__ void tc_store_chunk(uint8_t* tile, int row, int c, fl
 
 // D = A W^T with A (hi[,lo]) at a_tile and W (hi[,lo]) at w_tile
 template <int SPLIT>
-__device__ __forceinline__ void tc_issue_gemm(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, uint32_t idesc) {
-  umma::gemm_k64(tmem_d, a_tile, kTM, w_tile, kH, idesc, false);
+__device__ __forceinline__ void tc_issue_gemm(uint32_t tmem_d, uint64_t a_desc, uint64_t w_desc, uint32_t idesc) {
+  umma::gemm_k64_desc(tmem_d, a_desc, kTM, w_desc, kH, idesc, false);
   if (SPLIT == 3) {
-    umma::gemm_k64(tmem_d, a_tile + EdgeTcSmem<SPLIT>::kT, kTM, w_tile, kH, idesc, true);
-    umma::gemm_k64(tmem_d, a_tile, kTM, w_tile + EdgeTcSmem<SPLIT>::kW, kH, idesc, true);
+    umma::gemm_k64_desc(tmem_d, a_desc + (uint64_t)(EdgeTcSmem<SPLIT>::kT >> 4), kTM, w_desc, kH, idesc, true);
+    umma::gemm_k64_desc(tmem_d, a_desc, kTM, w_desc + (uint64_t)(EdgeTcSmem<SPLIT>::kW >> 4), kH, idesc, true);
   }
 }
 
@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 32;
   const uint32_t idesc = umma::make_idesc_tf32(128, 64);
-  const uint32_t sW2 = umma::smem_u32(smem + SM::off_W2), sW3 = umma::smem_u32(smem + SM::off_W3);
-  const uint32_t sA = umma::smem_u32(smem + SM::off_A);
+  const uint64_t dW2 = umma::make_desc(umma::smem_u32(smem + SM::off_W2)), dW3 = umma::make_desc(umma::smem_u32(smem + SM::off_W3));
+  const uint64_t dA = umma::make_desc(umma::smem_u32(smem + SM::off_A));
   uint8_t* At = smem + SM::off_A;
   uint32_t phase = 0;
 
@@ -222,10 +222,13 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (warp == 0) {
       umma::fence_after();
-      tc_issue_gemm<SPLIT>(tmem, sA, sW2, idesc);
-      umma::commit(&v->bar[0]);
+      if (umma::elect_one()) {
+        tc_issue_gemm<SPLIT>(tmem, dA, dW2, idesc);
+        umma::commit(&v->bar[0]);
+      }
+      __syncwarp();
     }
     umma::mbar_wait(&v->bar[0], phase);
     umma::fence_after();
@@ -257,10 +260,13 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (warp == 0) {
       umma::fence_after();
-      tc_issue_gemm<SPLIT>(tmem + 64, sA, sW3, idesc);
-      umma::commit(&v->bar[1]);
+      if (umma::elect_one()) {
+        tc_issue_gemm<SPLIT>(tmem + 64, dA, dW3, idesc);
+        umma::commit(&v->bar[1]);
+      }
+      __syncwarp();
     }
     // ---- msum: column walk over the m tile while the tensor core runs (read-only on both sides).
     //      thread (col, grp) sums rows 32grp..32grp+31 of column col, one atomic per run of equal row ids.

@@ -60,6 +60,24 @@ __device__ __forceinline__ void gemm_k64(uint32_t tmem_d, uint32_t a_saddr, int 
   }
 }
 
+// Same GEMM from a descriptor built once per kernel: per MMA only the 14-bit start-address field moves (bytes >> 4;
+// no carry out of the field, shared memory is < 256 KB) -- one add per operand in the issuing thread.
+__device__ __forceinline__ void gemm_k64_desc(uint32_t tmem_d, uint64_t da, int a_rows, uint64_t db, int b_rows,
+                                              uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t aoff = (ks >> 2) * (a_rows * 128) + (ks & 3) * 32;
+    const uint32_t boff = (ks >> 2) * (b_rows * 128) + (ks & 3) * 32;
+    mma_tf32(tmem_d, da + (uint64_t)(aoff >> 4), db + (uint64_t)(boff >> 4), idesc, (ks > 0 || accumulate_first) ? 1u : 0u);
+  }
+}
+// one lane of a converged warp (the form under which the compiler keeps tcgen05.mma operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }

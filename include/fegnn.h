@@ -116,10 +116,11 @@ const char* fegnn_last_error(void);
 int fegnn_version(void);
 /* kernels launched by this library so far in this process (host-side counter; bench.py reports it) */
 unsigned long long fegnn_launch_count(void);
-/* Arithmetic mode of a phase: 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32 tiles, 3 = tcgen05
- * error-compensated 3xTF32 tiles (fp32-grade).  phase: "edge_forward" (0, 1, 3; default 1) or
- * "edge_backward" (0, 1; default 1).  Layers with attention=True or Fe > 4 always take mode 0 in the
- * backward (Fe > 4 also in the forward).  Process-wide. */
+/* Arithmetic mode of a phase.  "edge_forward": 0 = fp32 FMA kernel, 1 = tcgen05 single-pass TF32 tiles (default),
+ * 3 = tcgen05 error-compensated 3xTF32 tiles (fp32-grade).  "edge_backward": 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with
+ * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
+ * 256 / 512 threads per 128-edge tile (4 is the default).  Layers with attention=True or Fe > 4 always take mode 0 in
+ * the backward (Fe > 4 also in the forward).  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
 
