@@ -132,14 +132,17 @@ def set_mode(phase: str, mode: int) -> None:
     check(lib.fegnn_set_mode(phase.encode(), int(mode)), "fegnn_set_mode")
 
 
+PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward")
+
+
 def set_precision(name: str) -> None:
-    """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase runs on
-    tcgen05 TF32 tiles, forward and backward (stated tolerance).  "tf32x3": TF32 backward, 3xTF32
-    (fp32-grade) forward."""
-    table = {"fp32": (0, 0), "tf32": (1, 4), "tf32x3": (3, 4)}
-    fwd, bwd = table[name]
-    set_mode("edge_forward", fwd)
-    set_mode("edge_backward", bwd)
+    """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase and the
+    dense real<->virtual phase run on tcgen05 TF32 tiles, forward and backward (stated tolerance).
+    "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual phase)."""
+    table = {"fp32": (0, 0, 0, 0), "tf32": (1, 4, 1, DEFAULT_MODES["virtual_backward"]),
+             "tf32x3": (3, 4, 0, DEFAULT_MODES["virtual_backward"])}
+    for phase, mode in zip(PHASES, table[name]):
+        set_mode(phase, mode)
 
 
 def get_mode(phase: str) -> int:
@@ -152,9 +155,10 @@ def check(rc: int, what: str = "") -> None:
         raise FegnnError(f"{what or 'fegnn'} failed with code {rc}: {msg}")
 
 
+DEFAULT_MODES = {ph: get_mode(ph) for ph in PHASES}      # the library's built-in defaults
 if os.environ.get("FEGNN_PRECISION"):
     set_precision(os.environ["FEGNN_PRECISION"])
-for _phase in ("edge_forward", "edge_backward"):
+for _phase in PHASES:
     _env = os.environ.get("FEGNN_MODE_" + _phase.upper())
     if _env is not None:
         set_mode(_phase, int(_env))

@@ -15,6 +15,7 @@
 #include "mmd.cu"
 #include "node_kernels.cu"
 #include "virtual_kernels.cu"
+#include "virtual_tc.cu"
 
 using namespace fegnn;
 
@@ -49,6 +50,10 @@ int g_edge_fwd_mode = 1;
 // 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands
 // and MN-major weight-gradient operands (256 / 512 threads per tile)
 int g_edge_bwd_mode = 4;
+
+// 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
+int g_virt_fwd_mode = 1;
+int g_virt_bwd_mode = 0;
 
 int sm_count() {
   static int sms = 0;
@@ -172,11 +177,18 @@ int fegnn_set_mode(const char* phase, int mode) {
     g_edge_bwd_mode = mode;
     return 0;
   }
+  if (strcmp(phase, "virtual_forward") == 0 || strcmp(phase, "virtual_backward") == 0) {
+    if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "%s mode must be 0 or 1", phase);
+    (phase[8] == 'f' ? g_virt_fwd_mode : g_virt_bwd_mode) = mode;
+    return 0;
+  }
   return fail(FEGNN_EINVAL, "unknown phase '%s'", phase);
 }
 int fegnn_get_mode(const char* phase) {
   if (phase != nullptr && strcmp(phase, "edge_forward") == 0) return g_edge_fwd_mode;
   if (phase != nullptr && strcmp(phase, "edge_backward") == 0) return g_edge_bwd_mode;
+  if (phase != nullptr && strcmp(phase, "virtual_forward") == 0) return g_virt_fwd_mode;
+  if (phase != nullptr && strcmp(phase, "virtual_backward") == 0) return g_virt_bwd_mode;
   return -1;
 }
 
@@ -267,7 +279,8 @@ int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
   CK(cudaMemsetAsync(sv->Dsum, 0, sizeof(float) * 3 * d->C * (size_t)d->B, S(stream)));
   CK(cudaMemsetAsync(sv->Usum, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
   CK(cudaMemsetAsync(xsum_new, 0, sizeof(float) * 3 * (size_t)d->B, S(stream)));
-  CK(launch_virtual_fwd(a, sm_count(), S(stream)));
+  if (g_virt_fwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION)) CK(launch_virtual_fwd_tc<2>(a, sm_count(), S(stream)));
+  else CK(launch_virtual_fwd(a, sm_count(), S(stream)));
   return 0;
 }
 

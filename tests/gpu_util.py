@@ -20,13 +20,13 @@ TOLERANCES = {"fp32": (2e-5, 2e-4), "tf32x3": (2e-5, 2e-2), "tf32": (1e-2, 2e-2)
 @contextlib.contextmanager
 def precision(name):
     from fastegnn_b200 import _lib
-    old = (_lib.get_mode("edge_forward"), _lib.get_mode("edge_backward"))
+    old = {ph: _lib.get_mode(ph) for ph in _lib.PHASES}
     _lib.set_precision(name)
     try:
         yield TOLERANCES[name]
     finally:
-        _lib.set_mode("edge_forward", old[0])
-        _lib.set_mode("edge_backward", old[1])
+        for ph, m in old.items():
+            _lib.set_mode(ph, m)
 
 
 def make_graph_case(seed, sizes, deg, C, Fe=2, nf=2, L=4, gravity=None, attention=False, normalize=False,

@@ -307,3 +307,55 @@ def test_edge_backward_modes(name, mode, layer):
             fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
     bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
     assert not bad, bad
+
+
+VIRT_TOL = {0: 3e-5, 1: 4e-3}      # fp32 FMA kernels / tcgen05 TF32 tiles, relative to each tensor's max
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
+@pytest.mark.parametrize("layer", [0, 1])
+def test_virtual_forward_modes(name, mode, layer):
+    """fegnn_virtual_forward alone (fp32 FMA kernel vs tcgen05 TF32 kernel) against staged.virtual_fwd."""
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    l = layer
+    last = l == cfg.n_layers - 1
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"] | (L.F_LAST if last else 0), cfg.gravity)
+    ptrs = s["layer_ptrs"](s["gparams"], f"gcl_{l}")
+    sv = s["SavedBlock"](dims, dev)
+    sv.buf.zero_()
+    S_ = sm.saved[l]
+    x, Z, v = _g(S_["x"], dev), _g(S_["Z"], dev), s["v"]
+    sv.view("Av", (N, H)).copy_(_g(S_["npre"]["Av"], dev))
+    sv.view("G1", (B, Cc, H)).copy_(_g(S_["pre"]["G1"], dev))
+    sv.view("tsum", (N, 3)).copy_(_g(S_["e"]["tsum"], dev))
+    sv.view("sv", (N,)).copy_(_g(S_["npre"]["sv"], dev))
+    if cfg.gravity is not None:
+        sv.view("sg", (N,)).copy_(_g(S_["npre"]["sg"], dev))
+    x_new, xsum_new = torch.empty(N, 3, device=dev), torch.empty(B, 3, device=dev)
+    old = L.get_mode("virtual_forward")
+    try:
+        L.set_mode("virtual_forward", mode)
+        L.check(lib.fegnn_virtual_forward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), L.ptr(x), L.ptr(v), L.ptr(Z),
+                                          C.byref(sv.c), L.ptr(x_new), L.ptr(xsum_new), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("virtual_forward", old)
+    tol = VIRT_TOL[mode]
+    errs = []
+    _chk(errs, "x_new", x_new, S_["vf"]["x_new"], tol)
+    _chk(errs, "u", sv.view("u", (N, Cc, H)), S_["vf"]["u"], tol)
+    _chk(errs, "Dsum", sv.view("Dsum", (B, 3, Cc)), S_["vf"]["Dsum"], tol)
+    _chk(errs, "Usum", sv.view("Usum", (B, Cc, H)), S_["vf"]["Usum"], tol)
+    _chk(errs, "xsum_new", xsum_new, S_["vf"]["xsum_new"], tol)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/virtual_fwd_mode{mode}_{name}_l{l}.txt", "w") as fh:
+        for n_, e, t in errs:
+            fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
+    assert not bad, bad
