@@ -53,7 +53,7 @@ int g_edge_bwd_mode = 4;
 
 // 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
 int g_virt_fwd_mode = 1;
-int g_virt_bwd_mode = 0;
+int g_virt_bwd_mode = 1;
 
 int sm_count() {
   static int sms = 0;
@@ -358,7 +358,15 @@ int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegn
   a.g_wav = gr->attv_w; a.g_bav = gr->attv_b;
   CK(cudaMemsetAsync(gG1, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
   CK(cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)d->Nl, S(stream)));
-  CK(launch_virtual_bwd(a, sm_count(), S(stream)));
+  // tensor-core form: two kernels; `gu` doubles as the [N,C,H] scratch that carries the total dL/du between them
+  if (d->flags & FEGNN_F_LAST) a.gu = nullptr;        // last layer: phi_h is discarded, a gu buffer holds no input
+  if (g_virt_bwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION) && gu != nullptr) {
+    a.gu_work = const_cast<float*>(gu);
+    a.u = sv->u;                                       // the heads are recomputed from the saved u
+    CK(launch_virtual_bwd_tc<4>(a, sm_count(), S(stream)));
+  } else {
+    CK(launch_virtual_bwd(a, sm_count(), S(stream)));
+  }
   return 0;
 }
 
@@ -567,7 +575,7 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
                                   stream));
     if (!last) TRY(fegnn_node_h_backward(&dl, g, p, gr, sv, s.gh, s.gzh1, s.gm, s.gu, stream));
     TRY(fegnn_virtual_backward(&dl, g, p, gr, w.x[l], v, w.Z[l], sv, gx_new, gxsum_next, s.gDsum,
-                               last ? nullptr : s.gUsum, last ? nullptr : s.gu, s.gAv, s.gG1, s.gx[cur], s.gZ[cur],
+                               last ? nullptr : s.gUsum, s.gu, s.gAv, s.gG1, s.gx[cur], s.gZ[cur],
                                s.gsv, s.gsg, s.gt, stream));
     TRY(fegnn_edge_backward(&dl, g, p, gr, w.x[l], sv, last ? nullptr : s.gm, s.gt, s.gP, s.gQ, s.gx[cur], stream));
     TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[l], sv, s.gG1, s.gS[cur], s.gZ[cur], s.gxsum[cur], stream));

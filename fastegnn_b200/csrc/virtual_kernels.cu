@@ -21,6 +21,7 @@ struct VirtArgs {
   float *u, *x_new, *Dsum, *Usum, *xsum_new;
   // backward inputs
   const float *gx_new, *gxsum_next, *gDsum, *gUsum, *gu;
+  float* gu_work;              // tensor-core backward: [N,C,H] scratch (total dL/du between its two kernels)
   // backward outputs
   float *gAv, *gG1, *gx, *gZ, *gsv, *gsg, *gt;
   float *g_wv1, *g_V2, *g_c2, *g_Wxv, *g_bxv, *g_wxv, *g_WX, *g_bX, *g_wX, *g_wav, *g_bav;

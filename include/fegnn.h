@@ -120,7 +120,8 @@ unsigned long long fegnn_launch_count(void);
  * 3 = tcgen05 error-compensated 3xTF32 tiles (fp32-grade).  "edge_backward": 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with
  * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
  * 256 / 512 threads per 128-edge tile (4 is the default).  Layers with attention=True or Fe > 4 always take mode 0 in
- * the backward (Fe > 4 also in the forward).  Process-wide. */
+ * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
+ * TF32 kernels (default; attention=True layers always take 0).  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
 
@@ -185,7 +186,9 @@ int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegn
                            fegnn_layer_grads* gr, const float* x, const float* v, const float* Z,
                            const fegnn_layer_saved* sv, const float* gx_new /*[N,3]*/,
                            const float* gxsum_next /*[B,3] or NULL*/, const float* gDsum, const float* gUsum,
-                           const float* gu /*[N,C,H] or NULL (last layer)*/,
+                           const float* gu /*[N,C,H] or NULL; input dL/du from phi_h (ignored with FEGNN_F_LAST).  With
+                                             the tensor-core mode a non-NULL buffer is also used as scratch and OVERWRITTEN
+                                             (it carries the total dL/du between the two kernels); NULL selects the fp32 kernel*/,
                            float* gAv /*[N,H] =*/, float* gG1 /*[B,C,H] zeroed here, +=*/, float* gx /*[Nl,3] zeroed here, owned rows =*/,
                            float* gZ /*[B,3,C] +=*/, float* gsv /*[N] =*/, float* gsg /*[N] =*/, float* gt /*[N,3] =*/,
                            void* stream);

@@ -359,3 +359,74 @@ def test_virtual_forward_modes(name, mode, layer):
             fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
     bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
     assert not bad, bad
+
+
+VIRT_BWD_TOL = {0: (3e-5, 2e-4), 1: (6e-3, 6e-3)}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
+@pytest.mark.parametrize("layer", [0, 1])
+def test_virtual_backward_modes(name, mode, layer):
+    """fegnn_virtual_backward alone (fp32 FMA kernel vs the two tcgen05 TF32 kernels) against staged.virtual_bwd."""
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    l = layer
+    last = l == cfg.n_layers - 1
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"] | (L.F_LAST if last else 0), cfg.gravity)
+    prefix = f"gcl_{l}"
+    ptrs = s["layer_ptrs"](s["gparams"], prefix)
+    sv = s["SavedBlock"](dims, dev)
+    sv.buf.zero_()
+    S_, bs = sm.saved[l], sm.bsaved[l]
+    x, Z, v = _g(S_["x"], dev), _g(S_["Z"], dev), s["v"]
+    sv.view("Av", (N, H)).copy_(_g(S_["npre"]["Av"], dev))
+    sv.view("G1", (B, Cc, H)).copy_(_g(S_["pre"]["G1"], dev))
+    sv.view("u", (N, Cc, H)).copy_(_g(S_["vf"]["u"], dev))
+    sv.view("sv", (N,)).copy_(_g(S_["npre"]["sv"], dev))
+    if cfg.gravity is not None:
+        sv.view("sg", (N,)).copy_(_g(S_["npre"]["sg"], dev))
+    gviews = {k: torch.zeros_like(p) for k, p in s["gparams"].items() if k.startswith(prefix + ".")}
+    gr = s["layer_ptrs"](gviews, prefix)
+    a, b, c = bs["a"], bs["b"], bs["c"]
+    gx_new, gxsum_next = _g(bs["gx_new"], dev), _g(bs["gxsum_next"], dev)
+    gDsum_x, gUsum_x = _g(a["gDsum"], dev), _g(a["gUsum"], dev)
+    gu_x = torch.full((N, Cc, H), float("nan"), device=dev) if last else _g(b["gu"], dev)   # last layer: scratch only
+    e32 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.float32)
+    gAv, gG1, gx = e32(N, H), e32(B, Cc, H), e32(N, 3)
+    gsv, gsg, gt = e32(N), e32(N), e32(N, 3)
+    gZ_acc = _g(a["gZ"], dev)
+    old = L.get_mode("virtual_backward")
+    try:
+        L.set_mode("virtual_backward", mode)
+        L.check(lib.fegnn_virtual_backward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), C.byref(gr), L.ptr(x), L.ptr(v),
+                                           L.ptr(Z), C.byref(sv.c), L.ptr(gx_new), L.ptr(gxsum_next), L.ptr(gDsum_x),
+                                           None if last else L.ptr(gUsum_x), L.ptr(gu_x), L.ptr(gAv), L.ptr(gG1),
+                                           L.ptr(gx), L.ptr(gZ_acc), L.ptr(gsv), L.ptr(gsg), L.ptr(gt), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("virtual_backward", old)
+    tol, tol_w = VIRT_BWD_TOL[mode]
+    errs = []
+    _chk(errs, "gAv", gAv, c["gAv"], tol)
+    _chk(errs, "gG1", gG1, c["gG1"], tol)
+    _chk(errs, "gx", gx, c["gx"], tol)
+    _chk(errs, "gZ(acc)", gZ_acc, a["gZ"] + c["gZ"], tol)
+    _chk(errs, "gsv", gsv, c["gsv"], tol)
+    _chk(errs, "gt", gt, c["gt"], tol)
+    if cfg.gravity is not None:
+        _chk(errs, "gsg", gsg, c["gsg"], tol)
+    want = {}
+    staged._scatter_wg(want, prefix, c["wg"], sm.w[l], 64, Cc, cfg.edge_attr_nf)
+    for k, wv in want.items():
+        _chk(errs, "wgrad." + k, gviews[k], wv, tol_w)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/virtual_bwd_mode{mode}_{name}_l{l}.txt", "w") as fh:
+        for n_, e, t in errs:
+            fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
+    assert not bad, bad
