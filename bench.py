@@ -281,7 +281,8 @@ def main():
     # one rank or whole graphs per rank: the step (incl. the weight-gradient all-reduce, which NCCL lets a stream
     # capture record) is ONE CUDA graph; the partitioned path keeps its per-layer collectives eager
     use_graph = not args.no_graph and not part
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-12, capturable=use_graph)
+    from fastegnn_b200 import FusedAdam
+    opt = FusedAdam(model.parameters(), lr=5e-4, weight_decay=1e-12)      # torch.optim.Adam's step as one launch
     params = [p for p in model.parameters()]
     gen = torch.Generator().manual_seed(0)
     ns = min(hp["sample"] * C, min(data["sizes"]))
@@ -444,7 +445,11 @@ def main():
                                                "(CPU restatement of the reference's torch op chain)")
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph still references the communicator: skip the (occasionally hanging) NCCL teardown
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def phase_profile(model, t, dev, data, E, N, B, C, flush):

@@ -117,6 +117,7 @@ SIGNATURES = {
     "fegnn_model_backward_scratch_floats": (C.c_size_t, [_PD]),
     "fegnn_model_forward": (C.c_int, [_PD, i32, i32, _PG, _PP] + [vp] * 9 + [vp, C.c_size_t, vp]),
     "fegnn_model_backward": (C.c_int, [_PD, i32, i32, _PG, _PP, _PP] + [vp] * 11 + [vp, vp, C.c_size_t, vp]),
+    "fegnn_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float, vp]),
     "fegnn_mmd_forward": (C.c_int, [i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
     "fegnn_mmd_backward": (C.c_int, [i32, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
 }

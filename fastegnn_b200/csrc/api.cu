@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "adam.cu"
 #include "edge_kernels.cu"
 #include "edge_tc.cu"
 #include "edge_tc_bwd.cu"
@@ -594,6 +595,17 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf); ++g_launches;
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ optimizer step (utils/train.py:168-170)
+int fegnn_adam_step(int64_t n, float* p, const float* g, float* m, float* v, const unsigned char* live, float* step,
+                    float lr, double beta1, double beta2, float eps, float weight_decay, void* stream) {
+  RQ(n >= 0 && (n & 3) == 0 && step);
+  RQ(n == 0 || (p && g && m && v && live));
+  RQ(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(live) & 3) == 0);
+  CK(launch_adam(n, p, g, m, v, live, step, lr, beta1, beta2, eps, weight_decay, sm_count(), S(stream)));
   return 0;
 }
 

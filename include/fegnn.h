@@ -242,6 +242,14 @@ int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma,
                        const float* x, const float* Z, const int32_t* sample_idx, const float* gloss /*[1]*/,
                        float* gx /*[N,3] zeroed here*/, float* gZ /*[B,3,C] =*/, void* stream);
 
+/* ------------------------------------------------------------------ optimizer step
+ * torch.optim.Adam (amsgrad=False, maximize=False; utils/train.py:168-170, main_*.py optimizer construction) over ONE
+ * flat buffer: n floats (multiple of 4, 16-byte aligned pointers).  live[i] == 0 marks elements of parameters that
+ * received no gradient this step (torch skips such parameters).  `step` is a device float, incremented here.        */
+int fegnn_adam_step(int64_t n, float* p, const float* g, float* m, float* v, const unsigned char* live /*[n]*/,
+                    float* step /*[1] device*/, float lr, double beta1, double beta2, float eps, float weight_decay,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

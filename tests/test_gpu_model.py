@@ -264,3 +264,57 @@ def _adam_check():
     sd = m.state_dict()
     for k in ("gcl_3.node_mlp.0.weight", "gcl_3.node_mlp_virtual.2.bias"):
         assert torch.equal(sd[k].cpu(), params[k])
+
+
+def test_fused_adam_matches_torch_adam():
+    """FusedAdam (one launch over flat buffers) == torch.optim.Adam over 4 training steps of the model, including the
+    parameters that never receive a gradient (last layer's node_mlp*: skipped, state untouched), then 2 steps with
+    foreign (non-flat) gradients."""
+    from fastegnn_b200 import FusedAdam, _lib
+    cfg, params, inp = make_graph_case(seed=77, sizes=[60, 50], deg=6, C=3, L=3, gravity=[0, -1, 0])
+    _lib.set_precision("fp32")
+    try:
+        dev = "cuda:0"
+        ma, mb = build_gpu_model(cfg, params, dev), build_gpu_model(cfg, params, dev)
+        oa = torch.optim.Adam(ma.parameters(), lr=5e-3, weight_decay=1e-2)
+        ob = FusedAdam(mb.parameters(), lr=5e-3, weight_decay=1e-2)
+        g = {k: v.to(dev) for k, v in inp.items()}
+
+        def grads(m, opt):
+            opt.zero_grad(set_to_none=True)
+            x, Z = m(node_feat=g["node_feat"], node_loc=g["node_loc"], node_vel=g["node_vel"], edge_index=g["edge_index"],
+                     data_batch=g["data_batch"], loc_mean=g["loc_mean"], edge_attr=g["edge_attr"])
+            ((x * g["wx"]).sum() + (Z * g["wz"]).sum()).backward()
+        for _ in range(4):
+            grads(ma, oa)
+            grads(mb, ob)
+            # identical gradient VALUES for both optimizers (Adam's first steps are sign-like: atomics-order noise in
+            # near-zero gradients would otherwise flip updates), written in place so mb keeps its flat gradient buffer
+            for pa, pb in zip(ma.parameters(), mb.parameters()):
+                assert (pa.grad is None) == (pb.grad is None)
+                if pa.grad is not None:
+                    pb.grad.copy_(pa.grad)
+            assert ob._flat_grad_ptr(list(mb.parameters())) is not None
+            oa.step()
+            ob.step()
+        gen = torch.Generator(device=dev).manual_seed(5)
+        for _ in range(2):
+            for pa, pb in zip(ma.parameters(), mb.parameters()):
+                if pa.grad is None:
+                    continue
+                r = torch.randn(pa.shape, device=dev, generator=gen)
+                pa.grad, pb.grad = r.clone(), r.clone()
+            oa.step()
+            ob.step()
+        torch.cuda.synchronize()
+        for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+            scale = pa.abs().max().item() + 1e-12
+            assert (pa - pb).abs().max().item() <= 2e-6 * scale, n
+        sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+        assert sa.keys() == sb.keys()
+        for k in sa:
+            for key in ("exp_avg", "exp_avg_sq"):          # fp32 rounding order differs (fma): 1e-5 of the tensor's max
+                ta, tb = sa[k][key], sb[k][key]
+                assert (ta - tb).abs().max().item() <= 1e-5 * (ta.abs().max().item() + 1e-30), (k, key)
+    finally:
+        _lib.set_precision("tf32")
