@@ -536,15 +536,26 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
-    which = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if "bf16_tflops" in peaks else "fallback 1590"
-    flop = 6 * 2 * H * H * E       # recompute 2 + dgrad 2 + wgrad 2 GEMMs of [E,64]x[64,64]
+    which = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks else "fallback 1590"
+    flop = 6 * 2 * H * H * E       # recompute 2 + dgrad 2 + wgrad 2 GEMMs of [E,64]x[64,64]; bias-sum GEMM columns not counted
     t_s = out["edge_bwd"] * 1e-3
     ach = flop / t_s / 1e12
-    roof = dict(kernel="edge_bwd_kernel (one launch = all E edges of one layer; timed with its two output memsets)",
-                bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None,
+    traffic = None
+    try:                           # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per launch
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        traffic = tr.get(f"edge_bwd_tc2_kernel<4>@E={E}")
+    except Exception:
+        pass
+    algo_bytes = E * (4 + 4 + 4 * 2 + 2 * 256 + 24 + 12 + 256 + 2 * 268)    # no-reuse model, SURVEY.md 8(d): ~1.35 KB/edge
+    roof = dict(kernel="bwd2::edge_bwd_tc2_kernel<4> (tcgen05 TF32, one launch = all E edges of one layer; CUDA events "
+                       "around the C-ABI call incl. its two output memsets, L2 flushed)",
+                bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
                 peak_source=which,
-                note="fp32 FMA formulation this round: the fp32 pipe's nominal peak is 74 TFLOP/s "
-                     f"(frac of that: {ach / 74.0:.3f}); algorithmic flops = 6 GEMMs x 2*64*64 per edge")
+                note="algorithmic flops = 6 GEMMs x 2*64*64 = 49152 per edge; operands are TF32 (nominal dense rate is half "
+                     f"of the bf16 rate the peak was measured at, so frac of a TF32 roof is ~{2 * ach / peak_tf:.3f}); the "
+                     f"no-reuse byte model is {algo_bytes / 1e6:.0f} MB per launch = {algo_bytes / t_s / 1e9:.0f} GB/s at this "
+                     "duration, far under the HBM roof, and measured DRAM traffic is ~13x smaller still (P/Q/x rows are "
+                     "L2-resident): the kernel is latency-bound per 128-edge tile (4 dependent GEMM stages), see DESIGN.md 4")
     return dict(roofline=roof, phases_ms_layer0=out)
 
 

@@ -445,6 +445,35 @@ int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved*
 
 namespace {
 
+// The per-graph phases run one CTA per graph.  fegnn_model_forward / backward put them on a second stream (fork / join
+// with events, all capturable) so they overlap the node- and edge-parallel kernels instead of idling 147 SMs.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream* s = &per_dev[dev];
+  if (s->st == nullptr) {
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return s;
+}
+#define FORK(side, main)                                 \
+  do {                                                   \
+    CK(cudaEventRecord((side)->fork, (main)));           \
+    CK(cudaStreamWaitEvent((side)->st, (side)->fork, 0)); \
+  } while (0)
+#define JOIN(side, main)                                 \
+  do {                                                   \
+    CK(cudaEventRecord((side)->join, (side)->st));       \
+    CK(cudaStreamWaitEvent((main), (side)->join, 0));    \
+  } while (0)
+
 struct ModelWs {
   // per layer l in [0, L]: state entering layer l (index L = outputs)
   float *h[33], *x[33], *Z[33], *Sx[33], *xsum[33];
@@ -524,19 +553,26 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
     CK(cudaGetLastError());
   }
   TRY(fegnn_graph_xsum(d->N, d->B, w.x[0], g->batch, w.xsum[0], stream));
+  SideStream* sd = side_stream();
+  RQ(sd != nullptr);
+  void* side = sd->st;
+  FORK(sd, st);                                   // side: graph_pre(0)
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
     const bool last = l == L - 1;
     if (last) dl.flags |= FEGNN_F_LAST;
     const fegnn_layer_params* p = &layers[l];
     fegnn_layer_saved* sv = &w.saved[l];
-    TRY(fegnn_graph_pre_forward(&dl, g, p, w.Z[l], w.Sx[l], w.xsum[l], sv, stream));
+    TRY(fegnn_graph_pre_forward(&dl, g, p, w.Z[l], w.Sx[l], w.xsum[l], sv, side));       // side (1 CTA per graph)
     TRY(fegnn_node_pre_forward(&dl, p, w.h[l], sv, stream));
     TRY(fegnn_edge_forward(&dl, g, p, w.x[l], sv, stream));
+    JOIN(sd, st);                                 // virtual needs G1, M of graph_pre
     TRY(fegnn_virtual_forward(&dl, g, p, w.x[l], v, w.Z[l], sv, w.x[l + 1], w.xsum[l + 1], stream));
+    FORK(sd, st);                                 // side: graph_post(l) [-> graph_pre(l+1)] under node_h, node_pre, edge
     if (!last) TRY(fegnn_node_h_forward(&dl, g, p, w.h[l], sv, w.h[l + 1], stream));
-    TRY(fegnn_graph_post_forward(&dl, g, p, w.Z[l], w.Sx[l], sv, w.Z[l + 1], w.Sx[l + 1], stream));
+    TRY(fegnn_graph_post_forward(&dl, g, p, w.Z[l], w.Sx[l], sv, w.Z[l + 1], w.Sx[l + 1], side));
   }
+  JOIN(sd, st);
   CK(cudaMemcpyAsync(x_out, w.x[L], sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(Z_out, w.Z[L], sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -565,6 +601,10 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
   const float* gS_new = nullptr;
   const float* gxsum_next = nullptr;
   int cur = 0;
+  SideStream* sd = side_stream();
+  RQ(sd != nullptr);
+  void* side = sd->st;
+  FORK(sd, st);                                   // side: graph_post_bwd(L-1)
   for (int l = L - 1; l >= 0; --l) {
     fegnn_dims dl = *d;
     const bool last = l == L - 1;
@@ -573,18 +613,21 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     fegnn_layer_grads* gr = &grads[l];
     const fegnn_layer_saved* sv = &w.saved[l];
     TRY(fegnn_graph_post_backward(&dl, g, p, gr, w.Sx[l], sv, gZ_new, gS_new, s.gZ[cur], s.gS[cur], s.gDsum, s.gUsum,
-                                  stream));
+                                  side));                                                   // side, under node_h_bwd
     if (!last) TRY(fegnn_node_h_backward(&dl, g, p, gr, sv, s.gh, s.gzh1, s.gm, s.gu, stream));
+    JOIN(sd, st);
     TRY(fegnn_virtual_backward(&dl, g, p, gr, w.x[l], v, w.Z[l], sv, gx_new, gxsum_next, s.gDsum,
                                last ? nullptr : s.gUsum, s.gu, s.gAv, s.gG1, s.gx[cur], s.gZ[cur],
                                s.gsv, s.gsg, s.gt, stream));
+    FORK(sd, st);                                 // side: graph_pre_bwd(l) -> graph_post_bwd(l-1), under edge_bwd, node_pre_bwd
+    TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[l], sv, s.gG1, s.gS[cur], s.gZ[cur], s.gxsum[cur], side));
     TRY(fegnn_edge_backward(&dl, g, p, gr, w.x[l], sv, last ? nullptr : s.gm, s.gt, s.gP, s.gQ, s.gx[cur], stream));
-    TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[l], sv, s.gG1, s.gS[cur], s.gZ[cur], s.gxsum[cur], stream));
     TRY(fegnn_node_pre_backward(&dl, p, gr, w.h[l], s.gP, s.gQ, s.gAv, last ? nullptr : s.gzh1, s.gsv, s.gsg, s.gh,
                                 stream));
     gx_new = s.gx[cur]; gZ_new = s.gZ[cur]; gS_new = s.gS[cur]; gxsum_next = s.gxsum[cur];
     cur ^= 1;
   }
+  JOIN(sd, st);
   if (N > 0) {
     final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, st>>>(d->N, gx_new, gxsum_next, g->batch, g_x0); ++g_launches;
     CK(cudaGetLastError());
