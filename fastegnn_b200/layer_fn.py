@@ -75,7 +75,8 @@ class LayerPhases:
         gDsum, gUsum = self._e(B, 3, Cc), self._e(B, Cc, L.H)
         L.check(lib.fegnn_graph_post_backward(pd, pg, pp, pgg, L.ptr(S), ps, L.ptr(gZ_new), L.ptr(gS_new), L.ptr(gZ),
                                               L.ptr(gS), L.ptr(gDsum), L.ptr(gUsum), st), "graph_post_backward")
-        gzh1 = gm = gu = None
+        gzh1 = gm = None
+        gu = self._e(N, Cc, L.H)      # last layer: no input (FEGNN_F_LAST), still the scratch of the tensor-core kernels
         if not self.last:
             gzh1, gm, gu = self._e(N, L.H), self._e(N, L.H), self._e(N, Cc, L.H)
             L.check(lib.fegnn_node_h_backward(pd, pg, pp, pgr, ps, L.ptr(gh_new), L.ptr(gzh1), L.ptr(gm), L.ptr(gu),
