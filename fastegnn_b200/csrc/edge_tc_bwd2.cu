@@ -492,10 +492,12 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
             gq = fmaf(g1v[j + 1], v->wq[c0 + j + 1], gq);
           }
         }
+#ifndef FEGNN_EXP_NO_GQ
 #pragma unroll
         for (int ch = 0; ch < CPT / 4; ++ch)
           atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
                     make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) g1v[j] = 0.f;

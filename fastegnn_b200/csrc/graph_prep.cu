@@ -103,8 +103,48 @@ __global__ void __launch_bounds__(256) scan_apply(const int* __restrict__ in, in
   if (total != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) *total = run;
 }
 
+// One launch for small inputs (n <= 64 K: degree arrays and digit histograms of Water-3D-size graphs): thread t owns
+// the contiguous chunk [t*per, (t+1)*per), the block scans the 1024 chunk sums.  in may alias out.
+constexpr int kSmallScan = 65536;
+__global__ void __launch_bounds__(1024) scan_small(const int* __restrict__ in, int n, int* __restrict__ out,
+                                                   int* __restrict__ total) {
+  __shared__ int wsum[32];
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int tsum = 0;
+  for (int i = lo; i < hi; ++i) tsum += in[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = tsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = wsum[lane], ti = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    wsum[lane] = ti - t;
+  }
+  __syncthreads();
+  int run = wsum[w] + inc - tsum;
+  for (int i = lo; i < hi; ++i) {       // in[i] is read before out[i] is written: safe when aliased
+    const int v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (total != nullptr && threadIdx.x == 1023) *total = run;
+}
+
 static cudaError_t exclusive_scan(const int* in, int n, int* out, int* total, int* sums, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if (n <= kSmallScan) {
+    scan_small<<<1, 1024, 0, st>>>(in, n, out, total); ++g_launches;
+    return cudaGetLastError();
+  }
   int nb = (n + kScanChunk - 1) / kScanChunk;
   scan_block_sums<<<nb, 256, 0, st>>>(in, n, sums); ++g_launches;
   scan_sums<<<1, 1024, 0, st>>>(sums, nb); ++g_launches;

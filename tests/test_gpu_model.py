@@ -318,3 +318,100 @@ def test_fused_adam_matches_torch_adam():
                 assert (ta - tb).abs().max().item() <= 1e-5 * (ta.abs().max().item() + 1e-30), (k, key)
     finally:
         _lib.set_precision("tf32")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_degenerate_graphs_against_oracle(prec):
+    """Edge cases of the reference semantics: a batch with NO edges at all (every mean is 0/clamp(1)), and a batch whose
+    graphs are single nodes with self-loops / duplicate edges only."""
+    g = torch.Generator().manual_seed(9)
+    cases = []
+    # (a) 3 graphs, no edges
+    N, B, C = 37, 3, 3
+    batch = torch.cat([torch.full((n,), b, dtype=torch.long) for b, n in enumerate([20, 1, 16])])
+    cases.append(("no_edges", N, B, C, batch, torch.zeros(2, 0, dtype=torch.long)))
+    # (b) 5 single-node graphs: self-loops and duplicates only
+    batch = torch.arange(5)
+    ei = torch.tensor([[0, 0, 1, 3, 3, 3], [0, 0, 1, 3, 3, 3]])
+    cases.append(("self_loops", 5, 5, 2, batch, ei))
+    for name, N, B, C, batch, ei in cases:
+        x = torch.randn(N, 3, generator=g)
+        inp = dict(node_feat=torch.rand(N, 2, generator=g), node_loc=x, node_vel=torch.randn(N, 3, generator=g) * 0.3,
+                   loc_mean=torch.stack([x[batch == b].mean(0) for b in range(B)]).unsqueeze(-1).repeat(1, 1, C) +
+                   0.2 * torch.randn(B, 3, C, generator=g),
+                   edge_attr=torch.rand(ei.size(1), 2, generator=g), edge_index=ei, data_batch=batch,
+                   wx=torch.randn(N, 3, generator=g), wz=torch.randn(B, 3, C, generator=g))
+        cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=2, hidden_nf=64, virtual_channels=C, n_layers=2)
+        params = orc.make_params(cfg, 123)
+        orc.rescale_coord_heads(params, 300.0)
+        with precision(prec) as (tol_out, tol_grad):
+            res = gpu_run(cfg, params, inp)
+        bad, report = compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=f"{name} [{prec}] ")
+        assert not bad, (name, bad, report)
+
+
+def test_eval_forward_without_autograd_matches_training_forward():
+    """utils/train.py:24-27,191-192: validation / test run the model under model.eval() (and here torch.no_grad()):
+    the forward-only path must give the training forward's outputs and keep no graph."""
+    cfg, params, inp = make_graph_case(seed=61, sizes=[90, 70, 40], deg=7, C=3, L=4, gravity=[0, -1, 0])
+    dev = "cuda:0"
+    m = build_gpu_model(cfg, params, dev)
+    g = {k: v.to(dev) for k, v in inp.items()}
+    kw = dict(node_feat=g["node_feat"], node_loc=g["node_loc"], node_vel=g["node_vel"], edge_index=g["edge_index"],
+              data_batch=g["data_batch"], loc_mean=g["loc_mean"], edge_attr=g["edge_attr"])
+    m.train()
+    x_tr, Z_tr = m(**kw)
+    m.eval()
+    with torch.no_grad():
+        x_ev, Z_ev = m(**kw)
+    assert not x_ev.requires_grad and not Z_ev.requires_grad
+    # atomics order may differ between two launches: fp32 rounding only
+    assert rel_err(x_ev.cpu(), x_tr.detach().cpu()) < 1e-5 and rel_err(Z_ev.cpu(), Z_tr.detach().cpu()) < 1e-5
+
+
+def test_full_size_water3d_properties():
+    """BASELINE.json config 4 at full size (8 000 particles, ~1.8e5 edges): size-independent properties instead of the
+    oracle -- SE(3) equivariance of the outputs, invariance of the result to the ORDER of the edge list (graph prep
+    sorts it), finite gradients for every live parameter."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import make_cloud
+    from fastegnn_b200 import FastEGNN
+    dev = "cuda:0"
+    data = make_cloud(8000, 25.0, 3, seed=0, gravity=None)
+    torch.manual_seed(0)
+    m = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=64, virtual_channels=3, device=dev, n_layers=4)
+    sd = m.state_dict()
+    orc.rescale_coord_heads(sd, 100.0)
+    m.load_state_dict(sd)
+    t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+
+    def run(x, v, ei, ea, lm):
+        return m(node_feat=t["node_feat"], node_loc=x, node_vel=v, edge_index=ei, data_batch=t["batch"], loc_mean=lm,
+                 edge_attr=ea)
+    x0, Z0 = run(t["loc_0"], t["vel_0"], t["edge_index"], t["edge_attr"], t["loc_mean"])
+    assert x0.shape == (8000, 3) and torch.isfinite(x0).all() and torch.isfinite(Z0).all()
+    # rotation + translation
+    gen = torch.Generator().manual_seed(1)
+    R, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=torch.float64))
+    if torch.det(R) < 0:
+        R[:, 0] = -R[:, 0]
+    R = R.float().to(dev)
+    tr = torch.tensor([0.3, -0.2, 0.5], device=dev)
+    lm_rt = (t["loc_mean"].transpose(1, 2) @ R + tr).transpose(1, 2).contiguous()
+    x1, Z1 = run(t["loc_0"] @ R + tr, t["vel_0"] @ R, t["edge_index"], t["edge_attr"], lm_rt)
+    scale = float(x0.abs().max())
+    assert float((x0 @ R + tr - x1).abs().max()) < 1e-4 * max(1.0, scale)
+    assert float(((Z0.transpose(1, 2) @ R + tr).transpose(1, 2) - Z1).abs().max()) < 1e-4 * max(1.0, scale)
+    # edge order
+    perm = torch.randperm(t["edge_index"].size(1), generator=gen).to(dev)
+    x2, Z2 = run(t["loc_0"], t["vel_0"], t["edge_index"][:, perm].contiguous(), t["edge_attr"][perm].contiguous(),
+                 t["loc_mean"])
+    assert rel_err(x2.detach().cpu(), x0.detach().cpu()) < 1e-5 and rel_err(Z2.detach().cpu(), Z0.detach().cpu()) < 1e-5
+    # gradients
+    (x0.square().mean() + Z0.square().mean()).backward()
+    for n, p in m.named_parameters():
+        dead = n.startswith("gcl_3.node_mlp")
+        assert (p.grad is None) == dead, n
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), n
