@@ -517,6 +517,8 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     virt_fwd_fn, virt_bwd_fn = dict(calls)["virtual_fwd"], dict(calls)["virtual_bwd"]
     calls += [(f"virtual_fwd[mode={m}]", with_mode("virtual_forward", m, virt_fwd_fn)) for m in (0, 1)]
     calls += [(f"virtual_bwd[mode={m}]", with_mode("virtual_backward", m, virt_bwd_fn)) for m in (0, 1)]
+    npre_fn = dict(calls)["node_pre_fwd"]
+    calls += [(f"node_pre_fwd[mode={m}]", with_mode("node_forward", m, npre_fn)) for m in (0, 1)]
     edge_bwd_fn = dict(calls)["edge_bwd"]
     calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4)]
     for name, fn in calls:

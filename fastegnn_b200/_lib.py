@@ -133,15 +133,14 @@ def set_mode(phase: str, mode: int) -> None:
     check(lib.fegnn_set_mode(phase.encode(), int(mode)), "fegnn_set_mode")
 
 
-PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward")
+PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward", "node_forward")
 
 
 def set_precision(name: str) -> None:
     """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase and the
     dense real<->virtual phase run on tcgen05 TF32 tiles, forward and backward (stated tolerance).
-    "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual phase)."""
-    table = {"fp32": (0, 0, 0, 0), "tf32": (1, 4, 1, DEFAULT_MODES["virtual_backward"]),
-             "tf32x3": (3, 4, 0, DEFAULT_MODES["virtual_backward"])}
+    "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual and node phases)."""
+    table = {"fp32": (0, 0, 0, 0, 0), "tf32": (1, 4, 1, 1, 1), "tf32x3": (3, 4, 0, 1, 0)}
     for phase, mode in zip(PHASES, table[name]):
         set_mode(phase, mode)
 

@@ -17,6 +17,7 @@
 #include "node_kernels.cu"
 #include "virtual_kernels.cu"
 #include "virtual_tc.cu"
+#include "node_tc.cu"
 
 using namespace fegnn;
 
@@ -55,6 +56,8 @@ int g_edge_bwd_mode = 4;
 // 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
 int g_virt_fwd_mode = 1;
 int g_virt_bwd_mode = 1;
+// per-node dense phases: 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels
+int g_node_fwd_mode = 1;
 
 int sm_count() {
   static int sms = 0;
@@ -178,6 +181,11 @@ int fegnn_set_mode(const char* phase, int mode) {
     g_edge_bwd_mode = mode;
     return 0;
   }
+  if (strcmp(phase, "node_forward") == 0) {
+    if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "%s mode must be 0 or 1", phase);
+    g_node_fwd_mode = mode;
+    return 0;
+  }
   if (strcmp(phase, "virtual_forward") == 0 || strcmp(phase, "virtual_backward") == 0) {
     if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "%s mode must be 0 or 1", phase);
     (phase[8] == 'f' ? g_virt_fwd_mode : g_virt_bwd_mode) = mode;
@@ -188,6 +196,7 @@ int fegnn_set_mode(const char* phase, int mode) {
 int fegnn_get_mode(const char* phase) {
   if (phase != nullptr && strcmp(phase, "edge_forward") == 0) return g_edge_fwd_mode;
   if (phase != nullptr && strcmp(phase, "edge_backward") == 0) return g_edge_bwd_mode;
+  if (phase != nullptr && strcmp(phase, "node_forward") == 0) return g_node_fwd_mode;
   if (phase != nullptr && strcmp(phase, "virtual_forward") == 0) return g_virt_fwd_mode;
   if (phase != nullptr && strcmp(phase, "virtual_backward") == 0) return g_virt_bwd_mode;
   return -1;
@@ -249,7 +258,8 @@ int fegnn_node_pre_forward(const fegnn_dims* d, const fegnn_layer_params* p, con
   RQ(h && sv);
   NodePreArgs a = node_pre_args(d, p, h);
   a.P = sv->P; a.Q = sv->Q; a.Av = sv->Av; a.Uh = sv->Uh; a.sv = sv->sv; a.sg = sv->sg;
-  CK(launch_node_pre_fwd(a, sm_count(), S(stream)));
+  if (g_node_fwd_mode == 1) CK(launch_node_pre_fwd_tc(a, sm_count(), S(stream)));
+  else CK(launch_node_pre_fwd(a, sm_count(), S(stream)));
   return 0;
 }
 

@@ -121,7 +121,8 @@ unsigned long long fegnn_launch_count(void);
  * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
  * 256 / 512 threads per 128-edge tile (4 is the default).  Layers with attention=True or Fe > 4 always take mode 0 in
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
- * TF32 kernels (default; attention=True layers always take 0).  Process-wide. */
+ * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels, 1 = tcgen05 TF32
+ * (default) for fegnn_node_pre_forward.  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
 

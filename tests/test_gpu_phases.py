@@ -430,3 +430,43 @@ def test_virtual_backward_modes(name, mode, layer):
             fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
     bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
+@pytest.mark.parametrize("layer", [0, 1])
+def test_node_pre_forward_modes(name, mode, layer):
+    """fegnn_node_pre_forward alone (fp32 FMA kernel vs tcgen05 TF32 kernel) against staged.node_pre."""
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    l = layer
+    last = l == cfg.n_layers - 1
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"] | (L.F_LAST if last else 0), cfg.gravity)
+    ptrs = s["layer_ptrs"](s["gparams"], f"gcl_{l}")
+    sv = s["SavedBlock"](dims, dev)
+    sv.buf.fill_(float("nan"))
+    S_ = sm.saved[l]
+    h = _g(S_["h"], dev)
+    old = L.get_mode("node_forward")
+    try:
+        L.set_mode("node_forward", mode)
+        L.check(lib.fegnn_node_pre_forward(C.byref(dims), C.byref(ptrs), L.ptr(h), C.byref(sv.c), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("node_forward", old)
+    tol = VIRT_TOL[mode]
+    errs = []
+    names = ["P", "Q", "Av", "sv"] + ([] if last else ["Uh"]) + (["sg"] if cfg.gravity is not None else [])
+    for k in names:
+        shp = (N,) if k in ("sv", "sg") else (N, H)
+        _chk(errs, k, sv.view(k, shp), S_["npre"][k], tol)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/node_pre_fwd_mode{mode}_{name}_l{l}.txt", "w") as fh:
+        for n_, e, t in errs:
+            fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
+    assert not bad, bad
