@@ -11,6 +11,7 @@ inside the timed region.
 Workloads (BASELINE.json configs):
   water3d   (default, config 4) 8 000 uniform particles, radius graph with mean degree ~25
             (E ~ 2e5 directed edges, ordered by ascending length), C=3, gravity [0,-1,0], B=1.
+  water3d_b20  the same clouds batched 20 per step, the reference's training batch (main_simulation.py:46).
   nbody100  (config 2) 100 graphs x 100 particles, shortest 50% of all ordered pairs.
   large     (config 5 shape, scaled by --nodes) uniform cloud, mean degree 30, C=8.
 With N>1 ranks: water3d / nbody100 (whole small graphs, as the reference batches them) go one batch per
@@ -73,7 +74,18 @@ def make_cloud(n: int, mean_deg: float, C: int, seed: int, gravity, r: float = 0
                 edge_attr=t(np.stack([length, length], axis=1)),                 # utils/train.py:41-43
                 batch=torch.zeros(n, dtype=torch.int64),
                 loc_mean=t(x.mean(0, keepdims=True).T[None].repeat(C, axis=2).astype(np.float32)),
-                n_graphs=1, C=C, gravity=gravity, sizes=[n])
+                n_graphs=1, C=C, gravity=gravity, sizes=[n], radius=r)
+
+
+def make_cloud_batch(n: int, B: int, mean_deg: float, C: int, seed: int, gravity):
+    """B independent clouds batched the way the reference's DataLoader collates them (main_simulation.py:46 trains with
+    batch_size 20): node tensors concatenated, edge_index offset by the cumulative node count."""
+    parts = [make_cloud(n, mean_deg, C, seed * 1000 + b, gravity) for b in range(B)]
+    cat = lambda k: torch.cat([p[k] for p in parts])
+    ei = torch.cat([p["edge_index"] + b * n for b, p in enumerate(parts)], dim=1)
+    return dict(node_feat=cat("node_feat"), loc_0=cat("loc_0"), vel_0=cat("vel_0"), loc_t=cat("loc_t"), edge_index=ei,
+                edge_attr=cat("edge_attr"), batch=torch.arange(B).repeat_interleave(n), loc_mean=cat("loc_mean"),
+                n_graphs=B, C=C, gravity=gravity, sizes=[n] * B, radius=parts[0]["radius"])
 
 
 def make_nbody(n: int, B: int, cutoff: float, C: int, seed: int):
@@ -108,6 +120,8 @@ def make_nbody(n: int, B: int, cutoff: float, C: int, seed: int):
 def make_workload(name: str, seed: int, nodes: int):
     if name == "water3d":
         return make_cloud(nodes or 8000, 25.0, 3, seed, [0, -1, 0]), dict(sigma=1.0, weight=0.01, sample=3)
+    if name == "water3d_b20":
+        return make_cloud_batch(nodes or 8000, 20, 25.0, 3, seed, [0, -1, 0]), dict(sigma=1.0, weight=0.01, sample=3)
     if name == "nbody100":
         return make_nbody(100, 100, 0.5, 3, seed), dict(sigma=1.5, weight=0.01, sample=3)
     if name == "large":
@@ -168,12 +182,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
-def oracle_step_fn(data, hp):
-    """The reference's training step (utils/train.py:49-170) on the CPU restatement of the model."""
+def oracle_step_fn(data, hp, device="cpu"):
+    """The reference's training step (utils/train.py:49-170) on the restatement of the model in the reference's own
+    torch op chain; device="cuda" gives the eager-PyTorch-on-the-same-GPU bar (--gpu-eager-bar)."""
     from oracle import fastegnn_oracle as orc
     cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=2, hidden_nf=H, virtual_channels=data["C"], n_layers=LAYERS,
                            gravity=data["gravity"])
-    params = {k: v.clone().requires_grad_(True) for k, v in orc.make_params(cfg, 0).items()}
+    params = {k: v.clone().to(device).requires_grad_(True) for k, v in orc.make_params(cfg, 0).items()}
+    if device != "cpu":
+        data = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
     opt = torch.optim.Adam(list(params.values()), lr=5e-4, weight_decay=1e-12)
     gen = torch.Generator().manual_seed(0)
     ns = min(hp["sample"] * data["C"], min(data["sizes"]))
@@ -185,7 +202,7 @@ def oracle_step_fn(data, hp):
                                     data["batch"], data["loc_mean"], data["edge_attr"])
         loss = torch.nn.functional.mse_loss(x, data["loc_t"])
         idx = sample_indices(data["sizes"], ns, gen).long()
-        local = [idx[b] - int(offs[b]) for b in range(len(data["sizes"]))]
+        local = [(idx[b] - int(offs[b])).to(device) for b in range(len(data["sizes"]))]
         loss = loss + hp["weight"] * orc.mmd_loss(x, Z, data["batch"], hp["sigma"], local)
         loss.backward()
         opt.step()
@@ -211,12 +228,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="water3d", choices=["water3d", "nbody100", "large"])
+    ap.add_argument("--workload", default="water3d", choices=["water3d", "water3d_b20", "nbody100", "large"])
     ap.add_argument("--nodes", type=int, default=0)
     ap.add_argument("--mode", default="auto", choices=["auto", "dp", "partitioned"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
+    ap.add_argument("--gpu-eager-bar", action="store_true",
+                    help="also time the reference's torch op chain (oracle/ restatement) eagerly on the same GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -436,6 +455,11 @@ def main():
             line["cuda_graph_error"] = graph_state["why"]
         if not args.no_phases and not part:
             line.update(phase_profile(model, dev_in, dev, data, E, N, B, C, flush))
+            if data.get("radius") is not None:
+                try:
+                    line["graph_build"] = graph_build_profile(data, dev_in, dev, B, flush)
+                except Exception as exc:                          # reported, never hides the headline numbers
+                    line["graph_build"] = dict(error=f"{type(exc).__name__}: {exc}"[:300])
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(cores)
             t_cpu = time_cpu(oracle_step_fn(data, hp), 1, 3)
@@ -443,6 +467,20 @@ def main():
                                         ms_per_step=t_cpu * 1e3,
                                         sample="the full workload: 1 warm-up + 3 timed training steps of oracle/ "
                                                "(CPU restatement of the reference's torch op chain)")
+        if args.gpu_eager_bar and world == 1:
+          try:
+            step = oracle_step_fn(data, hp, device=str(dev))
+
+            def eager():
+                step()
+                torch.cuda.synchronize()
+            t_eager = time_cpu(eager, 3, 10)
+            line["gpu_eager_baseline"] = dict(value=E * LAYERS / t_eager, unit="edges/s", ms_per_step=t_eager * 1e3,
+                                              kind="port", what="oracle/ (the reference's torch op chain: gather, cat, "
+                                              "Linear, scatter_add, autograd, torch.optim.Adam) run eagerly in fp32 on "
+                                              "this GPU, wall clock with a synchronize per step")
+          except Exception as exc:
+            line["gpu_eager_baseline"] = dict(error=f"{type(exc).__name__}: {exc}"[:300])
         print(json.dumps(line))
     if world > 1:
         # a captured graph still references the communicator: skip the (occasionally hanging) NCCL teardown
@@ -450,6 +488,38 @@ def main():
         torch.cuda.synchronize()
         sys.stdout.flush()
         os._exit(0)
+
+
+def graph_build_profile(data, t, dev, B, flush):
+    """the graph construction in front of the path (radius_graph + cutoff_edge + norm + the CSR sort) on
+    the device, next to the CPU restatement (oracle/radius_graph_oracle.py: KD-tree candidates + numpy sorts)."""
+    from fastegnn_b200 import CsrGraph
+    from oracle import radius_graph_oracle as rgo
+    r = data["radius"]
+    out = {}
+    for cr in (0.0, 0.5):
+        for _ in range(3):
+            g = CsrGraph.from_radius(t["loc_0"], t["batch"], B, r, cr, 2)
+        ts = []
+        for _ in range(10):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            g = CsrGraph.from_radius(t["loc_0"], t["batch"], B, r, cr, 2)       # includes its one host read of the count
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = sum(ts) / len(ts)
+        t0 = time.perf_counter()
+        o = rgo.radius_graph_csr(data["loc_0"].numpy(), np.array([0, data["loc_0"].size(0)]), r, cr)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        same = bool(o["row"].shape[0] == g.E and np.array_equal(g.col.cpu().numpy(), o["col"]))
+        out[f"cutoff_rate={cr}"] = dict(edges=int(g.E), candidates=int(g.n_candidates), ms=round(ms, 4),
+                                        edges_per_s=g.E / (ms * 1e-3), cpu_port_ms=round(cpu_ms, 2),
+                                        identical_to_oracle=same)
+    out["what"] = ("CsrGraph.from_radius (fegnn_radius_graph_count + _fill, CUDA events incl. the host read of the "
+                   "candidate count) vs oracle/radius_graph_oracle.py on 1 host thread")
+    return out
 
 
 def phase_profile(model, t, dev, data, E, N, B, C, flush):

@@ -235,6 +235,18 @@ class FastEGNN(nn.Module):
     # -- forward --------------------------------------------------------------------------
     def forward(self, node_feat, node_loc, node_vel, edge_index, data_batch, loc_mean, edge_attr=None, node_attr=None):
         _require_cuda(node_loc, "node_loc")
+        if isinstance(edge_index, CsrGraph):
+            # a graph already in kernel layout (CsrGraph.from_radius, or a CsrGraph reused across steps of a static
+            # batch): no per-forward sort.  Its edge_attr is used; the edge_attr argument must be None.
+            graph = edge_index
+            if edge_attr is not None:
+                raise TypeError("edge_attr must be None when edge_index is a prebuilt CsrGraph (it carries its own)")
+            if graph.Fe != self._edge_attr_nf or graph.N != node_loc.size(0) or graph.B != loc_mean.size(0):
+                raise RuntimeError(f"prebuilt graph (N={graph.N}, B={graph.B}, Fe={graph.Fe}) does not match the inputs "
+                                   f"(N={node_loc.size(0)}, B={loc_mean.size(0)}, edge_attr_nf={self._edge_attr_nf})")
+            params = [p for _, p in self.named_parameters()]
+            return _StackFn.apply(self, graph, node_feat.contiguous().float(), node_loc.contiguous().float(),
+                                  node_vel.contiguous().float(), loc_mean.contiguous().float(), *params)
         if edge_attr is None:
             if self._edge_attr_nf != 0:
                 raise TypeError("edge_attr is required when edge_attr_nf > 0 (the reference's torch.cat fails on None, "

@@ -96,6 +96,10 @@ SIGNATURES = {
     "fegnn_get_mode": (C.c_int, [C.c_char_p]),
     "fegnn_graph_prep_workspace_bytes": (C.c_size_t, [i32, i32]),
     "fegnn_graph_prep": (C.c_int, [i32, i32, i32, i32] + [vp] * 12 + [vp, C.c_size_t, vp]),
+    "fegnn_radius_graph_workspace_bytes": (C.c_size_t, [i32, i32]),
+    "fegnn_radius_graph_count": (C.c_int, [i32, i32, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "fegnn_radius_graph_fill": (C.c_int, [i32, i32, i32, C.c_float, C.c_double, vp, vp, vp, vp, i32, vp, vp, vp, i32,
+                                          vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
     "fegnn_embed_forward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),
     "fegnn_embed_backward": (C.c_int, [i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "fegnn_graph_xsum": (C.c_int, [i32, i32, vp, vp, vp, vp]),

@@ -13,6 +13,7 @@
 #include "edge_tc_bwd2.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
+#include "radius_graph.cu"
 #include "mmd.cu"
 #include "node_kernels.cu"
 #include "virtual_kernels.cu"
@@ -217,6 +218,39 @@ int fegnn_graph_prep(int32_t N, int32_t E, int32_t B, int32_t Fe, const int64_t*
     return fail(FEGNN_ENOMEM, "graph_prep workspace %zu < %zu bytes", workspace_bytes, graph_prep_workspace_bytes(N, E));
   CK(graph_prep(N, E, B, Fe, edge_index, data_batch, edge_attr, perm, rowptr, row, col, batch, gptr,
                 edge_attr_sorted, dinv, inv_nb, workspace, S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ graph construction
+size_t fegnn_radius_graph_workspace_bytes(int32_t N, int32_t B) { return radius_graph_workspace_bytes(N, B); }
+
+int fegnn_radius_graph_count(int32_t N, int32_t B, const float* x, const int64_t* data_batch, float r, int32_t* batch,
+                             int32_t* gptr, float* inv_nb, int32_t* cand_rowptr, int32_t* n_cand, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  RQ(N >= 0 && B >= 0 && r > 0.f);
+  RQ(gptr && cand_rowptr && n_cand && (B == 0 || inv_nb) && (N == 0 || (x && data_batch && batch && B >= 1)));
+  RQ(workspace != nullptr);
+  if (workspace_bytes < radius_graph_workspace_bytes(N, B))
+    return fail(FEGNN_ENOMEM, "radius_graph workspace %zu < %zu bytes", workspace_bytes, radius_graph_workspace_bytes(N, B));
+  CK(radius_graph_count(N, B, x, data_batch, r, batch, gptr, inv_nb, cand_rowptr, n_cand, workspace, S(stream)));
+  return 0;
+}
+
+int fegnn_radius_graph_fill(int32_t N, int32_t B, int32_t Fe, float r, double keep_frac, const int32_t* batch,
+                            const int32_t* gptr, const int32_t* cand_rowptr, const int32_t* n_cand,
+                            int32_t cand_capacity, int32_t* cand_col, float* cand_dist, int32_t* cand_row,
+                            int32_t out_capacity, int32_t* rowptr, int32_t* row, int32_t* col, float* edge_attr,
+                            float* dinv, int32_t* n_edges, void* workspace, size_t workspace_bytes, void* stream) {
+  RQ(N >= 0 && B >= 0 && r > 0.f && Fe >= 0 && Fe <= FEGNN_MAX_FE && cand_capacity >= 0 && out_capacity >= 0);
+  RQ(keep_frac >= 0.0);
+  RQ(rowptr && n_edges && cand_rowptr && n_cand && (N == 0 || (batch && gptr)));
+  RQ(cand_capacity == 0 || (cand_col && cand_dist && cand_row));
+  RQ(out_capacity == 0 || (row && col && (Fe == 0 || edge_attr)));
+  RQ(workspace != nullptr);
+  if (workspace_bytes < radius_graph_workspace_bytes(N, B))
+    return fail(FEGNN_ENOMEM, "radius_graph workspace %zu < %zu bytes", workspace_bytes, radius_graph_workspace_bytes(N, B));
+  CK(radius_graph_fill(N, B, Fe, r, keep_frac, cand_capacity, batch, gptr, cand_rowptr, n_cand, cand_col, cand_dist,
+                       cand_row, out_capacity, rowptr, row, col, edge_attr, dinv, n_edges, workspace, S(stream)));
   return 0;
 }
 

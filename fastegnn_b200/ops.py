@@ -66,6 +66,73 @@ class CsrGraph:
                          L.ptr(self.dinv), L.ptr(self.inv_nb))
 
 
+    @classmethod
+    def from_radius(cls, node_loc: torch.Tensor, data_batch: torch.Tensor, n_graphs: int, r: float,
+                    cutoff_rate: float = 0.0, edge_attr_nf: int = 2) -> "CsrGraph":
+        """Build the graph ON THE DEVICE (fegnn_radius_graph_count / _fill): every ordered pair of distinct nodes of
+        the same graph closer than r, the shortest int(E_b (1 - cutoff_rate)) of them per graph, in CSR order with
+        edge_attr = length in each of the edge_attr_nf columns.  Replaces radius_graph + cutoff_edge + norm of
+        datasets/simulation/dataset.py:80-82,96-101 (r = math.inf: the complete-graph / topk selection of
+        datasets/nbody/dataset.py:102-113) and the per-forward CSR sort.  One host read of the candidate count
+        sizes the buffers (this is dataset-time work, not part of the captured training step)."""
+        _require_cuda(node_loc, "node_loc")
+        dev = node_loc.device
+        x = node_loc.detach().contiguous().float()
+        if data_batch.dtype != torch.int64:
+            raise L.FegnnError("data_batch must be int64 (as produced by the reference loaders)")
+        db = data_batch.contiguous()
+        N, B, Fe = int(x.size(0)), int(n_graphs), int(edge_attr_nf)
+        if not r > 0:
+            raise L.FegnnError("r must be positive (math.inf for the complete graph)")
+        if not 0.0 <= cutoff_rate <= 1.0:
+            raise L.FegnnError("cutoff_rate must be in [0, 1]")
+        i32 = dict(device=dev, dtype=torch.int32)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self = cls.__new__(cls)
+        self.N, self.B, self.Fe, self.Nl = N, B, Fe, N
+        self.perm = None                                      # there is no caller-side edge list to permute
+        self.batch = torch.empty(N, **i32)
+        self.gptr = torch.empty(B + 1, **i32)
+        self.inv_nb = torch.empty(B, **f32)
+        self.dinv = torch.empty(N, **f32)
+        self.rowptr = torch.empty(N + 1, **i32)
+        cand_rowptr = torch.empty(N + 1, **i32)
+        counts = torch.zeros(2, **i32)                        # [n_cand, n_edges]
+        nbytes = int(lib.fegnn_radius_graph_workspace_bytes(N, B))
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        st = _stream()
+        L.check(lib.fegnn_radius_graph_count(N, B, L.ptr(x), L.ptr(db), float(r), L.ptr(self.batch), L.ptr(self.gptr),
+                                             L.ptr(self.inv_nb), L.ptr(cand_rowptr), L.ptr(counts[0:1]), L.ptr(ws),
+                                             nbytes, st), "fegnn_radius_graph_count")
+        n_cand = int(counts[0].item())
+        keep_frac = 1.0 - float(cutoff_rate)                  # the reference's int(E * (1 - cutoff_rate)) in fp64
+        cap = max(n_cand, 1)
+        ccol = torch.empty(cap, **i32)
+        crow = torch.empty(cap, **i32)
+        cdist = torch.empty(cap, **f32)
+        row = torch.empty(cap, **i32)
+        col = torch.empty(cap, **i32)
+        ea = torch.empty(cap, max(Fe, 1), **f32)
+        L.check(lib.fegnn_radius_graph_fill(N, B, Fe, float(r), keep_frac, L.ptr(self.batch), L.ptr(self.gptr),
+                                            L.ptr(cand_rowptr), L.ptr(counts[0:1]), n_cand, L.ptr(ccol), L.ptr(cdist),
+                                            L.ptr(crow), cap, L.ptr(self.rowptr), L.ptr(row), L.ptr(col), L.ptr(ea),
+                                            L.ptr(self.dinv), L.ptr(counts[1:2]), L.ptr(ws), nbytes, st),
+                "fegnn_radius_graph_fill")
+        E = int(counts[1].item())
+        self.E = E
+        self.n_candidates = n_cand
+        self.row, self.col = row[:E], col[:E]
+        self.edge_attr = ea[:E] if Fe else torch.empty(0, **f32)
+        self._ws = ws
+        self.c = L.Graph(L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch), L.ptr(self.edge_attr),
+                         L.ptr(self.dinv), L.ptr(self.inv_nb))
+        return self
+
+    def edge_index(self) -> torch.Tensor:
+        """int64 [2,E] view of the CSR edge list for callers that want the reference's tensor (a cast, no arithmetic)."""
+        return torch.stack([self.row.long(), self.col.long()])
+
+
 def make_dims(N: int, Nl: int, E: int, B: int, C_: int, Fe: int, flags: int,
               gravity: Optional[Sequence[float]] = None, eps: float = 1e-8) -> L.Dims:
     d = L.Dims()

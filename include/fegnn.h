@@ -141,6 +141,34 @@ int fegnn_graph_prep(int32_t N, int32_t E, int32_t B, int32_t Fe,
                      float* dinv /*[N]*/, float* inv_nb /*[B]*/,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ graph construction on the device
+ * Replaces the step right before the path: torch_cluster.radius_graph + cutoff_edge (torch.sort of the lengths, keep
+ * the int(E (1 - cutoff_rate)) shortest) + torch.norm of datasets/simulation/dataset.py:80-82,96-101, the complete-graph
+ * / topk variant of datasets/nbody/dataset.py:102-113 (r = +inf) and the contact graph of
+ * datasets/protein/dataset.py:146-156,208-213 -- and emits the result directly as the CSR-by-row graph of
+ * fegnn_graph_prep (same arrays, same order: rows ascending, inside a row ascending (length, col), which is what a
+ * stable sort by row of the reference's length-ordered edge list gives).
+ *   candidates: ordered pairs (i,j), i != j, same graph, d2 < r*r, d2 = (dx*dx + dy*dy) + dz*dz in fp32 without FMA;
+ *   selection : per graph the int(E_b * keep_frac) first candidates in (length, col, row) order; keep_frac >= 1 keeps all;
+ *   edge_attr : every one of the Fe columns holds length = sqrtf(d2)  (dataset edge_attr + utils/train.py:41-43).
+ * Two calls, because the edge count is data dependent and nothing here allocates or synchronises:
+ *   fegnn_radius_graph_count -> batch / gptr / inv_nb, cand_rowptr [N+1] (exclusive) and *n_cand (device);
+ *   the caller reads *n_cand, provides candidate scratch (3 x cand_capacity words) and outputs of out_capacity
+ *   entries (out_capacity >= the final edge count, cand_capacity >= *n_cand always suffices), then
+ *   fegnn_radius_graph_fill -> rowptr [N+1], row / col / edge_attr / dinv and *n_edges (device).
+ * The workspace must be the same, untouched block in both calls. */
+size_t fegnn_radius_graph_workspace_bytes(int32_t N, int32_t B);
+int fegnn_radius_graph_count(int32_t N, int32_t B, const float* x /*[N,3]*/, const int64_t* data_batch /*[N]*/, float r,
+                             int32_t* batch /*[N]*/, int32_t* gptr /*[B+1]*/, float* inv_nb /*[B]*/,
+                             int32_t* cand_rowptr /*[N+1]*/, int32_t* n_cand /*[1]*/,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int fegnn_radius_graph_fill(int32_t N, int32_t B, int32_t Fe, float r, double keep_frac,
+                            const int32_t* batch, const int32_t* gptr, const int32_t* cand_rowptr, const int32_t* n_cand,
+                            int32_t cand_capacity, int32_t* cand_col, float* cand_dist, int32_t* cand_row,
+                            int32_t out_capacity, int32_t* rowptr /*[N+1]*/, int32_t* row, int32_t* col,
+                            float* edge_attr /*[out_capacity,Fe]*/, float* dinv /*[N]*/, int32_t* n_edges /*[1]*/,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ phases of one layer (forward)
  * Names follow oracle/staged.py, which spells the same pipeline out on the CPU.  */
 
