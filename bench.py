@@ -511,7 +511,7 @@ def graph_build_profile(data, t, dev, B, flush):
             ts.append(s.elapsed_time(e))
         ms = sum(ts) / len(ts)
         t0 = time.perf_counter()
-        o = rgo.radius_graph_csr(data["loc_0"].numpy(), np.array([0, data["loc_0"].size(0)]), r, cr)
+        o = rgo.radius_graph_csr(data["loc_0"].numpy(), np.concatenate([[0], np.cumsum(data["sizes"])]), r, cr)
         cpu_ms = (time.perf_counter() - t0) * 1e3
         same = bool(o["row"].shape[0] == g.E and np.array_equal(g.col.cpu().numpy(), o["col"]))
         out[f"cutoff_rate={cr}"] = dict(edges=int(g.E), candidates=int(g.n_candidates), ms=round(ms, 4),

@@ -198,12 +198,15 @@ class FastEGNN(nn.Module):
         self._cache = None          # .to() / .cuda() / .float() re-allocate parameter storage
         return super()._apply(fn, *a, **k)
 
+    def _signature_tensors(self):
+        return (self.virtual_node_feat, self.embedding_in.weight,
+                getattr(self, "gcl_%d" % (self.n_layers - 1)).node_mlp_virtual[2].bias)
+
     def _param_table(self):
         """(fegnn_layer_params[L], ordered parameter names).  Cached; storage addresses are
         stable under optimizer steps and load_state_dict (both write in place)."""
         named = dict(self.named_parameters())
-        sig = tuple(p.data_ptr() for p in (self.virtual_node_feat, self.embedding_in.weight,
-                                           getattr(self, "gcl_%d" % (self.n_layers - 1)).node_mlp_virtual[2].bias))
+        sig = tuple(p.data_ptr() for p in self._signature_tensors())
         if self._cache is None or self._cache[0] != sig:
             for n, p in named.items():
                 if not p.is_cuda or p.dtype != torch.float32:

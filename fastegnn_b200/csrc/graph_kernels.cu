@@ -162,9 +162,9 @@ __global__ void __launch_bounds__(kThreads) graph_post_bwd_kernel(GraphArgs a) {
       a.gZ[(size_t)b * 3 * C + tid] = g;
       a.gDsum[(size_t)b * 3 * C + tid] = g * inb;
     }
-    if (last) {
+    if (last) {                 // no phi_hv: S' = S is discarded (top layer, gS_new == null) or passed through (FastRF)
       for (int i = tid; i < C * kH; i += kThreads) {
-        a.gS[(size_t)b * C * kH + i] = 0.f;
+        a.gS[(size_t)b * C * kH + i] = a.gS_new != nullptr ? a.gS_new[(size_t)b * C * kH + i] : 0.f;
         a.gUsum[(size_t)b * C * kH + i] = 0.f;
       }
       continue;

@@ -88,9 +88,10 @@ constexpr size_t kNodePreFwdSmem = (kWFloats + kTileFloats + 2 * kH) * sizeof(fl
 // Work item = (node tile, weight block).  The grid is a multiple of the number of active blocks, so a
 // CTA always meets the same block and stages its 64x64 weight once; small N still fills the GPU
 // (N = 8000 -> 63 tiles x 6 blocks = 378 CTAs instead of 63).
-__device__ __forceinline__ int node_pre_block_id(int k, bool last, bool grav) {
+__device__ __forceinline__ int node_pre_block_id(int k, bool last, bool grav, bool rf = false) {
   // k-th ACTIVE block -> block id (0 P, 1 Q, 2 Av, 3 Uh, 4 vel, 5 grav)
   if (last && k >= 3) ++k;
+  if (rf && k >= 4) ++k;       // FastRF: phi_v acts on |v| (rf_vel_* kernels), not on h
   (void)grav;
   return k;
 }
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_pre_fwd_kernel(NodePreArgs a
   float* vec = T0 + kTileFloats;     // head blocks: [0] first-layer bias, [1] output weight
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
-  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav);
+  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav, a.flags & FEGNN_F_RF);
   const int cta = blockIdx.x / nactive, nctas = gridDim.x / nactive;
   const float* wsrc = blk <= 1 ? a.edge_w0 : blk == 2 ? a.edgev_w0 : blk == 3 ? a.node_w0 : blk == 4 ? a.vel_w0 : a.grav_w0;
   const int ld = blk <= 1 ? a.ld1 : blk == 2 ? a.ldv : blk == 3 ? a.ldn : kH;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_pre_bwd_kernel(NodePreArgs a
   float* vec = TG + kTileFloats;   // [0] = first-layer bias of a head, [1] = its output weight
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.gUh == nullptr;
-  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav);
+  const int blk = node_pre_block_id(blockIdx.x % nactive, last, grav, a.flags & FEGNN_F_RF);
   const int cta = blockIdx.x / nactive, nctas = gridDim.x / nactive;
   const int ntiles = (a.N + kTM - 1) / kTM;
   const float* G = blk == 0 ? a.gP : blk == 1 ? a.gQ : blk == 2 ? a.gAv : blk == 3 ? a.gUh : nullptr;
@@ -492,7 +493,7 @@ cudaError_t launch_node_pre_fwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
-  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - (grav ? 0 : 0);
+  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
   node_pre_fwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreFwdSmem, st>>>(a, nactive); ++g_launches;
   return cudaGetLastError();
 }
@@ -501,7 +502,7 @@ cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.gUh == nullptr;
-  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0);
+  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
   node_pre_bwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreBwdSmem, st>>>(a, nactive); ++g_launches;
   return cudaGetLastError();
 }
@@ -537,6 +538,78 @@ cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   if (ntiles == 0) return cudaSuccess;
   node_h_bwd1_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   node_h_bwd2_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------- FastRF velocity head
+// models/FastRF.py:76-80,135,165: sv_i = w2 . silu(w0 n_i + b0) + b2, n_i = |v_i| (torch.norm, detached), w0 [H,1].
+__global__ void __launch_bounds__(256) rf_vel_fwd_kernel(int N, const float* __restrict__ v, const float* __restrict__ w0,
+                                                         const float* __restrict__ b0, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ sv) {
+  __shared__ float sw0[kH], sb0[kH], sw2[kH];
+  if (threadIdx.x < kH) {
+    sw0[threadIdx.x] = w0[threadIdx.x];
+    sb0[threadIdx.x] = b0[threadIdx.x];
+    sw2[threadIdx.x] = w2[threadIdx.x];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float vx = v[(size_t)i * 3], vy = v[(size_t)i * 3 + 1], vz = v[(size_t)i * 3 + 2];
+  const float n = sqrtf(vx * vx + vy * vy + vz * vz);
+  float s = b2[0];
+#pragma unroll 8
+  for (int k = 0; k < kH; ++k) s = fmaf(silu_f(fmaf(sw0[k], n, sb0[k])), sw2[k], s);
+  sv[i] = s;
+}
+// thread (k = tid & 63, lane group = tid >> 6) accumulates column k over a strided subset of the nodes
+__global__ void __launch_bounds__(256) rf_vel_bwd_kernel(int N, const float* __restrict__ v, const float* __restrict__ w0,
+                                                         const float* __restrict__ b0, const float* __restrict__ w2,
+                                                         const float* __restrict__ gsv, float* __restrict__ g_w0,
+                                                         float* __restrict__ g_b0, float* __restrict__ g_w2,
+                                                         float* __restrict__ g_b2) {
+  __shared__ float red[4][3][kH];
+  __shared__ float redb[4];
+  const int k = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const float wk = w0[k], bk = b0[k], w2k = w2[k];
+  float a_w0 = 0.f, a_b0 = 0.f, a_w2 = 0.f, a_b2 = 0.f;
+  for (int i = blockIdx.x * 4 + grp; i < N; i += gridDim.x * 4) {
+    const float vx = v[(size_t)i * 3], vy = v[(size_t)i * 3 + 1], vz = v[(size_t)i * 3 + 2];
+    const float n = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float g = gsv[i];
+    float act, der;
+    silu_grad_f(fmaf(wk, n, bk), act, der);
+    a_w2 = fmaf(g, act, a_w2);
+    const float t = g * w2k * der;
+    a_b0 += t;
+    a_w0 = fmaf(t, n, a_w0);
+    a_b2 += g;
+  }
+  red[grp][0][k] = a_w0; red[grp][1][k] = a_b0; red[grp][2][k] = a_w2;
+  if (k == 0) redb[grp] = a_b2;
+  __syncthreads();
+  if (grp == 0) {
+    const float s0 = red[0][0][k] + red[1][0][k] + red[2][0][k] + red[3][0][k];
+    const float s1 = red[0][1][k] + red[1][1][k] + red[2][1][k] + red[3][1][k];
+    const float s2 = red[0][2][k] + red[1][2][k] + red[2][2][k] + red[3][2][k];
+    if (g_w0 != nullptr) atomicAdd(g_w0 + k, s0);
+    if (g_b0 != nullptr) atomicAdd(g_b0 + k, s1);
+    if (g_w2 != nullptr) atomicAdd(g_w2 + k, s2);
+    if (k == 0 && g_b2 != nullptr) atomicAdd(g_b2, redb[0] + redb[1] + redb[2] + redb[3]);
+  }
+}
+cudaError_t launch_rf_vel_fwd(int N, const float* v, const float* w0, const float* b0, const float* w2, const float* b2,
+                              float* sv, cudaStream_t st) {
+  if (N == 0) return cudaSuccess;
+  rf_vel_fwd_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, v, w0, b0, w2, b2, sv); ++g_launches;
+  return cudaGetLastError();
+}
+cudaError_t launch_rf_vel_bwd(int N, const float* v, const float* w0, const float* b0, const float* w2, const float* gsv,
+                              float* g_w0, float* g_b0, float* g_w2, float* g_b2, int sms, cudaStream_t st) {
+  if (N == 0) return cudaSuccess;
+  int grid = (N + 3) / 4;
+  if (grid > 2 * sms) grid = 2 * sms;
+  rf_vel_bwd_kernel<<<grid, 256, 0, st>>>(N, v, w0, b0, w2, gsv, g_w0, g_b0, g_w2, g_b2); ++g_launches;
   return cudaGetLastError();
 }
 

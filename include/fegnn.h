@@ -45,6 +45,10 @@ extern "C" {
 #define FEGNN_F_TANH 4u
 #define FEGNN_F_GRAVITY 8u
 #define FEGNN_F_LAST 16u      /* last layer of the stack: phi_h / phi_hv outputs are discarded (:276) */
+#define FEGNN_F_RF 32u        /* FastRF sibling (models/FastRF.py:6-186): the layer has no phi_h / phi_hv (h and S pass
+                                 through every layer unchanged, :186) and phi_v acts on |v_i| (Linear(1,H), :76-80,135):
+                                 vel_w0 is [H,1] and the head is evaluated by fegnn_rf_vel_forward / _backward instead
+                                 of fegnn_node_pre_*.  Understood by fegnn_node_pre_* and fegnn_model_*.            */
 
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
@@ -121,8 +125,9 @@ unsigned long long fegnn_launch_count(void);
  * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
  * 256 / 512 threads per 128-edge tile (4 is the default).  Layers with attention=True or Fe > 4 always take mode 0 in
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
- * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels, 1 = tcgen05 TF32
- * (default) for fegnn_node_pre_forward.  Process-wide. */
+ * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels (default), 1 = tcgen05
+ * TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's atol 1e-4 on
+ * its U(0,10) inputs).  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
 
@@ -234,9 +239,16 @@ int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fe
                             const float* gsv, const float* gsg, float* gh /*[N,H] in: dL/dh' (residual), out: dL/dh*/,
                             void* stream);
 
+/* FastRF's velocity head (models/FastRF.py:76-80,135,165): sv_i = w2 . silu(w0 |v_i| + b0) + b2 with
+ * |v_i| = sqrt(vx^2 + vy^2 + vz^2) (detached data).  The backward accumulates (+=) into gr->vel_*. */
+int fegnn_rf_vel_forward(int32_t N, const float* v /*[N,3]*/, const fegnn_layer_params* p, float* sv /*[N]*/, void* stream);
+int fegnn_rf_vel_backward(int32_t N, const float* v, const fegnn_layer_params* p, fegnn_layer_grads* gr,
+                          const float* gsv /*[N]*/, void* stream);
+
 /* ------------------------------------------------------------------ whole layer / whole stack
  * fegnn_layer_forward == one E_GCL_vel.forward (:192-223) with S in [B,C,H];
- * fegnn_model_forward == FastEGNN.forward (:265-276) after graph prep.
+ * fegnn_model_forward == FastEGNN.forward (:265-276) after graph prep; with FEGNN_F_RF in d->flags it is
+ * FastRF.forward (models/FastRF.py:228-240): every layer reads the embedding h and the initial S.
  * Workspace layout is private; sizes come from the *_floats queries.            */
 size_t fegnn_layer_saved_floats(const fegnn_dims* d);
 int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out);

@@ -214,7 +214,7 @@ def layer_forward(params: Dict[str, Tensor], p: str, cfg: OracleConfig,
     x_new = x_new + torch.mean(-D * s_xv, dim=-1)
     x_new = x_new + _mlp2(params, f"{p}.coord_mlp_vel", h, False) * v
     if cfg.gravity is not None:
-        g = torch.as_tensor(cfg.gravity, dtype=x.dtype)                   # :259 (int64 there; promoted)
+        g = torch.as_tensor(cfg.gravity, dtype=x.dtype, device=x.device)                   # :259 (int64 there; promoted)
         x_new = x_new + _mlp2(params, f"{p}.gravity_mlp", h, False) * g
 
     # coord_model_virtual, :146-150

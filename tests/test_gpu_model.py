@@ -87,7 +87,7 @@ def test_seeded_batches_against_oracle(name, prec):
     assert not bad, (bad, [r for r in report if any(b in r for b in bad)])
 
 
-@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("prec", PRECISIONS + ["tf32_all"])
 def test_equivariance_property(prec):
     """equivariant_test.py:18-62 with seeds: FastEGNN(G R + t) == FastEGNN(G) R + t, atol 1e-4 -- in every
     arithmetic mode (the MLP inputs are invariants, so TF32 operand rounding does not break equivariance)."""
@@ -119,7 +119,11 @@ def test_equivariance_property(prec):
             return out.detach().cpu()
         a = run(x, v) @ R + t
         b = run(x @ R + t, v @ R)
-        ok = torch.allclose(a, b, atol=1e-4)
+        # "tf32_all" (opt-in tcgen05 node_pre forward) rounds the unbounded h to TF32: stated bound 1e-3 there
+        ok = torch.allclose(a, b, atol=1e-3 if prec == "tf32_all" else 1e-4)
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/equivariance_{prec}.txt", "a") as f:
+            f.write(f"seed {seed}: max |f(xR+t) - (f(x)R+t)| = {float((a - b).abs().max()):.3e}  (|out| max {float(a.abs().max()):.2f})\n")
         if not ok:
             _lib.set_precision("tf32")
         assert ok, float((a - b).abs().max())
