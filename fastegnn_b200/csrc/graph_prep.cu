@@ -139,8 +139,53 @@ __global__ void __launch_bounds__(1024) scan_small(const int* __restrict__ in, i
   if (total != nullptr && threadIdx.x == 1023) *total = run;
 }
 
+// Arrays that fit shared memory (n <= 12 K: the degree array and the digit histograms of a Water-3D-size graph, the
+// per-graph counts of any batch): coalesced load into shared memory, per-thread chunk scan there, coalesced store.
+constexpr int kSmemScan = 12160;                      // 47.5 KB of static shared memory
+__global__ void __launch_bounds__(1024) scan_smem(const int* __restrict__ in, int n, int* __restrict__ out,
+                                                  int* __restrict__ total) {
+  __shared__ int buf[kSmemScan];
+  __shared__ int wsum[32];
+  for (int i = threadIdx.x; i < n; i += 1024) buf[i] = in[i];
+  __syncthreads();
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int tsum = 0;
+  for (int i = lo; i < hi; ++i) tsum += buf[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = tsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = wsum[lane], ti = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    wsum[lane] = ti - t;
+  }
+  __syncthreads();
+  int run = wsum[w] + inc - tsum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = buf[i];
+    buf[i] = run;
+    run += v;
+  }
+  if (total != nullptr && threadIdx.x == 1023) *total = run;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) out[i] = buf[i];
+}
+
 static cudaError_t exclusive_scan(const int* in, int n, int* out, int* total, int* sums, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if (n <= kSmemScan) {
+    scan_smem<<<1, 1024, 0, st>>>(in, n, out, total); ++g_launches;
+    return cudaGetLastError();
+  }
   if (n <= kSmallScan) {
     scan_small<<<1, 1024, 0, st>>>(in, n, out, total); ++g_launches;
     return cudaGetLastError();
@@ -159,11 +204,11 @@ __global__ void count_rows_kernel(int E, const int64_t* __restrict__ row64, int*
 }
 __global__ void batch_kernel(int N, const int64_t* __restrict__ b64, int* __restrict__ batch, int* __restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) {
-    int b = (int)b64[i];
-    batch[i] = b;
-    atomicAdd(cnt + b, 1);
-  }
+  const int b = i < N ? (int)b64[i] : -1;
+  if (i < N) batch[i] = b;
+  // data_batch is non-decreasing: a warp usually holds one graph id -> one atomic per run of equal ids, not per node
+  const unsigned same = __match_any_sync(0xffffffffu, b);
+  if (b >= 0 && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(cnt + b, __popc(same));
 }
 __global__ void recip_kernel(int n, const int* __restrict__ ptr, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
