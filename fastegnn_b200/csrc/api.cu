@@ -82,6 +82,20 @@ int check_dims(const fegnn_dims* d) {
 }
 
 inline size_t al4(size_t n) { return (n + 3) & ~(size_t)3; }
+// Zero two float buffers with ONE memset node when they are neighbours in the caller's block (the model driver's
+// workspaces place them so; padding between 16-byte aligned slots is owned by the block), else with two.
+cudaError_t zero_pair(float* a, size_t na, float* b, size_t nb, cudaStream_t st) {
+  if (na == 0 || nb == 0) {
+    if (na) return cudaMemsetAsync(a, 0, sizeof(float) * na, st);
+    if (nb) return cudaMemsetAsync(b, 0, sizeof(float) * nb, st);
+    return cudaSuccess;
+  }
+  if (b == a + al4(na)) return cudaMemsetAsync(a, 0, sizeof(float) * (al4(na) + nb), st);
+  if (a == b + al4(nb)) return cudaMemsetAsync(b, 0, sizeof(float) * (al4(nb) + na), st);
+  cudaError_t e = cudaMemsetAsync(a, 0, sizeof(float) * na, st);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(b, 0, sizeof(float) * nb, st);
+}
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ld1(const fegnn_dims* d) { return 2 * kH + 1 + d->Fe; }
 inline int ldv(const fegnn_dims* d) { return 2 * kH + 1 + d->C; }
@@ -307,8 +321,7 @@ int fegnn_edge_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_la
   RQ(g && x && sv);
   EdgeArgs a = edge_args(d, g, p, x, sv);
   a.msum = sv->msum; a.tsum = sv->tsum;
-  CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
-  CK(cudaMemsetAsync(sv->tsum, 0, sizeof(float) * 3 * (size_t)d->N, S(stream)));
+  CK(zero_pair(sv->msum, kH * (size_t)d->N, sv->tsum, 3 * (size_t)d->N, S(stream)));
   const int mode = d->Fe <= kTcMaxFe ? g_edge_fwd_mode : 0;
   if (mode == 3) CK(launch_edge_fwd_tc<3>(a, sm_count(), S(stream)));
   else if (mode == 1) CK(launch_edge_fwd_tc<1>(a, sm_count(), S(stream)));
@@ -324,8 +337,7 @@ int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
   RQ(g && x && v && Z && sv && x_new && xsum_new);
   VirtArgs a = virt_args(d, g, p, x, v, Z, sv);
   a.u = sv->u; a.x_new = x_new; a.Dsum = sv->Dsum; a.Usum = sv->Usum; a.xsum_new = xsum_new;
-  CK(cudaMemsetAsync(sv->Dsum, 0, sizeof(float) * 3 * d->C * (size_t)d->B, S(stream)));
-  CK(cudaMemsetAsync(sv->Usum, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
+  CK(zero_pair(sv->Dsum, 3 * d->C * (size_t)d->B, sv->Usum, kH * d->C * (size_t)d->B, S(stream)));
   CK(cudaMemsetAsync(xsum_new, 0, sizeof(float) * 3 * (size_t)d->B, S(stream)));
   if (g_virt_fwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION)) CK(launch_virtual_fwd_tc<2>(a, sm_count(), S(stream)));
   else CK(launch_virtual_fwd(a, sm_count(), S(stream)));
@@ -404,8 +416,7 @@ int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegn
   a.g_Wxv = gr->crv_w0; a.g_bxv = gr->crv_b0; a.g_wxv = gr->crv_w2;
   a.g_WX = gr->cvv_w0; a.g_bX = gr->cvv_b0; a.g_wX = gr->cvv_w2;
   a.g_wav = gr->attv_w; a.g_bav = gr->attv_b;
-  CK(cudaMemsetAsync(gG1, 0, sizeof(float) * kH * d->C * (size_t)d->B, S(stream)));
-  CK(cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)d->Nl, S(stream)));
+  CK(zero_pair(gG1, kH * d->C * (size_t)d->B, gx, 3 * (size_t)d->Nl, S(stream)));
   // tensor-core form: two kernels; `gu` doubles as the [N,C,H] scratch that carries the total dL/du between them
   if (d->flags & FEGNN_F_LAST) a.gu = nullptr;        // last layer: phi_h is discarded, a gu buffer holds no input
   if (g_virt_bwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION) && gu != nullptr) {
@@ -428,8 +439,7 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   a.gm = gm; a.gt = gt; a.gP = gP; a.gQ = gQ; a.gx = gx;
   a.g_w1 = gr->edge_w0; a.g_W2 = gr->edge_w2; a.g_b2 = gr->edge_b2;
   a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
-  CK(cudaMemsetAsync(gP, 0, sizeof(float) * kH * (size_t)d->N, S(stream)));
-  CK(cudaMemsetAsync(gQ, 0, sizeof(float) * kH * (size_t)d->Nl, S(stream)));
+  CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
   if (g_edge_bwd_mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
   else if (g_edge_bwd_mode == 4 && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
@@ -574,13 +584,13 @@ void bwd_scratch_bind(const fegnn_dims* d, float* base, BwdScratch* s) {
   float* p = base;
   auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
   s->gh = take(N * kH);
-  s->gx[0] = take(Nl * 3); s->gx[1] = take(Nl * 3);
+  s->gx[0] = take(Nl * 3); s->gG1 = take(B * C * kH); s->gx[1] = take(Nl * 3);   // gG1 next to either gx: one memset node
   s->gZ[0] = take(B * 3 * C); s->gZ[1] = take(B * 3 * C);
   s->gS[0] = take(B * C * kH); s->gS[1] = take(B * C * kH);
   s->gxsum[0] = take(B * 3); s->gxsum[1] = take(B * 3);
   s->gDsum = take(B * 3 * C); s->gUsum = take(B * C * kH);
   s->gzh1 = take(N * kH); s->gm = take(N * kH); s->gu = take(N * C * kH);
-  s->gAv = take(N * kH); s->gG1 = take(B * C * kH);
+  s->gAv = take(N * kH);
   s->gsv = take(N); s->gsg = take(N); s->gt = take(N * 3);
   s->gP = take(N * kH); s->gQ = take(Nl * kH);
 }
