@@ -13,6 +13,7 @@ Workloads (BASELINE.json configs):
             (E ~ 2e5 directed edges, ordered by ascending length), C=3, gravity [0,-1,0], B=1.
   water3d_b20  the same clouds batched 20 per step, the reference's training batch (main_simulation.py:46).
   nbody100  (config 2) 100 graphs x 100 particles, shortest 50% of all ordered pairs.
+  protein   (config 3 shape) 50 frames x 855 backbone atoms, 10 A contact graph, shortest 50% kept.
   large     (config 5 shape, scaled by --nodes) uniform cloud, mean degree 30, C=8.
 With N>1 ranks: water3d / nbody100 (whole small graphs, as the reference batches them) go one batch per
 rank with a single weight-gradient all-reduce per step (--mode dp, SURVEY.md 5.1 mode 1, weak scaling);
@@ -88,6 +89,33 @@ def make_cloud_batch(n: int, B: int, mean_deg: float, C: int, seed: int, gravity
                 n_graphs=B, C=C, gravity=gravity, sizes=[n] * B, radius=parts[0]["radius"])
 
 
+def make_protein(n: int, B: int, cutoff_rate: float, C: int, seed: int, r: float = 10.0, blob_sigma: float = 9.5):
+    """Config 3 shape (datasets/protein/dataset.py:89,146-156,208-213): B frames of n backbone atoms as a compact blob
+    (the AdK trajectory is not available offline; sigma chosen so that ~3.4e4 directed edges per frame survive, the
+    middle of SURVEY.md 8's 2-5e4 estimate), 10 A contact graph without self loops, shortest (1 - cutoff_rate)
+    of the edges kept, ordered by ascending length."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for b in range(B):
+        x = (rng.standard_normal((n, 3)) * blob_sigma).astype(np.float32)
+        row, col = radius_graph_np(x.astype(np.float64), r)
+        length = np.linalg.norm(x[row] - x[col], axis=1)
+        order = np.argsort(length, kind="stable")[:int(row.size * (1 - cutoff_rate))]
+        row, col, length = row[order], col[order], length[order].astype(np.float32)
+        v = (rng.standard_normal((n, 3)) * 0.1).astype(np.float32)
+        q = rng.random(n).astype(np.float32)
+        parts.append(dict(x=x, v=v, nf=np.stack([np.linalg.norm(v, axis=1), q / q.max()], 1).astype(np.float32),
+                          ei=np.stack([row, col]).astype(np.int64) + b * n, ea=np.stack([length, length], 1),
+                          lm=x.mean(0, keepdims=True).T.repeat(C, axis=1)))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    cat = lambda k, ax=0: np.concatenate([p[k] for p in parts], axis=ax)
+    x, v = cat("x"), cat("v")
+    return dict(node_feat=t(cat("nf")), loc_0=t(x), vel_0=t(v), loc_t=t((x + v).astype(np.float32)),
+                edge_index=t(cat("ei", 1)), edge_attr=t(cat("ea").astype(np.float32)),
+                batch=torch.arange(B).repeat_interleave(n), loc_mean=t(np.stack([p["lm"] for p in parts]).astype(np.float32)),
+                n_graphs=B, C=C, gravity=None, sizes=[n] * B)
+
+
 def make_nbody(n: int, B: int, cutoff: float, C: int, seed: int):
     """datagen/system.py:21-39 initial conditions + datasets/nbody/dataset.py:102-113 edge selection."""
     rng = np.random.default_rng(seed)
@@ -124,6 +152,8 @@ def make_workload(name: str, seed: int, nodes: int):
         return make_cloud_batch(nodes or 8000, 20, 25.0, 3, seed, [0, -1, 0]), dict(sigma=1.0, weight=0.01, sample=3)
     if name == "nbody100":
         return make_nbody(100, 100, 0.5, 3, seed), dict(sigma=1.5, weight=0.01, sample=3)
+    if name == "protein":
+        return make_protein(855, 50, 0.5, 3, seed), dict(sigma=1.5, weight=0.01, sample=3)
     if name == "large":
         return make_cloud(nodes or 1_000_000, 30.0, 8, seed, None), dict(sigma=1.0, weight=0.01, sample=3)
     raise SystemExit(f"unknown workload {name}")
@@ -182,13 +212,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
-def oracle_step_fn(data, hp, device="cpu"):
+def oracle_step_fn(data, hp, device="cpu", model="fastegnn"):
     """The reference's training step (utils/train.py:49-170) on the restatement of the model in the reference's own
     torch op chain; device="cuda" gives the eager-PyTorch-on-the-same-GPU bar (--gpu-eager-bar)."""
     from oracle import fastegnn_oracle as orc
     cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=2, hidden_nf=H, virtual_channels=data["C"], n_layers=LAYERS,
                            gravity=data["gravity"])
-    params = {k: v.clone().to(device).requires_grad_(True) for k, v in orc.make_params(cfg, 0).items()}
+    if model == "fastrf":
+        from oracle import fastrf_oracle as rfo
+        make_params, forward = rfo.make_params, rfo.fastrf_forward
+    else:
+        make_params, forward = orc.make_params, orc.fastegnn_forward
+    params = {k: v.clone().to(device).requires_grad_(True) for k, v in make_params(cfg, 0).items()}
     if device != "cpu":
         data = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
     opt = torch.optim.Adam(list(params.values()), lr=5e-4, weight_decay=1e-12)
@@ -198,8 +233,8 @@ def oracle_step_fn(data, hp, device="cpu"):
 
     def step():
         opt.zero_grad()
-        x, Z = orc.fastegnn_forward(params, cfg, data["node_feat"], data["loc_0"], data["vel_0"], data["edge_index"],
-                                    data["batch"], data["loc_mean"], data["edge_attr"])
+        x, Z = forward(params, cfg, data["node_feat"], data["loc_0"], data["vel_0"], data["edge_index"],
+                       data["batch"], data["loc_mean"], data["edge_attr"])
         loss = torch.nn.functional.mse_loss(x, data["loc_t"])
         idx = sample_indices(data["sizes"], ns, gen).long()
         local = [(idx[b] - int(offs[b])).to(device) for b in range(len(data["sizes"]))]
@@ -228,7 +263,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="water3d", choices=["water3d", "water3d_b20", "nbody100", "large"])
+    ap.add_argument("--workload", default="water3d", choices=["water3d", "water3d_b20", "nbody100", "protein", "large"])
+    ap.add_argument("--model", default="fastegnn", choices=["fastegnn", "fastrf"],
+                    help="fastrf: the radial-field sibling (models/FastRF.py, main_protein.py:114) on the same kernels")
     ap.add_argument("--nodes", type=int, default=0)
     ap.add_argument("--mode", default="auto", choices=["auto", "dp", "partitioned"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
@@ -260,7 +297,8 @@ def main():
                "weight-gradient all-reduce per step") if part else \
               f"{world} ranks, whole graphs per rank, weight-gradient all-reduce per step"
     config = dict(workload=f"{args.workload}: N={N} nodes, E={E} directed edges{' (global)' if part else ''}, "
-                           f"B={B} graph(s), C={C}, L={LAYERS}, H={H}, gravity={data['gravity']}; "
+                           f"B={B} graph(s), C={C}, L={LAYERS}, H={H}, gravity={data['gravity']}"
+                           f"{', model=FastRF' if args.model == 'fastrf' else ''}; "
                            f"step = fwd + MSE + {hp['weight']}*MMD + bwd + Adam",
                   l2="flushed (256 MiB write) before every timed step", parallelism=par)
     metric = "layer fwd+bwd edges/sec (full train step: fwd+MSE+MMD+bwd+Adam), Water-3D shape"
@@ -270,7 +308,7 @@ def main():
         if rank != 0:
             return
         torch.set_num_threads(cores)
-        step = oracle_step_fn(data, hp)
+        step = oracle_step_fn(data, hp, model=args.model)
         t = time_cpu(step, max(1, min(args.warmup, 2)), max(1, min(args.steps, 5)))
         val = E * LAYERS / t
         line = dict(impl="reference", metric=metric, value=val, unit="edges/s", n_gpus=args.gpus,
@@ -295,8 +333,12 @@ def main():
     from fastegnn_b200 import _lib
 
     torch.manual_seed(0)
-    model = FastEGNN(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=H, virtual_channels=C, device=dev,
-                     n_layers=LAYERS, gravity=data["gravity"])
+    if args.model == "fastrf":
+        from fastegnn_b200 import FastRF as Model
+    else:
+        Model = FastEGNN
+    model = Model(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=H, virtual_channels=C, device=dev,
+                  n_layers=LAYERS, gravity=data["gravity"])
     # one rank or whole graphs per rank: the step (incl. the weight-gradient all-reduce, which NCCL lets a stream
     # capture record) is ONE CUDA graph; the partitioned path keeps its per-layer collectives eager
     use_graph = not args.no_graph and not part
@@ -453,7 +495,9 @@ def main():
                     gpu_launches=int(launches), cuda_graph=graph_state["g"] is not None)
         if graph_state["why"]:
             line["cuda_graph_error"] = graph_state["why"]
-        if not args.no_phases and not part:
+        if args.model != "fastegnn":
+            line["model"] = args.model
+        if not args.no_phases and not part and args.model == "fastegnn":
             line.update(phase_profile(model, dev_in, dev, data, E, N, B, C, flush))
             if data.get("radius") is not None:
                 try:
@@ -462,14 +506,14 @@ def main():
                     line["graph_build"] = dict(error=f"{type(exc).__name__}: {exc}"[:300])
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(cores)
-            t_cpu = time_cpu(oracle_step_fn(data, hp), 1, 3)
+            t_cpu = time_cpu(oracle_step_fn(data, hp, model=args.model), 1, 3)
             line["cpu_baseline"] = dict(value=E * LAYERS / t_cpu, unit="edges/s", cores=cores, kind="port",
                                         ms_per_step=t_cpu * 1e3,
                                         sample="the full workload: 1 warm-up + 3 timed training steps of oracle/ "
                                                "(CPU restatement of the reference's torch op chain)")
         if args.gpu_eager_bar and world == 1:
           try:
-            step = oracle_step_fn(data, hp, device=str(dev))
+            step = oracle_step_fn(data, hp, device=str(dev), model=args.model)
 
             def eager():
                 step()

@@ -21,13 +21,15 @@ __global__ void embed_fwd_kernel(int N, int Fin, const float* __restrict__ nf, c
   h[idx] = acc;
 }
 
-constexpr int kEmbedChunk = 128;
-__global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, const float* __restrict__ nf,
+// A block owns `chunk` consecutive nodes (>= 512, so the per-block partial sums -- 64 x (1 + Fin) same-address atomics --
+// stay few: the 128-node chunks this replaced spent 25 us of a Water-3D step serialising 48 k atomics on 192 addresses).
+__global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, int chunk, const float* __restrict__ nf,
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ gh, float* __restrict__ gw,
                                                              float* __restrict__ gb, float* __restrict__ gnf) {
+  __shared__ float red[3][17][kH];
   const int n = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const int i0 = blockIdx.x * kEmbedChunk, i1 = min(N, i0 + kEmbedChunk);
+  const int i0 = blockIdx.x * chunk, i1 = min(N, i0 + chunk);
   float aw[16];
 #pragma unroll
   for (int f = 0; f < 16; ++f) aw[f] = 0.f;
@@ -39,10 +41,19 @@ __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, con
     for (int f = 0; f < 16; ++f)
       if (f < Fin) aw[f] = fmaf(g, nf[(size_t)i * Fin + f], aw[f]);
   }
-  atomicAdd(gb + n, ab);
+  if (grp > 0) {
+    red[grp - 1][16][n] = ab;
 #pragma unroll
-  for (int f = 0; f < 16; ++f)
-    if (f < Fin) atomicAdd(gw + n * Fin + f, aw[f]);
+    for (int f = 0; f < 16; ++f)
+      if (f < Fin) red[grp - 1][f][n] = aw[f];
+  }
+  __syncthreads();
+  if (grp == 0) {
+    atomicAdd(gb + n, ab + red[0][16][n] + red[1][16][n] + red[2][16][n]);
+#pragma unroll
+    for (int f = 0; f < 16; ++f)
+      if (f < Fin) atomicAdd(gw + n * Fin + f, aw[f] + red[0][f][n] + red[1][f][n] + red[2][f][n]);
+  }
   if (gnf != nullptr) {
     for (int idx = threadIdx.x; idx < (i1 - i0) * Fin; idx += kThreads) {
       int i = i0 + idx / Fin, f = idx % Fin;
@@ -463,7 +474,9 @@ cudaError_t launch_embed_fwd(int N, int Fin, const float* nf, const float* w, co
 cudaError_t launch_embed_bwd(int N, int Fin, const float* nf, const float* w, const float* gh, float* gw, float* gb,
                              float* gnf, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
-  embed_bwd_kernel<<<(N + kEmbedChunk - 1) / kEmbedChunk, kThreads, 0, st>>>(N, Fin, nf, w, gh, gw, gb, gnf); ++g_launches;
+  int chunk = (N + 147) / 148;
+  if (chunk < 512) chunk = 512;
+  embed_bwd_kernel<<<(N + chunk - 1) / chunk, kThreads, 0, st>>>(N, Fin, chunk, nf, w, gh, gw, gb, gnf); ++g_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_graph_xsum(int N, const float* x, const int* batch, float* xsum, cudaStream_t st) {

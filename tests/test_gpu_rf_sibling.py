@@ -79,3 +79,41 @@ def test_rf_seeded_batches_against_oracle(kw, prec):
     with precision(prec) as (tol_out, tol_grad):
         res = gpu_rf_run(cfg, params, inp)
     compare(cfg, params, inp, res, tol_out, tol_grad, prec)
+
+
+@pytest.mark.parametrize("model_name", ["fastrf", "fastegnn"])
+def test_protein_shape_graph_built_on_device(model_name):
+    """Config 3 shape end to end on the device: 3 frames x 855 atoms, 10 A contact graph with the shortest 50% kept
+    (datasets/protein/dataset.py:146-156,208-213) from CsrGraph.from_radius, consumed as a prebuilt graph by FastRF
+    (main_protein.py:114) and FastEGNN; compared with the oracle on the exported int64 edge list."""
+    from bench import make_protein
+    from fastegnn_b200 import CsrGraph, FastEGNN, FastRF
+    from oracle import fastegnn_oracle as orc
+    from oracle import fastrf_oracle as rfo
+    from oracle import radius_graph_oracle as rgo
+    data = make_protein(855, 3, 0.5, 3, seed=4)
+    x = data["loc_0"]
+    g = CsrGraph.from_radius(x.to(DEV), data["batch"].to(DEV), 3, 10.0, 0.5, 2)
+    o = rgo.radius_graph_csr(x.numpy(), np.arange(4) * 855, 10.0, 0.5)
+    np.testing.assert_array_equal(g.row.cpu().numpy(), o["row"])
+    np.testing.assert_array_equal(g.col.cpu().numpy(), o["col"])
+    cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=2, hidden_nf=64, virtual_channels=3, n_layers=4)
+    rf = model_name == "fastrf"
+    params = (rfo if rf else orc).make_params(cfg, 77)
+    orc.rescale_coord_heads(params, 1000.0)
+    m = (FastRF if rf else FastEGNN)(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, hidden_nf=64, virtual_channels=3,
+                                     device=DEV, n_layers=4)
+    m.load_state_dict({k: v.to(DEV) for k, v in params.items()})
+    ei, ea = g.edge_index().cpu(), g.edge_attr.cpu()
+    p64 = {k: v.double() for k, v in params.items()}
+    fwd = rfo.fastrf_forward if rf else orc.fastegnn_forward
+    x64, Z64 = fwd(p64, cfg, data["node_feat"].double(), x.double(), data["vel_0"].double(), ei, data["batch"],
+                   data["loc_mean"].double(), ea.double())
+    for prec in ("fp32", "tf32"):
+        with precision(prec) as (tol_out, _), torch.no_grad():
+            xg, Zg = m(node_feat=data["node_feat"].to(DEV), node_loc=x.to(DEV), node_vel=data["vel_0"].to(DEV), edge_index=g,
+                       data_batch=data["batch"].to(DEV), loc_mean=data["loc_mean"].to(DEV), edge_attr=None)
+        # the update x' - x is what the layers compute; coordinates themselves are O(10) Angstrom
+        upd, upd64 = (xg.cpu() - x).double(), x64 - x.double()
+        assert rel_err(upd, upd64) < 5 * tol_out, (prec, rel_err(upd, upd64))
+        assert rel_err(Zg.cpu(), Z64) < tol_out, prec
