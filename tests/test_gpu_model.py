@@ -428,3 +428,9 @@ def test_full_size_water3d_properties():
         assert (p.grad is None) == dead, n
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), n
+
+
+def test_driver_smoke_entry_point():
+    """__graft_entry__.smoke() -- what the driver runs on the GPU box before the bench -- must hold in both modes."""
+    import __graft_entry__ as entry
+    entry.smoke()
