@@ -328,6 +328,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"         # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
     from fastegnn_b200 import FastEGNN, mmd_loss
     from fastegnn_b200 import _lib
