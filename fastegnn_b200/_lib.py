@@ -115,6 +115,8 @@ SIGNATURES = {
     "fegnn_edge_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp, vp]),
     "fegnn_graph_pre_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp]),
     "fegnn_node_pre_backward": (C.c_int, [_PD, _PP, _PP, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_halo_push": (C.c_int, [i32, vp, vp, vp, vp, vp, vp]),
+    "fegnn_halo_reduce_push": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),
     "fegnn_rf_vel_forward": (C.c_int, [i32, vp, _PP, vp, vp]),
     "fegnn_rf_vel_backward": (C.c_int, [i32, vp, _PP, _PP, vp, vp]),
     "fegnn_layer_saved_floats": (C.c_size_t, [_PD]),

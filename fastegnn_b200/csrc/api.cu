@@ -14,6 +14,7 @@
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "radius_graph.cu"
+#include "halo.cu"
 #include "mmd.cu"
 #include "node_kernels.cu"
 #include "virtual_kernels.cu"
@@ -474,6 +475,22 @@ int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fe
   a.g_vel_w0 = gr->vel_w0; a.g_vel_b0 = gr->vel_b0; a.g_vel_w2 = gr->vel_w2; a.g_vel_b2 = gr->vel_b2;
   a.g_grav_w0 = gr->grav_w0; a.g_grav_b0 = gr->grav_b0; a.g_grav_w2 = gr->grav_w2; a.g_grav_b2 = gr->grav_b2;
   CK(launch_node_pre_bwd(a, sm_count(), S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ halo exchange over peer memory (partitioned path)
+int fegnn_halo_push(int32_t n, const int32_t* src_row, const uint64_t* dst_q, const uint64_t* dst_x, const float* Q,
+                    const float* x, void* stream) {
+  RQ(n >= 0 && (n == 0 || (src_row && dst_q && dst_x && Q && x)));
+  CK(launch_halo_push(n, src_row, reinterpret_cast<const unsigned long long*>(dst_q),
+                      reinterpret_cast<const unsigned long long*>(dst_x), Q, x, S(stream)));
+  return 0;
+}
+int fegnn_halo_reduce_push(int32_t n, int32_t first_halo_row, const uint64_t* dst_q, const uint64_t* dst_x, const float* gQ,
+                           const float* gx, void* stream) {
+  RQ(n >= 0 && first_halo_row >= 0 && (n == 0 || (dst_q && dst_x && gQ && gx)));
+  CK(launch_halo_reduce_push(n, first_halo_row, reinterpret_cast<const unsigned long long*>(dst_q),
+                             reinterpret_cast<const unsigned long long*>(dst_x), gQ, gx, S(stream)));
   return 0;
 }
 

@@ -239,6 +239,19 @@ int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fe
                             const float* gsv, const float* gsg, float* gh /*[N,H] in: dL/dh' (residual), out: dL/dh*/,
                             void* stream);
 
+/* ------------------------------------------------------------------ halo exchange over peer memory
+ * Multi-GPU form of the layer (one big graph in spatial slabs, fastegnn_b200/partitioned.py): a node is owned by one
+ * rank; rows [N, Nl) of Q / x are copies of remote neighbours ("halo").  These two calls move the rows over NVLink
+ * with direct peer stores / remote atomics instead of pack + all-to-all + unpack.  dst_q[k] / dst_x[k] are DEVICE
+ * ADDRESSES IN THE PEER's mapping of its Q (resp. x) array (torch symmetric memory gives the base pointers), fixed by
+ * the partition plan.  Ordering between ranks (a barrier on the stream) is the caller's.
+ *   fegnn_halo_push:        for k < n: Q_peer[dst row k] = Q[src_row[k]], x_peer[...] = x[src_row[k]]     (forward)
+ *   fegnn_halo_reduce_push: for k < n: Q_owner[dst row k] += gQ[first_halo_row + k], same for gx          (backward) */
+int fegnn_halo_push(int32_t n, const int32_t* src_row /*[n]*/, const uint64_t* dst_q /*[n]*/, const uint64_t* dst_x /*[n]*/,
+                    const float* Q /*[Nl,H]*/, const float* x /*[Nl,3]*/, void* stream);
+int fegnn_halo_reduce_push(int32_t n, int32_t first_halo_row, const uint64_t* dst_q /*[n]*/, const uint64_t* dst_x /*[n]*/,
+                           const float* gQ /*[Nl,H]*/, const float* gx /*[Nl,3]*/, void* stream);
+
 /* FastRF's velocity head (models/FastRF.py:76-80,135,165): sv_i = w2 . silu(w0 |v_i| + b0) + b2 with
  * |v_i| = sqrt(vx^2 + vy^2 + vz^2) (detached data).  The backward accumulates (+=) into gr->vel_*. */
 int fegnn_rf_vel_forward(int32_t N, const float* v /*[N,3]*/, const fegnn_layer_params* p, float* sv /*[N]*/, void* stream);
