@@ -268,6 +268,8 @@ def main():
                     help="fastrf: the radial-field sibling (models/FastRF.py, main_protein.py:114) on the same kernels")
     ap.add_argument("--nodes", type=int, default=0)
     ap.add_argument("--mode", default="auto", choices=["auto", "dp", "partitioned"])
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="partitioned path: halo exchange by direct peer-memory kernels over NVLink (default) or NCCL all-to-all")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
@@ -293,8 +295,8 @@ def main():
     scaling = "weak" if not (part and args.workload == "large") else "strong"
     par = "1 rank"
     if world > 1:
-        par = (f"{world} ranks, ONE graph in {world} slabs: halo exchange + per-graph all-reduce per layer, "
-               "weight-gradient all-reduce per step") if part else \
+        par = (f"{world} ranks, ONE graph in {world} slabs: halo exchange ({'peer-memory kernels over NVLink' if args.halo == 'p2p' else 'NCCL all-to-all'}) "
+               "+ per-graph all-reduce per layer, weight-gradient all-reduce per step") if part else \
               f"{world} ranks, whole graphs per rank, weight-gradient all-reduce per step"
     config = dict(workload=f"{args.workload}: N={N} nodes, E={E} directed edges{' (global)' if part else ''}, "
                            f"B={B} graph(s), C={C}, L={LAYERS}, H={H}, gravity={data['gravity']}"
@@ -358,7 +360,13 @@ def main():
         loc = plan.localize(rank, dict(node_feat=data["node_feat"].numpy(), loc_0=data["loc_0"].numpy(),
                                        vel_0=data["vel_0"].numpy(), loc_t=data["loc_t"].numpy()),
                             dict(edge_attr=data["edge_attr"].numpy()))
-        runner = PartitionedFastEGNN(model, plan, rank, dev)
+        try:
+            runner = PartitionedFastEGNN(model, plan, rank, dev, halo=args.halo)
+        except Exception as exc:                  # symmetric memory needs one NVLink domain; NCCL works everywhere
+            if args.halo != "p2p":
+                raise
+            config["parallelism"] += f" [peer-memory halo unavailable ({type(exc).__name__}), NCCL all-to-all used]"
+            runner = PartitionedFastEGNN(model, plan, rank, dev, halo="nccl")
         n_own = runner.comm.N
         local = {k: torch.from_numpy(v) for k, v in loc.items()}
         local["loc_mean"] = data["loc_mean"]

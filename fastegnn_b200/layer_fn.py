@@ -81,7 +81,9 @@ class LayerPhases:
             gzh1, gm, gu = self._e(N, L.H), self._e(N, L.H), self._e(N, Cc, L.H)
             L.check(lib.fegnn_node_h_backward(pd, pg, pp, pgr, ps, L.ptr(gh_new), L.ptr(gzh1), L.ptr(gm), L.ptr(gu),
                                               st), "node_h_backward")
-        gAv, gG1, gx = self._e(N, L.H), self._e(B, Cc, L.H), self._e(Nl, 3)
+        gAv, gG1 = self._e(N, L.H), self._e(B, Cc, L.H)
+        own_buffers = getattr(hooks, "grad_halo_buffers", None)      # peer-memory halo path: gQ / gx live in symmetric memory
+        gQ, gx = own_buffers(self) if own_buffers is not None else (self._e(Nl, L.H), self._e(Nl, 3))
         gsv, gsg, gt = self._e(N), self._e(N), self._e(N, 3)
         # partitioned: the virtual phase adds only this rank's share of dZ -> keep it apart until it is all-reduced
         gZ_part = gZ if hooks is None else torch.zeros(B, 3, Cc, device=self.dev, dtype=torch.float32)
@@ -89,7 +91,7 @@ class LayerPhases:
                                            L.ptr(gxsum_next), L.ptr(gDsum), None if self.last else L.ptr(gUsum),
                                            L.ptr(gu), L.ptr(gAv), L.ptr(gG1), L.ptr(gx), L.ptr(gZ_part), L.ptr(gsv),
                                            L.ptr(gsg), L.ptr(gt), st), "virtual_backward")
-        gP, gQ = self._e(N, L.H), self._e(Nl, L.H)
+        gP = self._e(N, L.H)
         L.check(lib.fegnn_edge_backward(pd, pg, pp, pgr, L.ptr(x), ps, L.ptr(gm), L.ptr(gt), L.ptr(gP), L.ptr(gQ),
                                         L.ptr(gx), st), "edge_backward")
         if hooks is not None:

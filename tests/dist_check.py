@@ -56,18 +56,22 @@ def main():
                                    vel_0=data["vel_0"].numpy(), wx=wx.numpy()),
                         dict(edge_attr=data["edge_attr"].numpy()))
     lt = {k: torch.from_numpy(v).to(dev) for k, v in loc.items()}
-    runner = PartitionedFastEGNN(model, plan, rank, dev)
+    halo = os.environ.get("CHECK_HALO", "nccl")
+    runner = PartitionedFastEGNN(model, plan, rank, dev, halo=halo)
     N = runner.comm.N
-    xl = lt["loc_0"].clone().requires_grad_(True)
-    lm2 = t["loc_mean"].clone().requires_grad_(True)
-    xo, Zo = runner(lt["node_feat"], xl, lt["vel_0"], lt["edge_index"], lm2, lt["edge_attr"], n_global=n)
-    loss = (xo * lt["wx"][:N]).sum()
-    if rank == 0:                      # Z-only loss terms live on one rank (the total loss is the sum over ranks)
-        loss = loss + (Zo * wz.to(dev)).sum()
-    else:
-        loss = loss + 0.0 * Zo.sum()
-    loss.backward()
-    runner.allreduce_gradients()
+    # several steps through the same runner: the peer-memory path reuses its symmetric arrays from step to step
+    for it in range(3 if halo == "p2p" else 1):
+        model.zero_grad(set_to_none=True)
+        xl = lt["loc_0"].clone().requires_grad_(True)
+        lm2 = t["loc_mean"].clone().requires_grad_(True)
+        xo, Zo = runner(lt["node_feat"], xl, lt["vel_0"], lt["edge_index"], lm2, lt["edge_attr"], n_global=n)
+        loss = (xo * lt["wx"][:N]).sum()
+        if rank == 0:                  # Z-only loss terms live on one rank (the total loss is the sum over ranks)
+            loss = loss + (Zo * wz.to(dev)).sum()
+        else:
+            loss = loss + 0.0 * Zo.sum()
+        loss.backward()
+        runner.allreduce_gradients()
     torch.cuda.synchronize()
 
     def rel(a, b):
@@ -89,7 +93,7 @@ def main():
     ok = (errs["x"] < tol_out and errs["Z"] < tol_out and errs["gx0"] < tol_grad and errs["gloc_mean"] < tol_grad and
           worst_w < tol_grad and not bad_none)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_w{world}_c{C}_rank{rank}.txt"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{halo}_w{world}_c{C}_rank{rank}.txt"), "w") as f:
         f.write(f"world {world} rank {rank} N_owned {N} halo {runner.comm.Nl - N} ok {ok}\n")
         for k in ("x", "Z", "gx0", "gloc_mean"):
             f.write(f"{k}: {errs[k]:.3e}\n")
@@ -99,8 +103,10 @@ def main():
                 f.write(f"FAIL {k}: {e:.3e}\n")
     print(f"rank {rank}: ok={ok} x {errs['x']:.2e} Z {errs['Z']:.2e} gx0 {errs['gx0']:.2e} glm {errs['gloc_mean']:.2e} "
           f"w {worst_w:.2e} halo {runner.comm.Nl - N}", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)           # symmetric-memory handles and NCCL teardown order: exit without finalizers
 
 
 if __name__ == "__main__":
