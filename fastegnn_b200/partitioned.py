@@ -150,6 +150,33 @@ class HaloComm:
         self.allreduce(gG1, gZ_part)
 
 
+def p2p_address_tables(plan: SlabPlan, rank: int, n_layers: int, nl_max: int, base_q, base_x, base_gq, base_gx,
+                       row_bytes_q: int = 4 * L.H, row_bytes_x: int = 12):
+    """Destination byte addresses of the peer-memory halo kernels for `rank` (pure integer logic, unit-tested on the CPU
+    against a simulated address space).  base_* [world] = every rank's base address of its symmetric Q [L, nl_max, 64],
+    x [L, nl_max, 3], gQ [nl_max, 64] and gx [2, nl_max, 3] arrays.  Returns int64 numpy arrays
+        fwd_q, fwd_x [L][n_send]   where send entry k (grouped by destination, in the destination's halo order) lands,
+        bwd_q [n_recv], bwd_x [2][n_recv]   the owner's row of each of this rank's halo rows (gx has two slots)."""
+    parts = plan.parts
+    dst_row, dst_rank = [], []
+    for d in range(plan.world):
+        cnt = int(parts[rank]["send_counts"][d])
+        off = int(parts[d]["recv_counts"][:rank].sum())                # d's halo is ordered by (owner rank, owner-local id)
+        dst_row.append(parts[d]["n_own"] + off + np.arange(cnt, dtype=np.int64))
+        dst_rank.append(np.full(cnt, d, dtype=np.int64))
+    dst_row = np.concatenate(dst_row) if dst_row else np.zeros(0, np.int64)
+    dst_rank = np.concatenate(dst_rank) if dst_rank else np.zeros(0, np.int64)
+    bq, bx = np.asarray(base_q, dtype=np.int64)[dst_rank], np.asarray(base_x, dtype=np.int64)[dst_rank]
+    fwd_q = [bq + (l * nl_max + dst_row) * row_bytes_q for l in range(n_layers)]
+    fwd_x = [bx + (l * nl_max + dst_row) * row_bytes_x for l in range(n_layers)]
+    hg = parts[rank]["halo"]
+    own, lid = plan.owner[hg].astype(np.int64), plan.local_id[hg].astype(np.int64)
+    bwd_q = np.asarray(base_gq, dtype=np.int64)[own] + lid * row_bytes_q
+    bgx = np.asarray(base_gx, dtype=np.int64)[own]
+    bwd_x = [bgx + (slot * nl_max + lid) * row_bytes_x for slot in range(2)]
+    return fwd_q, fwd_x, bwd_q, bwd_x
+
+
 class P2PHaloComm(HaloComm):
     """Halo exchange by direct peer-memory access over NVLink / NVSwitch (csrc/halo.cu) instead of NCCL all-to-all.
 
@@ -175,26 +202,11 @@ class P2PHaloComm(HaloComm):
         for t in (self.Qs, self.xs, self.gQs, self.gxs):
             t.zero_()
         i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
-        # ---- forward: send entry k (grouped by destination d, in d's halo order) -> row of d's arrays
-        dst_row, dst_rank = [], []
-        for d in range(plan.world):
-            cnt = int(parts[rank]["send_counts"][d])
-            off = int(parts[d]["recv_counts"][:rank].sum())            # d's halo is ordered by (owner rank, owner-local id)
-            dst_row.append(parts[d]["n_own"] + off + np.arange(cnt, dtype=np.int64))
-            dst_rank.append(np.full(cnt, d, dtype=np.int64))
-        dst_row = np.concatenate(dst_row) if dst_row else np.zeros(0, np.int64)
-        dst_rank = np.concatenate(dst_rank) if dst_rank else np.zeros(0, np.int64)
-        bq = np.array(self.hQ.buffer_ptrs, dtype=np.int64)[dst_rank]
-        bx = np.array(self.hx.buffer_ptrs, dtype=np.int64)[dst_rank]
+        fq, fx, bq, bx = p2p_address_tables(plan, rank, n_layers, Nm, self.hQ.buffer_ptrs, self.hx.buffer_ptrs,
+                                            self.hgQ.buffer_ptrs, self.hgx.buffer_ptrs)
         self.send_idx32 = self.send_idx.to(torch.int32)
-        self.fwd_q = [i64(bq + (l * Nm + dst_row) * (4 * L.H)) for l in range(n_layers)]
-        self.fwd_x = [i64(bx + (l * Nm + dst_row) * 12) for l in range(n_layers)]
-        # ---- backward: my halo row j -> the owner's row
-        hg = parts[rank]["halo"]
-        own, lid = plan.owner[hg].astype(np.int64), plan.local_id[hg].astype(np.int64)
-        self.bwd_q = i64(np.array(self.hgQ.buffer_ptrs, dtype=np.int64)[own] + lid * (4 * L.H))
-        bgx = np.array(self.hgx.buffer_ptrs, dtype=np.int64)[own]
-        self.bwd_x = [i64(bgx + (slot * Nm + lid) * 12) for slot in range(2)]
+        self.fwd_q, self.fwd_x = [i64(a) for a in fq], [i64(a) for a in fx]
+        self.bwd_q, self.bwd_x = i64(bq), [i64(a) for a in bx]
         self._slot = 0
         self._layer_of = {}
 

@@ -108,3 +108,83 @@ def test_halo_exchange_and_allreduce_over_gloo(world):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), x, ei, out), nprocs=world, join=True)
     assert all(out[r] == (True, True, True) for r in range(world)), dict(out)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_memory_address_tables_in_a_simulated_address_space(world):
+    """The 64-bit destination tables of the peer-memory halo kernels (fegnn_halo_push / fegnn_halo_reduce_push): every
+    rank's symmetric arrays are numpy buffers at made-up base addresses; executing the tables as the kernels do (row
+    stores forward, row adds backward) must reproduce the NCCL-style exchange -- halo rows equal the owners' rows in every
+    layer, owners receive the sum of their users' halo gradients -- and never touch a byte outside the target rows."""
+    from fastegnn_b200.partitioned import SlabPlan, p2p_address_tables
+    x, ei = _cloud(n=500, deg=10, seed=3)
+    plan = SlabPlan(x, ei, world)
+    Lyr, H = 3, 64
+    nl = [p["n_own"] + p["halo"].size for p in plan.parts]
+    nm = max(nl)
+    rng = np.random.default_rng(1)
+    base_q = [(r + 1) << 40 for r in range(world)]
+    base_x = [((r + 1) << 40) + (1 << 36) for r in range(world)]
+    base_gq = [((r + 1) << 40) + (2 << 36) for r in range(world)]
+    base_gx = [((r + 1) << 40) + (3 << 36) for r in range(world)]
+    Q = [rng.standard_normal((Lyr, nm, H)).astype(np.float32) for _ in range(world)]
+    X = [rng.standard_normal((Lyr, nm, 3)).astype(np.float32) for _ in range(world)]
+    Qref = [q.copy() for q in Q]
+    Xref = [v.copy() for v in X]
+
+    def locate(addr, bases, row_bytes, rows_total):
+        r = int(addr >> 40) - 1
+        off = addr - bases[r]
+        assert 0 <= off < rows_total * row_bytes and off % row_bytes == 0
+        return r, off // row_bytes
+
+    # ---- forward push, layer by layer
+    for k in range(world):
+        fq, fx, _, _ = p2p_address_tables(plan, k, Lyr, nm, base_q, base_x, base_gq, base_gx)
+        src = plan.parts[k]["send_idx"]
+        for l in range(Lyr):
+            assert fq[l].shape == src.shape
+            for e in range(src.size):
+                d, row = locate(int(fq[l][e]), base_q, 4 * H, Lyr * nm)
+                d2, row2 = locate(int(fx[l][e]), base_x, 12, Lyr * nm)
+                assert d == d2 and row == row2 and d != k
+                assert l * nm + plan.parts[d]["n_own"] <= row < l * nm + nl[d]          # a halo row of layer l
+                Q[d].reshape(-1, H)[row] = Qref[k][l, src[e]]
+                X[d].reshape(-1, 3)[row] = Xref[k][l, src[e]]
+    for k, p in enumerate(plan.parts):
+        own, lid = plan.owner[p["halo"]], plan.local_id[p["halo"]]
+        for l in range(Lyr):
+            np.testing.assert_array_equal(Q[k][l, p["n_own"]:nl[k]], np.stack([Qref[o][l, i] for o, i in zip(own, lid)])
+                                          if own.size else Q[k][l, :0])
+            np.testing.assert_array_equal(Q[k][l, :p["n_own"]], Qref[k][l, :p["n_own"]])   # owned rows untouched
+            np.testing.assert_array_equal(Q[k][l, nl[k]:], Qref[k][l, nl[k]:])             # padding untouched
+            if own.size:
+                np.testing.assert_array_equal(X[k][l, p["n_own"]:nl[k]], np.stack([Xref[o][l, i] for o, i in zip(own, lid)]))
+
+    # ---- backward reduce push (both gx slots)
+    gQ = [rng.standard_normal((nm, H)) for _ in range(world)]
+    gX = [rng.standard_normal((2, nm, 3)) for _ in range(world)]
+    outQ = [g.copy() for g in gQ]
+    outX = [g.copy() for g in gX]
+    for slot in range(2):
+        for k, p in enumerate(plan.parts):
+            _, _, bq, bx = p2p_address_tables(plan, k, Lyr, nm, base_q, base_x, base_gq, base_gx)
+            assert bq.shape[0] == p["halo"].size
+            for j in range(p["halo"].size):
+                o, row = locate(int(bq[j]), base_gq, 4 * H, nm)
+                o2, row2 = locate(int(bx[slot][j]), base_gx, 12, 2 * nm)
+                assert o == o2 == plan.owner[p["halo"][j]] and row2 == slot * nm + row and row < plan.parts[o]["n_own"]
+                if slot == 0:
+                    outQ[o][row] += gQ[k][p["n_own"] + j]
+                outX[o].reshape(-1, 3)[row2] += gX[k][slot, p["n_own"] + j]
+    # reference: scatter-add of every user's halo rows by global node id
+    for slot in range(2):
+        accQ, accX = np.zeros((x.shape[0], H)), np.zeros((x.shape[0], 3))
+        for k, p in enumerate(plan.parts):
+            np.add.at(accQ, p["halo"], gQ[k][p["n_own"]:nl[k]])
+            np.add.at(accX, p["halo"], gX[k][slot, p["n_own"]:nl[k]])
+        for k, p in enumerate(plan.parts):
+            if slot == 0:
+                np.testing.assert_allclose(outQ[k][:p["n_own"]], gQ[k][:p["n_own"]] + accQ[p["owned"]], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(outX[k][slot, :p["n_own"]], gX[k][slot, :p["n_own"]] + accX[p["owned"]], rtol=0,
+                                       atol=1e-12)
