@@ -268,32 +268,31 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
       }
       __syncwarp();
     }
-    // ---- msum: column walk over the m tile while the tensor core runs (read-only on both sides).
-    //      thread (col, grp) sums rows 32grp..32grp+31 of column col, one atomic per run of equal row ids.
+    // ---- msum: walk over the m tile while the tensor core runs (read-only on both sides).  Thread (c4, grp) owns the
+    //      16-byte column quad c4 of the 8 rows of swizzle atom grp: one LDS.128 per row, one red.global.add.v4.f32 per
+    //      run of equal row ids (the scalar 32-row column walk this replaces was 17 % of the kernel's instructions).
     {
-      const int col = t & 63, grp = t >> 6;
-      const uint32_t cbase = (col >> 5) * (kTM * 128) + ((col & 3) << 2);
-      const int cch = (col & 31) >> 2;
+      const int c4 = t & 15, grp = t >> 4;
+      const uint8_t* gbase = At + (c4 >> 3) * (kTM * 128) + grp * 1024;
       int cur = -1;
-      float acc = 0.f;
-#pragma unroll 1
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const uint8_t* gbase = At + cbase + (grp * 4 + g8) * 1024;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = v->srow[grp * 32 + g8 * 8 + j];
-          const uint32_t o = j * 128 + ((cch ^ j) << 4);
-          float mv = *reinterpret_cast<const float*>(gbase + o);
-          if (SPLIT == 3) mv += *reinterpret_cast<const float*>(gbase + SM::kT + o);
-          if (k != cur) {
-            if (cur >= 0) atomicAdd(a.msum + (size_t)cur * kH + col, acc);
-            cur = k;
-            acc = 0.f;
-          }
-          acc += k >= 0 ? mv : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int k = v->srow[grp * 8 + j];
+        const uint32_t o = j * 128 + (((c4 & 7) ^ j) << 4);
+        float4 mv = *reinterpret_cast<const float4*>(gbase + o);
+        if (SPLIT == 3) {
+          const float4 lo = *reinterpret_cast<const float4*>(gbase + SM::kT + o);
+          mv.x += lo.x; mv.y += lo.y; mv.z += lo.z; mv.w += lo.w;
         }
+        if (k != cur) {
+          if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(a.msum + (size_t)cur * kH + c4 * 4), acc);
+          cur = k;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (k >= 0) { acc.x += mv.x; acc.y += mv.y; acc.z += mv.z; acc.w += mv.w; }
       }
-      if (cur >= 0) atomicAdd(a.msum + (size_t)cur * kH + col, acc);
+      if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(a.msum + (size_t)cur * kH + c4 * 4), acc);
     }
     umma::mbar_wait(&v->bar[1], phase);
     umma::fence_after();

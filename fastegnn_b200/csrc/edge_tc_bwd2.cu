@@ -518,27 +518,26 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
     }
     phase ^= 1;
     first_tile = false;
-    // ---- gP: row-segment sums of gz1 (column walk over TM) ; gx: both ends of every edge
+    // ---- gP: row-segment sums of gz1 over TM ; gx: both ends of every edge.  Thread (c4, grp) owns the 16-byte column
+    //      quad c4 of RPG4 consecutive rows: one LDS.128 per row, one red.global.add.v4.f32 per run of equal row ids.
     {
-      constexpr int GR = NT / 64, RPG = kTM / GR;       // row groups, rows per group
-      const int col = t & 63, grp = t >> 6;
-      const uint32_t cbase = (col >> 5) * (kTM * 128) + ((col & 7) << 2);
-      const int c8 = (col & 31) >> 3;
+      constexpr int GR4 = NT / 16, RPG4 = kTM / GR4;    // 32 groups x 4 rows (512 threads) / 16 groups x 8 rows (256)
+      const int c4 = t & 15, grp = t >> 4;
       int cur = -1;
-      float acc = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < RPG; ++i) {
-        const int rr = grp * RPG + i;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < RPG4; ++i) {
+        const int rr = grp * RPG4 + i;
         const int k = v->srow[rr];
-        const float mv = *reinterpret_cast<const float*>(TM + cbase + rr * 128 + ((c8 ^ (rr & 3)) << 5));
+        const float4 mv = *reinterpret_cast<const float4*>(TM + mn_chunk_off(rr, c4, kTM));
         if (k != cur) {
-          if (cur >= 0) atomicAdd(a.gP + (size_t)cur * kH + col, acc);
+          if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(a.gP + (size_t)cur * kH + c4 * 4), acc);
           cur = k;
-          acc = 0.f;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        acc += k >= 0 ? mv : 0.f;
+        if (k >= 0) { acc.x += mv.x; acc.y += mv.y; acc.z += mv.z; acc.w += mv.w; }
       }
-      if (cur >= 0) atomicAdd(a.gP + (size_t)cur * kH + col, acc);
+      if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(a.gP + (size_t)cur * kH + c4 * 4), acc);
     }
     if (t < kTM) {
       const int r = v->srow[t], c = v->scol[t];
