@@ -21,8 +21,9 @@ __global__ void embed_fwd_kernel(int N, int Fin, const float* __restrict__ nf, c
   h[idx] = acc;
 }
 
-// A block owns `chunk` consecutive nodes (>= 512, so the per-block partial sums -- 64 x (1 + Fin) same-address atomics --
-// stay few: the 128-node chunks this replaced spent 25 us of a Water-3D step serialising 48 k atomics on 192 addresses).
+// A block owns `chunk` consecutive nodes; its four row groups are summed in shared memory before the 64 x (1 + Fin)
+// atomics.  The kernel is bound by the latency of its strided row loop, not by the atomics (measured: 16 blocks of 512
+// nodes took 72 us on Water-3D, 63 blocks of 128 nodes 26 us), so chunks are SMALL (>= 64 nodes, ~4 blocks per SM).
 __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, int chunk, const float* __restrict__ nf,
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ gh, float* __restrict__ gw,
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, int
 #pragma unroll
   for (int f = 0; f < 16; ++f) aw[f] = 0.f;
   float ab = 0.f;
+#pragma unroll 4
   for (int i = i0 + grp; i < i1; i += 4) {
     float g = gh[(size_t)i * kH + n];
     ab += g;
@@ -474,8 +476,8 @@ cudaError_t launch_embed_fwd(int N, int Fin, const float* nf, const float* w, co
 cudaError_t launch_embed_bwd(int N, int Fin, const float* nf, const float* w, const float* gh, float* gw, float* gb,
                              float* gnf, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
-  int chunk = (N + 147) / 148;
-  if (chunk < 512) chunk = 512;
+  int chunk = (N + 4 * 148 - 1) / (4 * 148);
+  if (chunk < 64) chunk = 64;
   embed_bwd_kernel<<<(N + chunk - 1) / chunk, kThreads, 0, st>>>(N, Fin, chunk, nf, w, gh, gw, gb, gnf); ++g_launches;
   return cudaGetLastError();
 }
