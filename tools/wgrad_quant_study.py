@@ -5,6 +5,8 @@ if the operand tiles of its weight-gradient GEMMs (m, a1, g3, g2, gz1 -- 128 edg
   bf16      8-bit mantissa                          (halves the tile context, no scaling needed)
   fp16      10-bit mantissa, 5-bit exponent, unscaled
   fp16s     fp16 after dividing each 128 x 64 tile by its max-abs (one fp32 scale per tile, folded back after the GEMM)
+  fp16g     gradient tiles fp16 with ONE power-of-two scale per launch and tensor, activation tiles plain fp16
+  mixed     gradient tiles bf16, activation tiles fp16
 Everything else of the 4-layer backward stays fp64 (oracle/staged.py), so the numbers isolate the operand storage.
 Reported: worst relative error (of the tensor's max) of the edge-phase weight gradients over the layers, per format.
 
@@ -50,6 +52,9 @@ def q_tile(x, fmt):
             s = blk.abs().max().clamp(min=1e-300)
             out[t0:t0 + TILE] = (blk / s).to(torch.float16).double() * s
         return out
+    if fmt == "fp16g":          # ONE power-of-two scale per launch: the tensor's max lands at 2^8 (a bound pre-pass would be looser)
+        s = 2.0 ** (torch.floor(torch.log2(x.abs().max().clamp(min=1e-300))) - 8)
+        return (x / s).to(torch.float16).double() * s
     raise ValueError(fmt)
 
 
@@ -66,13 +71,16 @@ def edge_bwd_quant(fmt):
         gmm = gm[row] + gz3 @ w.W3
         gz2 = gmm * staged.dsilu(r["z2"])
         gz1 = (gz2 @ w.W2) * staged.dsilu(r["z1"])
-        q = lambda t: q_tile(t, fmt)
+        # "mixed": gradient tiles bf16 (no scale needed), activation tiles fp16; "fp16g": gradients with one scale per
+        # launch, activations plain fp16
+        qg = lambda t: q_tile(t, "bf16" if fmt == "mixed" else fmt)
+        qa = lambda t: q_tile(t, "fp16" if fmt in ("mixed", "fp16g") else fmt)
         wg = dict(out["wg"])
         ones_q_ea = torch.cat([torch.ones_like(r["q"])[:, None], r["q"][:, None], ea], dim=1)
-        aux = q(ones_q_ea)                                  # the [128 x 32] aux tile (1, q, ea...)
-        wg["W3"], wg["b3"] = q(gz3).T @ q(r["m"]), q(gz3).T @ aux[:, 0]
-        wg["W2"], wg["b2"] = q(gz2).T @ q(r["a1"]), q(gz2).T @ aux[:, 0]
-        wg["wq"], wg["Wa"] = q(gz1).T @ aux[:, 1], q(gz1).T @ aux[:, 2:]
+        aux = qa(ones_q_ea)                                 # the aux tile (1, q, ea...)
+        wg["W3"], wg["b3"] = qg(gz3).T @ qa(r["m"]), qg(gz3).T @ aux[:, 0]
+        wg["W2"], wg["b2"] = qg(gz2).T @ qa(r["a1"]), qg(gz2).T @ aux[:, 0]
+        wg["wq"], wg["Wa"] = qg(gz1).T @ aux[:, 1], qg(gz1).T @ aux[:, 2:]
         out["wg"] = wg
         return out
     return f
@@ -106,7 +114,7 @@ def main():
     for name, kw in cases.items():
         ref = run(kw, "fp64")
         print(f"== {name}")
-        for fmt in ("tf32", "fp16s", "bf16", "fp16"):
+        for fmt in ("tf32", "fp16s", "fp16g", "mixed", "bf16", "fp16"):
             g = run(kw, fmt)
             worst, where = 0.0, ""
             for k, v in ref.items():
