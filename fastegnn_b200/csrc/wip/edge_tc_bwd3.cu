@@ -1,0 +1,616 @@
+// edge_tc_bwd3.cu -- WORK IN PROGRESS, NOT PART OF THE BUILD (api.cu does not include it; compile check:
+// fastegnn_b200/csrc/wip/compile_check.sh).  Draft of the third tcgen05 formulation of the fused real-edge backward,
+// fp16 operand tiles (kind::f16, fp32 accumulation) and TWO tiles in flight per SM.
+//
+// Same contract as bwd2::edge_bwd_tc2_kernel (autograd of models/FastEGNN.py:102-108,125-129,156).  What changes:
+//   * one CTA = two independent 256-thread GROUPS (named barriers 1 / 2), each walking its own stream of 128-edge tiles
+//     through the same four dependent GEMM stages -- two tiles in flight with no cross-group choreography;
+//   * every operand is fp16: weights ONE 8 KB copy each (under SWIZZLE_128B the same row-major tile is the K-major B of the
+//     recompute and the MN-major B of the dgrad -- tf32 needed two copies); a1 / m / g3 / g2 / gz1 tiles 16 KB instead of
+//     32 KB; the TS-form A operand is two fp16 per 32-bit tensor-memory column; all layouts probed on the B200
+//     (tools/umma_probe_f16.cu, profiles/umma_probe_f16_r1_s5.txt);
+//   * gradients are stored times ONE power-of-two scale per launch and tensor (s3, s2, s1: numerics identical to TF32,
+//     tools/wgrad_quant_study.py); the scale is taken out again in the next epilogue and in the accumulator flush;
+//   * the four stages of a group use ONE fp32 accumulator (they are sequential); the weight-gradient accumulators
+//     (M = 64) of group 0 sit at lane 0 and those of group 1 at lane 16 of the SAME columns.
+// Shared memory: weights 16 KB + 2 x (5 tiles x 16 KB + vectors) ~ 200 KB.  Tensor memory: 2 x 128 + 152 columns.
+// Known precision difference to bwd2: the gP row-segment sums walk the fp16 gz1 tile (bwd2 walks an fp32 tile).
+#include "../common.cuh"
+#include "../umma.cuh"
+#include <cuda_fp16.h>
+
+namespace fegnn {
+namespace bwd3 {
+
+using bwd2::elect_one;
+using bwd2::silu_grad_tc;
+using bwd2::tmem_ld;
+using bwd2::tmem_st;
+using bwd2::tmem_st_wait;
+
+constexpr int kGroupThreads = 256, kGroups = 2, kThreads3 = kGroupThreads * kGroups, kCPT = 32;
+constexpr int kTileBytes = kTM * 128;            // [128 rows][64 fp16] = 16 KB, 128-byte rows, 8-row atoms, chunks ^ (row & 7)
+constexpr int kWBytes = kH * 128;                // [64][64] fp16 = 8 KB
+
+// byte offset of 16-byte chunk c8 (8 fp16: columns 8 c8 .. +7) of a row
+__device__ __forceinline__ uint32_t h_chunk_off(int row, int c8) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c8 ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint64_t make_desc_h(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // MN-major: next 64-element block along M / N; K-major: unused
+  d |= (uint64_t)(1024 >> 4) << 32;                     // SBO: next 8-row atom
+  d |= 1ull << 46;
+  d |= 2ull << 61;                                      // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ss_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// D[128 x 64] = A(tmem, packed fp16 [128 x 64]) * W^T : W [64 n][64 k] read K-major (4 MMAs of K = 16 = 32 bytes of a row)
+__device__ __forceinline__ void gemm_ts_k(uint32_t tmem_d, uint32_t tmem_a, uint64_t dW, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) mma_ts_f16(tmem_d, tmem_a + ks * 8, desc_add(dW, ks * 32), idesc, ks > 0);
+}
+// D[128 x 64] = A(tmem) * W : the same tile read MN-major (N = k, K = n; 16 K rows = 2048 bytes per MMA)
+__device__ __forceinline__ void gemm_ts_mn(uint32_t tmem_d, uint32_t tmem_a, uint64_t dW, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) mma_ts_f16(tmem_d, tmem_a + ks * 8, desc_add(dW, ks * 2048), idesc, ks > 0);
+}
+// D[64 x N] (+)= G^T B over the 128 edges of the tile (8 MMAs of K = 16 rows)
+__device__ __forceinline__ void gemm_wgrad(uint32_t tmem_d, uint64_t dG, uint64_t dB, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) mma_ss_f16(tmem_d, desc_add(dG, ks * 2048), desc_add(dB, ks * 2048), idesc, (ks > 0 || accumulate) ? 1u : 0u);
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(kGroupThreads) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+
+// this thread's 32 columns (column group cg) of row `row` -> fp16 tile (4 chunks of 16 bytes) and / or packed registers
+__device__ __forceinline__ void pack_row(const float (&v)[kCPT], uint32_t (&p)[kCPT / 2]) {
+#pragma unroll
+  for (int j = 0; j < kCPT / 2; ++j) p[j] = pack2(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void store_row_h(uint8_t* tile, int row, int cg, const uint32_t (&p)[kCPT / 2]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + h_chunk_off(row, cg * 4 + c)) = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+}
+__device__ __forceinline__ void load_row_h(const uint8_t* tile, int row, int cg, uint32_t (&p)[kCPT / 2]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile + h_chunk_off(row, cg * 4 + c));
+    p[4 * c] = u.x; p[4 * c + 1] = u.y; p[4 * c + 2] = u.z; p[4 * c + 3] = u.w;
+  }
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&p)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(p[8]),
+         "r"(p[9]), "r"(p[10]), "r"(p[11]), "r"(p[12]), "r"(p[13]), "r"(p[14]), "r"(p[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct SharedVec {                 // read-only after the prologue, both groups
+  float wq[kH], Wa[kTcMaxFe * kH], b2[kH], b3[kH], w4[kH];
+  float cw4[kH];                   // dw4 column sums (shared-memory atomics at kernel end)
+  uint32_t tmem_slot;
+};
+struct GroupVec {                  // per group
+  int srow[kTM], scol[kTM];
+  float sq[kTM], snrm[kTM], sd[kTM * 3], sgte[kTM * 3], sgs[kTM], sea[kTM * kTcMaxFe];
+  float spart[kTM], sgqp[kTM], ss[kTM];
+  uint64_t bar[6];
+};
+struct Smem3 {
+  static constexpr int off_W2 = 0, off_W3 = kWBytes;
+  static constexpr int off_groups = 2 * kWBytes;
+  // per group: TA | TM | AUX | TG | D1 (TM | AUX and TA | .. | AUX are the two-block B operands of the weight-gradient GEMMs)
+  static constexpr int g_TA = 0, g_TM = kTileBytes, g_AUX = 2 * kTileBytes, g_TG = 3 * kTileBytes, g_D1 = 4 * kTileBytes;
+  static constexpr int g_vec = 5 * kTileBytes;
+  static constexpr int g_bytes = ((g_vec + (int)sizeof(GroupVec) + 1023) / 1024) * 1024;
+  static constexpr int off_svec = off_groups + kGroups * g_bytes;
+  static constexpr size_t bytes = off_svec + sizeof(SharedVec) + 1024;
+};
+// tensor-memory columns: group g uses [128 g, 128 g + 128); the weight-gradient accumulators are shared (lane 16 g)
+constexpr uint32_t kACC = 0, kOPA = 64, kD2T = 96;
+constexpr uint32_t kR3 = 256, kR2 = 336, kDXZ = 416;        // [dW3 64 | aux 8], [dW2 64 | aux 8], [aux 8]
+
+struct Scales { float s3, s2, s1; };      // power-of-two factors applied to g3, g2, gz1 before the fp16 rounding
+
+__global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, Scales sc) {
+  using SM = Smem3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  SharedVec* sv = reinterpret_cast<SharedVec*>(smem + SM::off_svec);
+  const int t = threadIdx.x, G = t >> 8, tg = t & 255, wg = tg >> 5, lane = t & 31;
+  const int quarter = wg & 3, cg = wg >> 2, row = quarter * 32 + lane, c0 = cg * kCPT;
+  uint8_t* gs = smem + SM::off_groups + G * SM::g_bytes;
+  GroupVec* v = reinterpret_cast<GroupVec*>(gs + SM::g_vec);
+  uint8_t *TA = gs + SM::g_TA, *TM = gs + SM::g_TM, *AUX = gs + SM::g_AUX, *TG = gs + SM::g_TG, *D1 = gs + SM::g_D1;
+  const bool use_tanh = a.flags & FEGNN_F_TANH, norm = a.flags & FEGNN_F_NORMALIZE;
+  const float r3 = 1.f / sc.s3, r2 = 1.f / sc.s2, r1 = 1.f / sc.s1;
+
+  // ---- prologue (whole CTA): fp16 weight tiles, vectors, zero AUX, barriers, tensor memory
+  for (int i = t; i < kH * 8; i += kThreads3) {            // 64 rows x 8 chunks of 8 columns
+    const int n = i >> 3, c8 = i & 7;
+    const float4 w20 = *reinterpret_cast<const float4*>(a.W2 + (size_t)n * kH + c8 * 8);
+    const float4 w21 = *reinterpret_cast<const float4*>(a.W2 + (size_t)n * kH + c8 * 8 + 4);
+    const float4 w30 = *reinterpret_cast<const float4*>(a.W3 + (size_t)n * kH + c8 * 8);
+    const float4 w31 = *reinterpret_cast<const float4*>(a.W3 + (size_t)n * kH + c8 * 8 + 4);
+    *reinterpret_cast<uint4*>(smem + SM::off_W2 + h_chunk_off(n, c8)) =
+        make_uint4(pack2(w20.x, w20.y), pack2(w20.z, w20.w), pack2(w21.x, w21.y), pack2(w21.z, w21.w));
+    *reinterpret_cast<uint4*>(smem + SM::off_W3 + h_chunk_off(n, c8)) =
+        make_uint4(pack2(w30.x, w30.y), pack2(w30.z, w30.w), pack2(w31.x, w31.y), pack2(w31.z, w31.w));
+  }
+  for (int i = t; i < kH; i += kThreads3) {
+    sv->wq[i] = a.w1[(size_t)i * a.ld1 + 2 * kH];
+    for (int f = 0; f < a.Fe; ++f) sv->Wa[f * kH + i] = a.w1[(size_t)i * a.ld1 + 2 * kH + 1 + f];
+    sv->b2[i] = a.b2[i];
+    sv->b3[i] = a.b3[i];
+    sv->w4[i] = a.w4[i];
+    sv->cw4[i] = 0.f;
+  }
+  for (int i = tg; i < kTileBytes / 16; i += kGroupThreads) reinterpret_cast<uint4*>(AUX)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tg == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) umma::mbar_init(&v->bar[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (t < 32) umma::tmem_alloc<512>(&sv->tmem_slot);
+  umma::fence_smem_to_async();
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem = sv->tmem_slot;
+  const uint32_t tbase = tmem + G * 128;                                          // this group's columns
+  const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);                // + this thread's lane
+  const uint32_t twg = tmem + ((uint32_t)(16 * G) << 16);                         // weight-gradient accumulators: lane 0 / 16
+  const uint32_t id_k = idesc_f16(128, 64, 0, 0), id_mn = idesc_f16(128, 64, 0, 1);
+  const uint32_t id_wg72 = idesc_f16(64, 72, 1, 1), id_aux = idesc_f16(64, 8, 1, 1);
+  const uint64_t dW2k = make_desc_h(umma::smem_u32(smem + SM::off_W2), 16), dW3k = make_desc_h(umma::smem_u32(smem + SM::off_W3), 16);
+  const uint64_t dW2m = make_desc_h(umma::smem_u32(smem + SM::off_W2), kWBytes), dW3m = make_desc_h(umma::smem_u32(smem + SM::off_W3), kWBytes);
+  const uint64_t dTG = make_desc_h(umma::smem_u32(TG), kTileBytes);               // A of the weight-gradient GEMMs (M = 64: one block)
+  const uint64_t dTM_AUX = make_desc_h(umma::smem_u32(TM), kTileBytes);           // B = [TM | AUX], N = 72
+  const uint64_t dTA_AUX = make_desc_h(umma::smem_u32(TA), 2 * kTileBytes);       // B = [TA | AUX], N = 72
+  const uint64_t dTMa = make_desc_h(umma::smem_u32(TM), kTileBytes);              // A = gz1 (after m is dead)
+  const uint64_t dAUX = make_desc_h(umma::smem_u32(AUX), kTileBytes);             // B = AUX, N = 8
+  uint32_t phase = 0;
+  bool first_tile = true;
+  float pw4[kCPT];
+#pragma unroll
+  for (int j = 0; j < kCPT; ++j) pw4[j] = 0.f;
+
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  for (int tile = blockIdx.x * kGroups + G; tile < ntiles; tile += gridDim.x * kGroups) {
+    if (!first_tile) {                           // the previous tile's last GEMM still reads AUX and TM
+      umma::mbar_wait(&v->bar[4], phase ^ 1);
+      umma::fence_after();
+    }
+    umma::fence_before();
+    group_sync(G);
+    // ---- geometry: one thread per edge
+    if (tg < kTM) {
+      const int e = tile * kTM + tg;
+      int r = -1, c = 0;
+      float d0 = 0, d1 = 0, d2 = 0, q = 0, nrm = 1.f, g0 = 0, g1 = 0, g2 = 0;
+      float ea[kTcMaxFe];
+#pragma unroll
+      for (int f = 0; f < kTcMaxFe; ++f) ea[f] = 0.f;
+      if (e < a.E) {
+        r = a.row[e];
+        c = a.col[e];
+        d0 = a.x[(size_t)r * 3 + 0] - a.x[(size_t)c * 3 + 0];
+        d1 = a.x[(size_t)r * 3 + 1] - a.x[(size_t)c * 3 + 1];
+        d2 = a.x[(size_t)r * 3 + 2] - a.x[(size_t)c * 3 + 2];
+        q = d0 * d0 + d1 * d1 + d2 * d2;
+        g0 = a.gt[(size_t)r * 3 + 0]; g1 = a.gt[(size_t)r * 3 + 1]; g2 = a.gt[(size_t)r * 3 + 2];
+#pragma unroll
+        for (int f = 0; f < kTcMaxFe; ++f)
+          if (f < a.Fe) ea[f] = a.ea[(size_t)e * a.Fe + f];
+      }
+#pragma unroll
+      for (int f = 0; f < kTcMaxFe; ++f) v->sea[tg * kTcMaxFe + f] = ea[f];
+      v->sd[tg * 3 + 0] = d0; v->sd[tg * 3 + 1] = d1; v->sd[tg * 3 + 2] = d2;
+      if (norm) {
+        nrm = sqrtf(q) + a.eps;
+        const float inv = 1.f / nrm;
+        d0 *= inv; d1 *= inv; d2 *= inv;
+      }
+      v->srow[tg] = r;
+      v->scol[tg] = c;
+      v->sq[tg] = q;
+      v->snrm[tg] = nrm;
+      v->sgte[tg * 3 + 0] = g0; v->sgte[tg * 3 + 1] = g1; v->sgte[tg * 3 + 2] = g2;
+      v->sgs[tg] = d0 * g0 + d1 * g1 + d2 * g2;
+      // aux columns (1, q, ea0..ea3, 0, 0) = chunk 0 of the row
+      *reinterpret_cast<uint4*>(AUX + h_chunk_off(tg, 0)) =
+          make_uint4(pack2(r >= 0 ? 1.f : 0.f, q), pack2(ea[0], ea[1]), pack2(ea[2], ea[3]), 0u);
+    }
+    group_sync(G);
+    // ---- assembly: a1 = silu(z1) -> TA, silu'(z1) -> D1 (both fp16).  Half-warp per row, 4 columns per lane.
+    {
+      const int l16 = lane & 15, hsel = lane >> 4;
+      const float4 wq = *reinterpret_cast<const float4*>(sv->wq + 4 * l16);
+      constexpr int RPW = kTM / 8;               // 16 rows per warp
+#pragma unroll 1
+      for (int i0 = 0; i0 < RPW; i0 += 8) {
+        float4 p[4], qv[4];
+        int ri[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = wg * RPW + i0 + 2 * j + hsel;
+          ri[j] = v->srow[rr];
+          p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ri[j] >= 0) {
+            p[j] = *reinterpret_cast<const float4*>(a.P + (size_t)ri[j] * kH + 4 * l16);
+            qv[j] = *reinterpret_cast<const float4*>(a.Q + (size_t)v->scol[rr] * kH + 4 * l16);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = wg * RPW + i0 + 2 * j + hsel;
+          const float qi = v->sq[rr];
+          float z0 = p[j].x + qv[j].x + qi * wq.x, z1 = p[j].y + qv[j].y + qi * wq.y,
+                z2 = p[j].z + qv[j].z + qi * wq.z, z3 = p[j].w + qv[j].w + qi * wq.w;
+#pragma unroll
+          for (int f = 0; f < kTcMaxFe; ++f) {
+            if (f < a.Fe) {
+              const float ef = v->sea[rr * kTcMaxFe + f];
+              const float4 wf = *reinterpret_cast<const float4*>(sv->Wa + f * kH + 4 * l16);
+              z0 = fmaf(ef, wf.x, z0); z1 = fmaf(ef, wf.y, z1); z2 = fmaf(ef, wf.z, z2); z3 = fmaf(ef, wf.w, z3);
+            }
+          }
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f), od = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ri[j] >= 0) {
+            silu_grad_tc(z0, o.x, od.x); silu_grad_tc(z1, o.y, od.y);
+            silu_grad_tc(z2, o.z, od.z); silu_grad_tc(z3, o.w, od.w);
+          }
+          const uint32_t off = h_chunk_off(rr, l16 >> 1) + ((l16 & 1) << 3);       // 4 fp16 = half a chunk
+          *reinterpret_cast<uint2*>(TA + off) = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+          *reinterpret_cast<uint2*>(D1 + off) = make_uint2(pack2(od.x, od.y), pack2(od.z, od.w));
+        }
+      }
+    }
+    group_sync(G);
+    // ---- row owners move a1 into tensor memory (packed fp16 A operand of G1)
+    {
+      uint32_t p[kCPT / 2];
+      load_row_h(TA, row, cg, p);
+      tmem_st16u(tlane + kOPA + cg * 16, p);
+      tmem_st_wait();
+    }
+    umma::fence_smem_to_async();       // TA / AUX: generic-proxy writes -> visible to the tensor core
+    umma::fence_before();
+    group_sync(G);
+    if (wg == 0) {
+      umma::fence_after();
+      if (elect_one()) {
+        gemm_ts_k(tbase + kACC, tbase + kOPA, dW2k, id_k);                      // G1: z2 = a1 W2^T
+        umma::commit(&v->bar[0]);
+      }
+      __syncwarp();
+    }
+    umma::mbar_wait(&v->bar[0], phase);
+    umma::fence_after();
+    // ---- epilogue 1: m = silu(z2 + b2) -> A operand and TM ; silu'(z2) -> D2T (packed fp16)
+    {
+      float m[kCPT];
+      uint32_t pm[kCPT / 2], pd[kCPT / 2];
+      tmem_ld<kCPT>(tlane + kACC + c0, m);
+#pragma unroll
+      for (int j = 0; j < kCPT; j += 2) {
+        float a0, a1v, e0, e1;
+        silu_grad_tc(m[j] + sv->b2[c0 + j], a0, e0);
+        silu_grad_tc(m[j + 1] + sv->b2[c0 + j + 1], a1v, e1);
+        pm[j >> 1] = pack2(a0, a1v);
+        pd[j >> 1] = pack2(e0, e1);
+      }
+      tmem_st16u(tlane + kOPA + cg * 16, pm);
+      tmem_st16u(tlane + kD2T + cg * 16, pd);
+      store_row_h(TM, row, cg, pm);
+      tmem_st_wait();
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    group_sync(G);
+    if (wg == 0) {
+      umma::fence_after();
+      if (elect_one()) {
+        gemm_ts_k(tbase + kACC, tbase + kOPA, dW3k, id_k);                      // G2: z3 = m W3^T
+        umma::commit(&v->bar[1]);
+      }
+      __syncwarp();
+    }
+    umma::mbar_wait(&v->bar[1], phase);
+    umma::fence_after();
+    // ---- epilogue 2: a3, silu'(z3), s = w4 . a3 ; g3 = gs w4 silu'(z3) (times s3) -> A operand and TG
+    {
+      float a3[kCPT];
+      uint32_t pg[kCPT / 2];
+      tmem_ld<kCPT>(tlane + kACC + c0, a3);
+      float part = 0.f;
+      float d3[kCPT];
+#pragma unroll
+      for (int j = 0; j < kCPT; ++j) {
+        silu_grad_tc(a3[j] + sv->b3[c0 + j], a3[j], d3[j]);
+        part = fmaf(a3[j], sv->w4[c0 + j], part);
+      }
+      if (cg == 1) v->spart[row] = part;
+      group_sync(G);
+      const float other = cg == 0 ? v->spart[row] : 0.f;
+      group_sync(G);
+      if (cg == 0) v->spart[row] = part;
+      group_sync(G);
+      float s = cg == 0 ? part + other : part + v->spart[row];
+      float gsv = v->sgs[row];
+      if (use_tanh) {
+        s = tanhf(s);
+        gsv *= (1.f - s * s);
+      }
+      if (cg == 0) v->ss[row] = s;
+      const float gscaled = gsv * sc.s3;
+#pragma unroll
+      for (int j = 0; j < kCPT; j += 2) {
+        pw4[j] = fmaf(gsv, a3[j], pw4[j]);
+        pw4[j + 1] = fmaf(gsv, a3[j + 1], pw4[j + 1]);
+        pg[j >> 1] = pack2(gscaled * sv->w4[c0 + j] * d3[j], gscaled * sv->w4[c0 + j + 1] * d3[j + 1]);
+      }
+      tmem_st16u(tlane + kOPA + cg * 16, pg);
+      store_row_h(TG, row, cg, pg);
+      tmem_st_wait();
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    group_sync(G);
+    if (wg == 0) {
+      umma::fence_after();
+      if (elect_one()) {
+        gemm_ts_mn(tbase + kACC, tbase + kOPA, dW3m, id_mn);                    // D3 : g3 W3
+        umma::commit(&v->bar[2]);
+        gemm_wgrad(twg + kR3, dTG, dTM_AUX, id_wg72, !first_tile);              // [dW3 | db3 ..] += g3^T [m | 1, q, ea]
+        umma::commit(&v->bar[5]);                                               // TG / TM may be overwritten after this
+      }
+      __syncwarp();
+    }
+    umma::mbar_wait(&v->bar[2], phase);
+    umma::fence_after();
+    // ---- epilogue 3: g2 = (gm[row] + g3 W3) * silu'(z2) (times s2) -> A operand and TG
+    {
+      float g2v[kCPT];
+      uint32_t pd[kCPT / 2], pg[kCPT / 2];
+      tmem_ld<kCPT>(tlane + kACC + c0, g2v);
+      tmem_ld16u(tlane + kD2T + cg * 16, pd);
+      const int r = v->srow[row];
+#pragma unroll
+      for (int j = 0; j < kCPT; ++j) g2v[j] *= r3;
+      if (r >= 0 && a.gm != nullptr) {
+        const float4* gmr = reinterpret_cast<const float4*>(a.gm + (size_t)r * kH + c0);
+#pragma unroll
+        for (int ch = 0; ch < kCPT / 4; ++ch) {
+          const float4 g = gmr[ch];
+          g2v[ch * 4] += g.x; g2v[ch * 4 + 1] += g.y; g2v[ch * 4 + 2] += g.z; g2v[ch * 4 + 3] += g.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kCPT; j += 2) {
+        const float2 dd = unpack2(pd[j >> 1]);
+        const float x0 = r >= 0 ? g2v[j] * dd.x * sc.s2 : 0.f, x1 = r >= 0 ? g2v[j + 1] * dd.y * sc.s2 : 0.f;
+        pg[j >> 1] = pack2(x0, x1);
+      }
+      tmem_st16u(tlane + kOPA + cg * 16, pg);
+      umma::mbar_wait(&v->bar[5], phase);        // the dW3 GEMM has finished reading TG (g3) and TM (m)
+      store_row_h(TG, row, cg, pg);
+      tmem_st_wait();
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    group_sync(G);
+    if (wg == 0) {
+      umma::fence_after();
+      if (elect_one()) {
+        gemm_ts_mn(tbase + kACC, tbase + kOPA, dW2m, id_mn);                    // D2 : g2 W2
+        umma::commit(&v->bar[3]);
+        gemm_wgrad(twg + kR2, dTG, dTA_AUX, id_wg72, !first_tile);              // [dW2 | db2 ..] += g2^T [a1 | 1, q, ea]
+      }                                                                         // (completion: bar[4] below)
+      __syncwarp();
+    }
+    umma::mbar_wait(&v->bar[3], phase);
+    umma::fence_after();
+    // ---- epilogue 4: gz1 = (g2 W2) * silu'(z1) ; gQ scatter (fp32) ; gq = gz1 . wq ; gz1 (times s1) -> TM
+    {
+      float g1v[kCPT];
+      uint32_t pd[kCPT / 2], pg[kCPT / 2];
+      tmem_ld<kCPT>(tlane + kACC + c0, g1v);
+      load_row_h(D1, row, cg, pd);
+      const int r = v->srow[row];
+      float gq = 0.f;
+      if (r >= 0) {
+        const int c = v->scol[row];
+#pragma unroll
+        for (int j = 0; j < kCPT; j += 2) {
+          const float2 dd = unpack2(pd[j >> 1]);
+          g1v[j] *= r2 * dd.x;
+          g1v[j + 1] *= r2 * dd.y;
+          gq = fmaf(g1v[j], sv->wq[c0 + j], gq);
+          gq = fmaf(g1v[j + 1], sv->wq[c0 + j + 1], gq);
+        }
+#pragma unroll
+        for (int ch = 0; ch < kCPT / 4; ++ch)
+          atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
+                    make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kCPT; ++j) g1v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kCPT; j += 2) pg[j >> 1] = pack2(g1v[j] * sc.s1, g1v[j + 1] * sc.s1);
+      store_row_h(TM, row, cg, pg);
+      if (cg == 1) v->sgqp[row] = gq;
+      group_sync(G);
+      if (cg == 0) v->sgqp[row] += gq;           // total gq of the row
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    group_sync(G);
+    if (wg == 0) {
+      umma::fence_after();
+      if (elect_one()) {
+        gemm_wgrad(twg + kDXZ, dTMa, dAUX, id_aux, !first_tile);                // (dwq, dWa) += gz1^T (q, ea)  (columns 1..)
+        umma::commit(&v->bar[4]);        // waited at the top of the next tile / before the final flush
+      }
+      __syncwarp();
+    }
+    phase ^= 1;
+    first_tile = false;
+    // ---- gP: row-segment sums of gz1 over the fp16 tile: thread (c8, grp) owns the 16-byte chunk c8 of 4 consecutive rows
+    {
+      const int c8 = tg & 7, grp = tg >> 3;      // 8 chunks x 32 groups of 4 rows
+      int cur = -1;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      auto flush = [&](int node) {
+        float* dst = a.gP + (size_t)node * kH + c8 * 8;
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[0] * r1, acc[1] * r1, acc[2] * r1, acc[3] * r1));
+        atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4] * r1, acc[5] * r1, acc[6] * r1, acc[7] * r1));
+      };
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = grp * 4 + i;
+        const int k = v->srow[rr];
+        const uint4 u = *reinterpret_cast<const uint4*>(TM + h_chunk_off(rr, c8));
+        if (k != cur) {
+          if (cur >= 0) flush(cur);
+          cur = k;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        }
+        if (k >= 0) {
+          const float2 f0 = unpack2(u.x), f1 = unpack2(u.y), f2 = unpack2(u.z), f3 = unpack2(u.w);
+          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+          acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+        }
+      }
+      if (cur >= 0) flush(cur);
+    }
+    if (tg < kTM) {
+      const int r = v->srow[tg], c = v->scol[tg];
+      const float s = v->ss[tg], gq2 = 2.f * v->sgqp[tg];
+      const float inv = norm ? 1.f / v->snrm[tg] : 1.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float gd = r == c ? 0.f : s * v->sgte[tg * 3 + k] * inv + gq2 * v->sd[tg * 3 + k];
+        if (r >= 0 && r != c) atomicAdd(a.gx + (size_t)c * 3 + k, -gd);
+        bool tail;
+        float tot = warp_segsum(r >= 0 ? gd : 0.f, r, lane, tail);
+        if (tail && r >= 0) atomicAdd(a.gx + (size_t)r * 3 + k, tot);
+      }
+    }
+  }
+  // ---- flush: each group waits for its last aux GEMM; then the whole CTA meets and group 0's warps read BOTH groups'
+  //      weight-gradient tiles (M = 64 layout: row n of group g in lane (n / 16) * 32 + n % 16 + 16 g)
+  if (!first_tile) umma::mbar_wait(&v->bar[4], phase ^ 1);
+  umma::fence_after();
+#pragma unroll
+  for (int j = 0; j < kCPT; ++j) {
+    float s = pw4[j];
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (lane == 0) atomicAdd(&sv->cw4[c0 + j], s);
+  }
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  // a group that saw no tile left its accumulator lanes undefined: only groups with first_tile == false contribute.
+  // (blockIdx.x * 2 + G < ntiles decides that for every thread of the CTA without communication.)
+  const bool has0 = blockIdx.x * kGroups + 0 < ntiles, has1 = blockIdx.x * kGroups + 1 < ntiles;
+  if (G == 0) {
+    const int n = quarter * 16 + (lane & 15);
+    const bool mine = (lane < 16) ? has0 : has1;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+    float w[kCPT];
+    tmem_ld<kCPT>(tl + kR3 + c0, w);
+    if (mine && a.g_W3 != nullptr) {
+      float* dst = a.g_W3 + (size_t)n * kH + c0;
+#pragma unroll
+      for (int j = 0; j < kCPT; ++j) atomicAdd(dst + j, w[j] * r3);
+    }
+    tmem_ld<kCPT>(tl + kR2 + c0, w);
+    if (mine && a.g_W2 != nullptr) {
+      float* dst = a.g_W2 + (size_t)n * kH + c0;
+#pragma unroll
+      for (int j = 0; j < kCPT; ++j) atomicAdd(dst + j, w[j] * r2);
+    }
+    if (cg == 0) {
+      float x3[16], x2[16], xz[16];
+      tmem_ld<16>(tl + kR3 + 64, x3);          // only columns 64..71 were written; the rest of the x16 read is ignored
+      tmem_ld<16>(tl + kR2 + 64, x2);
+      tmem_ld<16>(tl + kDXZ, xz);
+      if (mine) {
+        if (a.g_b3 != nullptr) atomicAdd(a.g_b3 + n, x3[0] * r3);
+        if (a.g_b2 != nullptr) atomicAdd(a.g_b2 + n, x2[0] * r2);
+        if (a.g_w1 != nullptr) {
+          atomicAdd(a.g_w1 + (size_t)n * a.ld1 + 2 * kH, xz[1] * r1);
+#pragma unroll
+          for (int f = 0; f < kTcMaxFe; ++f)
+            if (f < a.Fe) atomicAdd(a.g_w1 + (size_t)n * a.ld1 + 2 * kH + 1 + f, xz[2 + f] * r1);
+        }
+      }
+    }
+    if (tg < kH && a.g_w4 != nullptr) atomicAdd(a.g_w4 + tg, sv->cw4[tg]);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (t < 32) umma::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace bwd3
+
+inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, float s3, float s2, float s1, int sms, cudaStream_t st) {
+  static bool attr = false;
+  const size_t bytes = bwd3::Smem3::bytes;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(bwd3::edge_bwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  if (ntiles == 0) return cudaSuccess;
+  const int pairs = (ntiles + bwd3::kGroups - 1) / bwd3::kGroups;
+  const int grid = pairs < sms ? pairs : sms;
+  bwd3::Scales sc{s3, s2, s1};
+  bwd3::edge_bwd_tc3_kernel<<<grid, bwd3::kThreads3, bytes, st>>>(a, sc); ++g_launches;
+  return cudaGetLastError();
+}
+
+}  // namespace fegnn
