@@ -119,6 +119,7 @@ __device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
 struct SharedVec {                 // read-only after the prologue, both groups
   float wq[kH], Wa[kTcMaxFe * kH], b2[kH], b3[kH], w4[kH];
   float cw4[kH];                   // dw4 column sums (shared-memory atomics at kernel end)
+  unsigned mw[2];                  // max |W2|, max |W3| (ordered uint bits)
   uint32_t tmem_slot;
 };
 struct GroupVec {                  // per group
@@ -141,9 +142,45 @@ struct Smem3 {
 constexpr uint32_t kACC = 0, kOPA = 64, kD2T = 96;
 constexpr uint32_t kR3 = 256, kR2 = 336, kDXZ = 416;        // [dW3 64 | aux 8], [dW2 64 | aux 8], [aux 8]
 
+// ---- per-launch scales.  A multi-block pre-pass leaves four non-negative maxima in `stats` (as ordered uint bits):
+//      [0] max |gt|, [1] max |gm|, [2] max |x - x_0| over the nodes (half the extent bounds every |d_e|), [3] unused.
+//      Every CTA of the main kernel turns them into three power-of-two factors with the bounds
+//        |g3| <= 2 ext * max|gt| * max|w4| * 1.1,  |g2| <= (max|gm| + 64 |g3| max|W3|) * 1.1,  |gz1| <= 64 |g2| max|W2| * 1.1
+//      so that every stored value stays below 2^15.  Loose by design: fp16 keeps full precision over 30 binades.
+__global__ void __launch_bounds__(256) edge_bwd_stats_kernel(int N, int Nl, const float* __restrict__ x,
+                                                             const float* __restrict__ gt, const float* __restrict__ gm,
+                                                             unsigned* __restrict__ stats /*[4], zeroed by the caller*/) {
+  float mt = 0.f, mm = 0.f, mx = 0.f;
+  const float x0 = x[0], x1 = x[1], x2 = x[2];
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = i0; i < (size_t)N * 3; i += stride) mt = fmaxf(mt, fabsf(gt[i]));
+  if (gm != nullptr)
+    for (size_t i = i0; i < (size_t)N * kH; i += stride) mm = fmaxf(mm, fabsf(gm[i]));
+  for (size_t i = i0; i < (size_t)Nl; i += stride)
+    mx = fmaxf(mx, fmaxf(fabsf(x[i * 3] - x0), fmaxf(fabsf(x[i * 3 + 1] - x1), fabsf(x[i * 3 + 2] - x2))));
+  for (int o = 16; o > 0; o >>= 1) {
+    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+    mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {             // non-negative floats order like their bit patterns
+    atomicMax(stats + 0, __float_as_uint(mt));
+    atomicMax(stats + 1, __float_as_uint(mm));
+    atomicMax(stats + 2, __float_as_uint(mx));
+  }
+}
+__device__ __forceinline__ float pow2_scale(float bound) {      // largest power of two s with bound * s <= 2^15
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                         // bound = f * 2^e, f in [0.5, 1)
+  e = 15 - e;
+  e = e < -60 ? -60 : (e > 60 ? 60 : e);
+  return ldexpf(1.f, e);
+}
+
 struct Scales { float s3, s2, s1; };      // power-of-two factors applied to g3, g2, gz1 before the fp16 rounding
 
-__global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, Scales sc) {
+__global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, const unsigned* __restrict__ stats) {
   using SM = Smem3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -154,9 +191,9 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
   GroupVec* v = reinterpret_cast<GroupVec*>(gs + SM::g_vec);
   uint8_t *TA = gs + SM::g_TA, *TM = gs + SM::g_TM, *AUX = gs + SM::g_AUX, *TG = gs + SM::g_TG, *D1 = gs + SM::g_D1;
   const bool use_tanh = a.flags & FEGNN_F_TANH, norm = a.flags & FEGNN_F_NORMALIZE;
-  const float r3 = 1.f / sc.s3, r2 = 1.f / sc.s2, r1 = 1.f / sc.s1;
 
-  // ---- prologue (whole CTA): fp16 weight tiles, vectors, zero AUX, barriers, tensor memory
+  // ---- prologue (whole CTA): fp16 weight tiles (+ their max magnitudes), vectors, zero AUX, barriers, tensor memory
+  float mw2 = 0.f, mw3 = 0.f;
   for (int i = t; i < kH * 8; i += kThreads3) {            // 64 rows x 8 chunks of 8 columns
     const int n = i >> 3, c8 = i & 7;
     const float4 w20 = *reinterpret_cast<const float4*>(a.W2 + (size_t)n * kH + c8 * 8);
@@ -167,7 +204,16 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
         make_uint4(pack2(w20.x, w20.y), pack2(w20.z, w20.w), pack2(w21.x, w21.y), pack2(w21.z, w21.w));
     *reinterpret_cast<uint4*>(smem + SM::off_W3 + h_chunk_off(n, c8)) =
         make_uint4(pack2(w30.x, w30.y), pack2(w30.z, w30.w), pack2(w31.x, w31.y), pack2(w31.z, w31.w));
+    mw2 = fmaxf(mw2, fmaxf(fmaxf(fmaxf(fabsf(w20.x), fabsf(w20.y)), fmaxf(fabsf(w20.z), fabsf(w20.w))),
+                           fmaxf(fmaxf(fabsf(w21.x), fabsf(w21.y)), fmaxf(fabsf(w21.z), fabsf(w21.w)))));
+    mw3 = fmaxf(mw3, fmaxf(fmaxf(fmaxf(fabsf(w30.x), fabsf(w30.y)), fmaxf(fabsf(w30.z), fabsf(w30.w))),
+                           fmaxf(fmaxf(fabsf(w31.x), fabsf(w31.y)), fmaxf(fabsf(w31.z), fabsf(w31.w)))));
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    mw2 = fmaxf(mw2, __shfl_xor_sync(0xffffffffu, mw2, o));
+    mw3 = fmaxf(mw3, __shfl_xor_sync(0xffffffffu, mw3, o));
+  }
+  if (t == 0) { sv->mw[0] = 0u; sv->mw[1] = 0u; }
   for (int i = t; i < kH; i += kThreads3) {
     sv->wq[i] = a.w1[(size_t)i * a.ld1 + 2 * kH];
     for (int f = 0; f < a.Fe; ++f) sv->Wa[f * kH + i] = a.w1[(size_t)i * a.ld1 + 2 * kH + 1 + f];
@@ -183,11 +229,28 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
     umma::mbar_fence_init();
   }
   if (t < 32) umma::tmem_alloc<512>(&sv->tmem_slot);
+  __syncthreads();                               // mw[] zeroed, vectors staged
+  if (lane == 0) {
+    atomicMax(&sv->mw[0], __float_as_uint(mw2));
+    atomicMax(&sv->mw[1], __float_as_uint(mw3));
+  }
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
   const uint32_t tmem = sv->tmem_slot;
+  Scales sc;
+  {
+    float mw4 = 0.f;
+    for (int i = 0; i < kH; ++i) mw4 = fmaxf(mw4, fabsf(sv->w4[i]));
+    const float mgt = __uint_as_float(stats[0]), mgm = __uint_as_float(stats[1]), ext = 2.f * __uint_as_float(stats[2]);
+    const float dmax = norm ? 1.f : ext * 1.7320508f;                          // |d_e| (unit vectors when normalised)
+    const float b3 = dmax * mgt * mw4 * 1.1f * 1.7320508f;                     // |dn . gt| <= |dn| |gt|, |gt| <= sqrt3 max
+    const float b2 = (mgm + 64.f * b3 * __uint_as_float(sv->mw[1])) * 1.1f;
+    const float b1 = 64.f * b2 * __uint_as_float(sv->mw[0]) * 1.1f;
+    sc.s3 = pow2_scale(b3); sc.s2 = pow2_scale(b2); sc.s1 = pow2_scale(b1);
+  }
+  const float r3 = 1.f / sc.s3, r2 = 1.f / sc.s2, r1 = 1.f / sc.s1;
   const uint32_t tbase = tmem + G * 128;                                          // this group's columns
   const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);                // + this thread's lane
   const uint32_t twg = tmem + ((uint32_t)(16 * G) << 16);                         // weight-gradient accumulators: lane 0 / 16
@@ -596,7 +659,8 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
 
 }  // namespace bwd3
 
-inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, float s3, float s2, float s1, int sms, cudaStream_t st) {
+// stats: 4 unsigned of caller scratch (device)
+inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st) {
   static bool attr = false;
   const size_t bytes = bwd3::Smem3::bytes;
   if (!attr) {
@@ -608,8 +672,12 @@ inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, float s3, float s2, fl
   if (ntiles == 0) return cudaSuccess;
   const int pairs = (ntiles + bwd3::kGroups - 1) / bwd3::kGroups;
   const int grid = pairs < sms ? pairs : sms;
-  bwd3::Scales sc{s3, s2, s1};
-  bwd3::edge_bwd_tc3_kernel<<<grid, bwd3::kThreads3, bytes, st>>>(a, sc); ++g_launches;
+  cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  int sblocks = (int)(((size_t)a.N * kH + 256 * 16 - 1) / (256 * 16));
+  sblocks = sblocks < 1 ? 1 : (sblocks > 4 * sms ? 4 * sms : sblocks);
+  bwd3::edge_bwd_stats_kernel<<<sblocks, 256, 0, st>>>(a.N, a.Nl, a.x, a.gt, a.gm, stats); ++g_launches;
+  bwd3::edge_bwd_tc3_kernel<<<grid, bwd3::kThreads3, bytes, st>>>(a, stats); ++g_launches;
   return cudaGetLastError();
 }
 
