@@ -14,6 +14,7 @@
 //   * the four stages of a group use ONE fp32 accumulator (they are sequential); the weight-gradient accumulators
 //     (M = 64) of group 0 sit at lane 0 and those of group 1 at lane 16 of the SAME columns.
 // Shared memory: weights 16 KB + 2 x (5 tiles x 16 KB + vectors) ~ 200 KB.  Tensor memory: 2 x 128 + 152 columns.
+// Not probed yet: N = 72 and N = 8 with M = 64 and a two-block MN-major B (cases F8 of tools/umma_probe_f16.cu).
 // Known precision difference to bwd2: the gP row-segment sums walk the fp16 gz1 tile (bwd2 walks an fp32 tile).
 #include "../common.cuh"
 #include "../umma.cuh"

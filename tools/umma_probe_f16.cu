@@ -168,11 +168,16 @@ int main() {
   // F7: M = 64 accumulator with the address at lane 16 (does it land in lanes 16-31 / 48-63 / ... of the same columns?)
   add("F7 kmajor M64 D at lane 16", Case{64, 64, 64, 0, 0, 16, 1024, 32, 16, 1024, 32, 0, 16});
   add("F7 A,B mn M64 K128 D at lane 16 (lbo=blk)", Case{64, 64, 128, 1, 1, 16384, 1024, 2048, 16384, 1024, 2048, 0, 16});
+  // F8 (added after the first run, not yet executed): N = 72 = one 64-element MN block + 8 columns of the next block
+  // (the [dW | bias sums] form of the weight-gradient GEMMs), and N = 8 alone
+  add("F8 A,B mn M64 N72 K128 (B two blocks)", Case{64, 72, 128, 1, 1, 16384, 1024, 2048, 16384, 1024, 2048, 0, 0});
+  add("F8 A,B mn M64 N72 K128 D at lane 16", Case{64, 72, 128, 1, 1, 16384, 1024, 2048, 16384, 1024, 2048, 0, 16});
+  add("F8 A,B mn M64 N8  K128", Case{64, 8, 128, 1, 1, 16384, 1024, 2048, 16384, 1024, 2048, 0, 0});
 
   __half *a_d, *b_d;
   uint32_t* p_d;
   float* d_d;
-  CK(cudaMalloc(&a_d, 32768)); CK(cudaMalloc(&b_d, 32768)); CK(cudaMalloc(&p_d, 128 * 64 * 4)); CK(cudaMalloc(&d_d, 128 * 64 * 4));
+  CK(cudaMalloc(&a_d, 32768)); CK(cudaMalloc(&b_d, 32768)); CK(cudaMalloc(&p_d, 128 * 64 * 4)); CK(cudaMalloc(&d_d, 128 * 128 * 4));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 1024));
   for (size_t ci = 0; ci < cases.size(); ++ci) {
     Case c = cases[ci];
@@ -205,7 +210,7 @@ int main() {
     CK(cudaMemcpy(a_d, Ai.data(), 32768, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(b_d, Bi.data(), 32768, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p_d, Ap.data(), 128 * 64 * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_d, 0xff, 128 * 64 * 4));
+    CK(cudaMemset(d_d, 0xff, 128 * 128 * 4));
     probe_kernel<<<1, 128, 2 * 32768 + 1024>>>(c, a_d, b_d, p_d, d_d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("[%s] kernel failed: %s\n", names[ci], cudaGetErrorString(e)); return 1; }
