@@ -645,7 +645,7 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     npre_fn = dict(calls)["node_pre_fwd"]
     calls += [(f"node_pre_fwd[mode={m}]", with_mode("node_forward", m, npre_fn)) for m in (0, 1)]
     edge_bwd_fn = dict(calls)["edge_bwd"]
-    calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4)]
+    calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4, 5)]
     for name, fn in calls:
         for _ in range(3):
             fn()

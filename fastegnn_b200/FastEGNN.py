@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .ops import CsrGraph, SavedBlock, _require_cuda, _stream, layer_ptrs, make_dims
+from .ops import CsrGraph, SavedBlock, _on, _require_cuda, _stream, layer_ptrs, make_dims, segment_reduce
 
 lib = L.lib
 
@@ -67,8 +67,6 @@ class E_GCL_vel(nn.Module):
             raise NotImplementedError("residual=False is not implemented (all reference mains use residual=True)")
         if node_attr_nf != 0:
             raise NotImplementedError("node_attr_nf must be 0 (the reference mains pass node_attr=None)")
-        if coords_agg != 'mean':
-            raise Exception('Wrong coords_agg parameter')      # same error text as :131; FastEGNN never passes it
         if not 1 <= virtual_channels <= L.MAX_C:
             raise NotImplementedError(f"virtual_channels must be in [1, {L.MAX_C}]")
         if not 0 <= edge_attr_nf <= L.MAX_FE:
@@ -99,6 +97,8 @@ class E_GCL_vel(nn.Module):
     def forward(self, node_feat, edge_index, coord, node_vel, virtual_coord, virtual_node_feat, data_batch,
                 edge_attr=None, node_attr=None):
         """(h, x, S, Z) of one layer, S in the reference's [B,H,C] layout (:192-223)."""
+        if self.coords_agg not in ('sum', 'mean'):
+            raise Exception('Wrong coords_agg parameter')      # raised at call time with the reference's text (:131)
         from .layer_fn import layer_forward     # phase-by-phase driver (also used by the partitioned path)
         return layer_forward(self, node_feat, edge_index, coord, node_vel, virtual_coord, virtual_node_feat,
                              data_batch, edge_attr)
@@ -119,10 +119,11 @@ class _StackFn(torch.autograd.Function):
         x_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
         Z_out = torch.empty(B, 3, Cc, device=dev, dtype=torch.float32)
         Fin = node_feat.size(1)
-        L.check(lib.fegnn_model_forward(pd, Lyr, Fin, C.byref(graph.c), table, L.ptr(mod.embedding_in.weight),
-                                        L.ptr(mod.embedding_in.bias), L.ptr(mod.virtual_node_feat), L.ptr(node_feat),
-                                        L.ptr(x0), L.ptr(v), L.ptr(loc_mean), L.ptr(x_out), L.ptr(Z_out), L.ptr(ws),
-                                        ws_floats, _stream()), "fegnn_model_forward")
+        with _on(dev):
+            L.check(lib.fegnn_model_forward(pd, Lyr, Fin, C.byref(graph.c), table, L.ptr(mod.embedding_in.weight),
+                                            L.ptr(mod.embedding_in.bias), L.ptr(mod.virtual_node_feat), L.ptr(node_feat),
+                                            L.ptr(x0), L.ptr(v), L.ptr(loc_mean), L.ptr(x_out), L.ptr(Z_out), L.ptr(ws),
+                                            ws_floats, _stream(dev)), "fegnn_model_forward")
         ctx.mod, ctx.graph, ctx.dims, ctx.ws, ctx.Fin = mod, graph, dims, ws, Fin
         ctx.save_for_backward(node_feat, v)
         ctx.names = names
@@ -146,12 +147,13 @@ class _StackFn(torch.autograd.Function):
         g_x0 = torch.empty(N, 3, device=dev, dtype=torch.float32)
         g_lm = torch.empty(B, 3, Cc, device=dev, dtype=torch.float32)
         g_nf = torch.empty_like(node_feat) if ctx.need_nf else None
-        L.check(lib.fegnn_model_backward(pd, Lyr, ctx.Fin, C.byref(graph.c), table, gtable,
-                                         L.ptr(mod.embedding_in.weight), L.ptr(views["embedding_in.weight"]),
-                                         L.ptr(views["embedding_in.bias"]), L.ptr(views["virtual_node_feat"]),
-                                         L.ptr(node_feat), L.ptr(v), L.ptr(gx), L.ptr(gZ), L.ptr(g_x0), L.ptr(g_lm),
-                                         L.ptr(g_nf), L.ptr(ctx.ws), L.ptr(scratch), scr_floats, _stream()),
-                "fegnn_model_backward")
+        with _on(dev):
+            L.check(lib.fegnn_model_backward(pd, Lyr, ctx.Fin, C.byref(graph.c), table, gtable,
+                                             L.ptr(mod.embedding_in.weight), L.ptr(views["embedding_in.weight"]),
+                                             L.ptr(views["embedding_in.bias"]), L.ptr(views["virtual_node_feat"]),
+                                             L.ptr(node_feat), L.ptr(v), L.ptr(gx), L.ptr(gZ), L.ptr(g_x0), L.ptr(g_lm),
+                                             L.ptr(g_nf), L.ptr(ctx.ws), L.ptr(scratch), scr_floats, _stream(dev)),
+                    "fegnn_model_backward")
         dead = mod._dead_names
         grads = tuple(None if n in dead else views[n] for n in names)
         return (None, None, g_nf, g_x0, None, g_lm) + grads
@@ -265,13 +267,12 @@ class FastEGNN(nn.Module):
 
 
 def unsorted_segment_sum(data, segment_ids, num_segments):
-    """models/FastEGNN.py:279-284 -- kept for API completeness (nothing in the path calls it)."""
-    result = data.new_zeros((num_segments, data.size(1)))
-    return result.index_add_(0, segment_ids, data)
+    """models/FastEGNN.py:279-284: rows of `data` [E,K] summed per segment -> [num_segments,K].  Module-level helper of
+    the reference file (the layer's own sums run inside the fused edge kernel); here fegnn_segment_sum: one warp per
+    row, red.global.add.  CUDA fp32 only, like everything in this package."""
+    return segment_reduce(data, segment_ids, num_segments, mean=False)
 
 
 def unsorted_segment_mean(data, segment_ids, num_segments):
-    """models/FastEGNN.py:287-294 -- kept for API completeness (nothing in the path calls it)."""
-    total = unsorted_segment_sum(data, segment_ids, num_segments)
-    count = torch.bincount(segment_ids, minlength=num_segments).clamp(min=1).to(data.dtype)
-    return total / count.unsqueeze(-1)
+    """models/FastEGNN.py:287-294: segment sums divided by the per-segment count clamped to >= 1."""
+    return segment_reduce(data, segment_ids, num_segments, mean=True)

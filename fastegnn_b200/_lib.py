@@ -16,7 +16,7 @@ H = 64
 MAX_C = 16
 MAX_FE = 8
 
-F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF = 1, 2, 4, 8, 16, 32
+F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF, F_COORDS_SUM = 1, 2, 4, 8, 16, 32, 64
 
 fp = C.POINTER(C.c_float)
 ip = C.POINTER(C.c_int32)
@@ -63,11 +63,21 @@ class LayerPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n, _ in LAYER_FIELDS]
 
 
-SAVED_FIELDS = ["P", "Q", "Av", "Uh", "sv", "sg", "M", "Zc", "G1", "msum", "tsum", "u", "zh1", "Dsum", "Usum"]
+SAVED_FIELDS = ["P", "Q", "Av", "Uh", "sv", "sg", "M", "Zc", "G1", "msum", "tsum", "u", "zh1", "Dsum", "Usum", "scratch"]
 
 
 class Saved(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in SAVED_FIELDS]
+
+
+P2P_MAX_WORLD, P2P_CHANNELS = 16, 4
+
+
+class P2P(C.Structure):
+    """fegnn_p2p: peers' signal pads / all-reduce slots (symmetric memory) + this rank's local counters."""
+    _fields_ = [("sig_peer", C.c_uint64 * P2P_MAX_WORLD), ("ar_peer", C.c_uint64 * P2P_MAX_WORLD),
+                ("epoch", C.c_void_p), ("done", C.c_void_p), ("err", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("ar_capacity", C.c_int32)]
 
 
 class FegnnError(RuntimeError):
@@ -117,6 +127,9 @@ SIGNATURES = {
     "fegnn_node_pre_backward": (C.c_int, [_PD, _PP, _PP, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "fegnn_halo_push": (C.c_int, [i32, vp, vp, vp, vp, vp, vp]),
     "fegnn_halo_reduce_push": (C.c_int, [i32, i32, vp, vp, vp, vp, vp]),
+    "fegnn_halo_push_signal": (C.c_int, [C.POINTER(P2P), i32, i32, vp, i32, vp, vp, vp, vp, vp]),
+    "fegnn_halo_reduce_apply": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_p2p_allreduce": (C.c_int, [C.POINTER(P2P), i32, i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), vp]),
     "fegnn_rf_vel_forward": (C.c_int, [i32, vp, _PP, vp, vp]),
     "fegnn_rf_vel_backward": (C.c_int, [i32, vp, _PP, _PP, vp, vp]),
     "fegnn_layer_saved_floats": (C.c_size_t, [_PD]),
@@ -125,6 +138,9 @@ SIGNATURES = {
     "fegnn_model_backward_scratch_floats": (C.c_size_t, [_PD]),
     "fegnn_model_forward": (C.c_int, [_PD, i32, i32, _PG, _PP] + [vp] * 9 + [vp, C.c_size_t, vp]),
     "fegnn_model_backward": (C.c_int, [_PD, i32, i32, _PG, _PP, _PP] + [vp] * 11 + [vp, vp, C.c_size_t, vp]),
+    "fegnn_peak_probe": (C.c_int, [i32, i32, vp, C.POINTER(C.c_double), vp]),
+    "fegnn_segment_reduce": (C.c_int, [C.c_int64, i32, i32, vp, vp, i32, vp, vp, vp]),
+    "fegnn_segment_reduce_backward": (C.c_int, [C.c_int64, i32, i32, vp, vp, vp, vp, vp]),
     "fegnn_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float, vp]),
     "fegnn_mmd_forward": (C.c_int, [i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
     "fegnn_mmd_backward": (C.c_int, [i32, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),

@@ -11,6 +11,7 @@
 #include "edge_tc.cu"
 #include "edge_tc_bwd.cu"
 #include "edge_tc_bwd2.cu"
+#include "edge_tc_bwd3.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "radius_graph.cu"
@@ -20,6 +21,8 @@
 #include "virtual_kernels.cu"
 #include "virtual_tc.cu"
 #include "node_tc.cu"
+#include "segment.cu"
+#include "peak_probe.cu"
 
 using namespace fegnn;
 
@@ -65,13 +68,13 @@ int g_virt_bwd_mode = 1;
 int g_node_fwd_mode = 0;
 
 int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static int sms[64] = {};                  // per device ordinal (a process may drive several GPUs)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 int check_dims(const fegnn_dims* d) {
@@ -119,7 +122,8 @@ VirtArgs virt_args(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_
   memset(&a, 0, sizeof(a));
   a.N = d->N; a.B = d->B; a.C = d->C; a.ldv = ldv(d); a.flags = d->flags;
   a.grav[0] = d->gravity[0]; a.grav[1] = d->gravity[1]; a.grav[2] = d->gravity[2];
-  a.batch = g->batch; a.x = x; a.v = v; a.Z = Z; a.Av = sv->Av; a.G1 = sv->G1; a.tsum = sv->tsum; a.dinv = g->dinv;
+  a.batch = g->batch; a.x = x; a.v = v; a.Z = Z; a.Av = sv->Av; a.G1 = sv->G1; a.tsum = sv->tsum;
+  a.dinv = (d->flags & FEGNN_F_COORDS_SUM) ? nullptr : g->dinv;   // coords_agg='sum': no 1/deg on the coordinate update
   a.sv = sv->sv; a.sg = sv->sg;
   a.wv1 = p->edgev_w0; a.V2 = p->edgev_w2; a.c2 = p->edgev_b2;
   a.Wxv = p->crv_w0; a.bxv = p->crv_b0; a.wxv = p->crv_w2;
@@ -196,7 +200,8 @@ int fegnn_set_mode(const char* phase, int mode) {
     return 0;
   }
   if (strcmp(phase, "edge_backward") == 0) {
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 4) return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2 or 4");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 5)
+      return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2, 4 or 5");
     g_edge_bwd_mode = mode;
     return 0;
   }
@@ -442,7 +447,9 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
   CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
-  if (g_edge_bwd_mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
+  if (g_edge_bwd_mode == 5 && tc_ok && sv->scratch != nullptr)
+    CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
+  else if (g_edge_bwd_mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
   else if (g_edge_bwd_mode == 4 && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
   else if (g_edge_bwd_mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
   else CK(launch_edge_bwd(a, sm_count(), S(stream)));
@@ -494,6 +501,59 @@ int fegnn_halo_reduce_push(int32_t n, int32_t first_halo_row, const uint64_t* ds
   return 0;
 }
 
+namespace {
+int p2p_args(const fegnn_p2p* p, P2PArgs* a) {
+  if (p == nullptr) return fail(FEGNN_EINVAL, "fegnn_p2p is null");
+  if (p->world < 1 || p->world > kP2PMaxWorld || p->rank < 0 || p->rank >= p->world)
+    return fail(FEGNN_EINVAL, "bad rank / world %d / %d (max %d)", p->rank, p->world, kP2PMaxWorld);
+  if (!p->epoch || !p->done || !p->err) return fail(FEGNN_EINVAL, "fegnn_p2p local counters are null");
+  for (int i = 0; i < kP2PMaxWorld; ++i) {
+    a->sig_peer[i] = i < p->world ? p->sig_peer[i] : 0ull;
+    a->ar_peer[i] = i < p->world ? p->ar_peer[i] : 0ull;
+    if (i < p->world && p->sig_peer[i] == 0) return fail(FEGNN_EINVAL, "signal pad of rank %d is null", i);
+  }
+  a->epoch = p->epoch; a->done = p->done; a->err = p->err;
+  a->rank = p->rank; a->world = p->world; a->ar_capacity = p->ar_capacity;
+  return 0;
+}
+}  // namespace
+static_assert(kP2PMaxWorld == FEGNN_P2P_MAX_WORLD && kP2PChannels == FEGNN_P2P_CHANNELS, "fegnn.h and halo.cu disagree");
+
+int fegnn_halo_push_signal(const fegnn_p2p* p, int32_t channel, int32_t n, const int32_t* src_row, int32_t row0,
+                           const uint64_t* dst_q, const uint64_t* dst_x, const float* Q, const float* x, void* stream) {
+  P2PArgs a;
+  TRY(p2p_args(p, &a));
+  RQ(channel >= 0 && channel < kP2PChannels && n >= 0 && row0 >= 0 && (n == 0 || (dst_q && dst_x && Q && x)));
+  CK(launch_halo_push_signal(a, channel, n, src_row, row0, reinterpret_cast<const unsigned long long*>(dst_q),
+                             reinterpret_cast<const unsigned long long*>(dst_x), Q, x, sm_count(), S(stream)));
+  return 0;
+}
+int fegnn_halo_reduce_apply(int32_t n_rows, const int32_t* rows, const int32_t* ptr, const int32_t* slots,
+                            const float* recv_q, const float* recv_x, float* gQ, float* gx, void* stream) {
+  RQ(n_rows >= 0 && (n_rows == 0 || (rows && ptr && slots && recv_q && recv_x && gQ && gx)));
+  CK(launch_halo_reduce_apply(n_rows, rows, ptr, slots, recv_q, recv_x, gQ, gx, S(stream)));
+  return 0;
+}
+int fegnn_p2p_allreduce(const fegnn_p2p* p, int32_t channel, int32_t nseg, float* const* seg_host, const int32_t* count_host,
+                        void* stream) {
+  P2PArgs a;
+  TRY(p2p_args(p, &a));
+  RQ(channel >= 0 && channel < kP2PChannels && nseg >= 1 && nseg <= 4 && seg_host && count_host);
+  P2PSegs g;
+  memset(&g, 0, sizeof(g));
+  long long tot = 0;
+  for (int i = 0; i < nseg; ++i) {
+    RQ(count_host[i] >= 0 && (count_host[i] == 0 || seg_host[i] != nullptr));
+    g.ptr[i] = seg_host[i]; g.count[i] = count_host[i];
+    tot += count_host[i];
+  }
+  g.nseg = nseg;
+  if (tot > a.ar_capacity) return fail(FEGNN_ENOMEM, "all-reduce of %lld floats exceeds the slot capacity %d", tot, a.ar_capacity);
+  for (int i = 0; i < a.world; ++i) RQ(a.ar_peer[i] != 0);
+  CK(launch_p2p_allreduce(a, channel, g, S(stream)));
+  return 0;
+}
+
 // ------------------------------------------------------------------ FastRF velocity head (models/FastRF.py:76-80,135)
 int fegnn_rf_vel_forward(int32_t N, const float* v, const fegnn_layer_params* p, float* sv, void* stream) {
   RQ(N >= 0 && p && (N == 0 || (v && sv)) && p->vel_w0 && p->vel_b0 && p->vel_w2 && p->vel_b2);
@@ -513,7 +573,7 @@ size_t fegnn_layer_saved_floats(const fegnn_dims* d) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   return 3 * al4(N * kH) /*P Av Uh*/ + al4(Nl * kH) /*Q*/ + 2 * al4(N) /*sv sg*/ + al4(B * C * C) + al4(B * 3 * C) +
          al4(B * C * kH) /*M Zc G1*/ + al4(N * kH) + al4(N * 3) /*msum tsum*/ + al4(N * C * kH) /*u*/ +
-         al4(N * kH) /*zh1*/ + al4(B * 3 * C) + al4(B * C * kH) /*Dsum Usum*/;
+         al4(N * kH) /*zh1*/ + al4(B * 3 * C) + al4(B * C * kH) /*Dsum Usum*/ + 16 /*scratch*/;
 }
 int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out) {
   TRY(check_dims(d));
@@ -526,6 +586,7 @@ int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved*
   out->M = take(B * C * C); out->Zc = take(B * 3 * C); out->G1 = take(B * C * kH);
   out->msum = take(N * kH); out->tsum = take(N * 3); out->u = take(N * C * kH); out->zh1 = take(N * kH);
   out->Dsum = take(B * 3 * C); out->Usum = take(B * C * kH);
+  out->scratch = take(16);
   return 0;
 }
 
@@ -733,6 +794,29 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf); ++g_launches;
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ roofline probes (measurement, not the path)
+int fegnn_peak_probe(int32_t kind, int32_t iters, float* sink, double* ops_host, void* stream) {
+  RQ(kind >= 0 && kind <= 3 && iters >= 8 && sink && ops_host);
+  CK(launch_peak_probe(kind, iters, sink, ops_host, sm_count(), S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ unsorted_segment_sum / _mean (models/FastEGNN.py:279-294)
+int fegnn_segment_reduce(int64_t E, int32_t K, int32_t S_, const float* data, const int64_t* segment_ids, int32_t mean,
+                         float* out, float* count, void* stream) {
+  RQ(E >= 0 && K >= 1 && S_ >= 0 && (S_ == 0 || out) && (E == 0 || (data && segment_ids)) && (!mean || S_ == 0 || count));
+  CK(launch_segment_reduce(E, K, S_, data, reinterpret_cast<const long long*>(segment_ids), mean != 0, out, count,
+                           sm_count(), S(stream)));
+  return 0;
+}
+int fegnn_segment_reduce_backward(int64_t E, int32_t K, int32_t S_, const float* g_out, const int64_t* segment_ids,
+                                  const float* count, float* g_data, void* stream) {
+  RQ(E >= 0 && K >= 1 && S_ >= 0 && (E == 0 || (g_out && segment_ids && g_data)));
+  CK(launch_segment_gather(E, K, S_, g_out, reinterpret_cast<const long long*>(segment_ids), count, g_data, sm_count(),
+                           S(stream)));
   return 0;
 }
 

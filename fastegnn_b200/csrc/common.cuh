@@ -274,6 +274,24 @@ __device__ __forceinline__ void load_tile(float* __restrict__ T, const float* __
   }
 }
 
+// "Done once" flag PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting, so a process that
+// drives several GPUs (model on cuda:1 while the current device was 0 earlier) must opt in on each of them.
+struct DevOnce {
+  bool done[64] = {};
+  static int dev() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1;
+  }
+  bool get() const {
+    const int d = dev();
+    return d >= 0 && done[d];
+  }
+  void set() {
+    const int d = dev();
+    if (d >= 0) done[d] = true;
+  }
+};
+
 // Number of kernels this library has launched (host counter; read through fegnn_launch_count()).
 inline unsigned long long g_launches = 0;
 

@@ -395,11 +395,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd_kernel(EdgeArgs a) {
 
 // ---------------------------------------------------------------------------- host side
 cudaError_t launch_edge_fwd(const EdgeArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeFwdSmem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
@@ -408,11 +408,11 @@ cudaError_t launch_edge_fwd(const EdgeArgs& a, int sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_edge_bwd(const EdgeArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeBwdSmem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
 
 template <int SPLIT>
 cudaError_t launch_edge_fwd_tc(const EdgeArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
+  static DevOnce attr;
   const size_t bytes = EdgeTcSmem<SPLIT>::bytes;
-  if (!attr) {
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

@@ -520,12 +520,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_bwd_tc_kernel(EdgeArgs a) 
 }
 
 cudaError_t launch_edge_bwd_tc(const EdgeArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
+  static DevOnce attr;
   const size_t bytes = EdgeTcBwdSmem::bytes;
-  if (!attr) {
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

@@ -625,12 +625,12 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
 
 template <int CG>
 cudaError_t launch_edge_bwd_tc2(const EdgeArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
+  static DevOnce attr;
   const size_t bytes = bwd2::Smem::bytes;
-  if (!attr) {
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(bwd2::edge_bwd_tc2_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

@@ -1,6 +1,5 @@
-// edge_tc_bwd3.cu -- WORK IN PROGRESS, NOT PART OF THE BUILD (api.cu does not include it; compile check:
-// fastegnn_b200/csrc/wip/compile_check.sh).  Draft of the third tcgen05 formulation of the fused real-edge backward,
-// DESIGN.md section 6 item 2: fp16 operand tiles (kind::f16, fp32 accumulation) and TWO tiles in flight per SM.
+// edge_tc_bwd3.cu -- third tcgen05 formulation of the fused real-edge backward (edge_backward mode 5):
+// fp16 operand tiles (kind::f16, fp32 accumulation) and TWO tiles in flight per SM.
 //
 // Same contract as bwd2::edge_bwd_tc2_kernel (autograd of models/FastEGNN.py:102-108,125-129,156).  What changes:
 //   * one CTA = two independent 256-thread GROUPS (named barriers 1 / 2), each walking its own stream of 128-edge tiles
@@ -14,10 +13,9 @@
 //   * the four stages of a group use ONE fp32 accumulator (they are sequential); the weight-gradient accumulators
 //     (M = 64) of group 0 sit at lane 0 and those of group 1 at lane 16 of the SAME columns.
 // Shared memory: weights 16 KB + 2 x (5 tiles x 16 KB + vectors) ~ 200 KB.  Tensor memory: 2 x 128 + 152 columns.
-// Not probed yet: N = 72 and N = 8 with M = 64 and a two-block MN-major B (cases F8 of tools/umma_probe_f16.cu).
 // Known precision difference to bwd2: the gP row-segment sums walk the fp16 gz1 tile (bwd2 walks an fp32 tile).
-#include "../common.cuh"
-#include "../umma.cuh"
+#include "common.cuh"
+#include "umma.cuh"
 #include <cuda_fp16.h>
 
 namespace fegnn {
@@ -662,12 +660,12 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
 
 // stats: 4 unsigned of caller scratch (device)
 inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st) {
-  static bool attr = false;
+  static DevOnce attr;
   const size_t bytes = bwd3::Smem3::bytes;
-  if (!attr) {
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(bwd3::edge_bwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int ntiles = (a.E + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

@@ -328,11 +328,11 @@ __global__ void __launch_bounds__(kThreads) graph_pre_bwd_kernel(GraphArgs a) {
 
 #define FEGNN_GRAPH_SMEM(kernel)                                                                              \
   do {                                                                                                       \
-    static bool done_ = false;                                                                               \
-    if (!done_) {                                                                                            \
+    static DevOnce done_;                                                                               \
+    if (!done_.get()) {                                                                                            \
       cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphSmemBytes); \
       if (e_ != cudaSuccess) return e_;                                                                      \
-      done_ = true;                                                                                          \
+      done_.set();                                                                                          \
     }                                                                                                        \
   } while (0)
 

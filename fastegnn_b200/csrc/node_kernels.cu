@@ -489,11 +489,11 @@ cudaError_t launch_graph_xsum(int N, const float* x, const int* batch, float* xs
 
 #define FEGNN_SET_SMEM(kernel, bytes)                                                                        \
   do {                                                                                                       \
-    static bool done_ = false;                                                                               \
-    if (!done_) {                                                                                            \
+    static DevOnce done_;                                                                               \
+    if (!done_.get()) {                                                                                            \
       cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
       if (e_ != cudaSuccess) return e_;                                                                      \
-      done_ = true;                                                                                          \
+      done_.set();                                                                                          \
     }                                                                                                        \
   } while (0)
 
@@ -524,11 +524,11 @@ cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) 
 cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_h_z_kernel, kNodeHSmem);
   {
-    static bool done2_ = false;
-    if (!done2_) {
+    static DevOnce done2_;
+    if (!done2_.get()) {
       cudaError_t e_ = cudaFuncSetAttribute(node_h_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeHSmem);
       if (e_ != cudaSuccess) return e_;
-      done2_ = true;
+      done2_.set();
     }
   }
   int ntiles = (a.N + kTM - 1) / kTM;
@@ -542,11 +542,11 @@ cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
 cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   FEGNN_SET_SMEM(node_h_bwd1_kernel, kNodeHSmem);
   {
-    static bool done2_ = false;
-    if (!done2_) {
+    static DevOnce done2_;
+    if (!done2_.get()) {
       cudaError_t e_ = cudaFuncSetAttribute(node_h_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNodeHSmem);
       if (e_ != cudaSuccess) return e_;
-      done2_ = true;
+      done2_.set();
     }
   }
   int ntiles = (a.N + kTM - 1) / kTM;

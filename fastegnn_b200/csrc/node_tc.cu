@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(256, 2) node_pre_fwd_tc_kernel(NodePreArgs a) 
 }  // namespace ntc
 
 cudaError_t launch_node_pre_fwd_tc(const NodePreArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(ntc::node_pre_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ntc::PreSmem::bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;

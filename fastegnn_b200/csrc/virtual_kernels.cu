@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) virtual_fwd_kernel(VirtArgs a) {
       const int i = tile * TN + tid;
       if (i < a.N) {
         const int b = s->sb[tid];
-        const float di = a.dinv[i], svi = a.sv[i];
+        const float di = a.dinv != nullptr ? a.dinv[i] : 1.f, svi = a.sv[i];
         const float sgi = grav ? a.sg[i] : 0.f;
         const float invC = 1.f / (float)C;
 #pragma unroll
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) virtual_bwd_kernel(VirtArgs a) {
     if (tid < TN) {
       const int i = tile * TN + tid;
       if (i < a.N) {
-        const float di = a.dinv[i];
+        const float di = a.dinv != nullptr ? a.dinv[i] : 1.f;
         float gsv = 0.f, gsg = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -557,11 +557,11 @@ __global__ void __launch_bounds__(kThreads, 1) virtual_bwd_kernel(VirtArgs a) {
 }
 
 cudaError_t launch_virtual_fwd(const VirtArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(virtual_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVirtFwdSmem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int TN = kTM / a.C;
   int ntiles = (a.N + TN - 1) / TN;
@@ -571,11 +571,11 @@ cudaError_t launch_virtual_fwd(const VirtArgs& a, int sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_virtual_bwd(const VirtArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(virtual_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVirtBwdSmem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int TN = kTM / a.C;
   int ntiles = (a.N + TN - 1) / TN;

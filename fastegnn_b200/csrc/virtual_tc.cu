@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       const int i = tile * TN + t;
       if (i < a.N) {
         const int b = v->sb[t];
-        const float di = a.dinv[i], svi = a.sv[i];
+        const float di = a.dinv != nullptr ? a.dinv[i] : 1.f, svi = a.sv[i];
         const float sgi = grav ? a.sg[i] : 0.f;
         const float invC = 1.f / (float)C;
 #pragma unroll
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     if (t < TN) {
       const int i = tile * TN + t;
       if (i < a.N) {
-        const float di = a.dinv[i];
+        const float di = a.dinv != nullptr ? a.dinv[i] : 1.f;
         float gsv = 0.f, gsg = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1033,12 +1033,12 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
 
 template <int CG>
 cudaError_t launch_virtual_fwd_tc(const VirtArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
+  static DevOnce attr;
   const size_t bytes = vtc::FwdSmem::bytes;
-  if (!attr) {
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(vtc::virtual_fwd_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int TN = kTM / a.C;
   const int ntiles = (a.N + TN - 1) / TN;
@@ -1053,15 +1053,15 @@ cudaError_t launch_virtual_fwd_tc(const VirtArgs& a, int sms, cudaStream_t st) {
 namespace fegnn {
 template <int CG>
 cudaError_t launch_virtual_bwd_tc(const VirtArgs& a, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(vtc::virtual_bwd_heads_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)vtc::HeadsSmem::bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(vtc::virtual_bwd_trunk_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)vtc::TrunkSmem::bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.set();
   }
   const int TN = kTM / a.C;
   const int ntiles = (a.N + TN - 1) / TN;

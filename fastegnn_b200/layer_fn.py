@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .ops import CsrGraph, SavedBlock, _require_cuda, _stream, layer_ptrs, make_dims
+from .ops import CsrGraph, SavedBlock, _on, _require_cuda, _stream, layer_ptrs, make_dims
 
 lib = L.lib
 
@@ -37,7 +37,15 @@ class LayerPhases:
 
     # ---- forward
     def forward(self, h, x, v, Z, S, xsum, hooks=None):
-        d, g, p, sv, st = self.d, self.g, self.p, self.saved, _stream()
+        with _on(self.dev):                      # the C ABI launches on the runtime's current device
+            return self._forward(h, x, v, Z, S, xsum, hooks)
+
+    def backward(self, grads, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks=None, graph_grads=None):
+        with _on(self.dev):
+            return self._backward(grads, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks, graph_grads)
+
+    def _forward(self, h, x, v, Z, S, xsum, hooks=None):
+        d, g, p, sv, st = self.d, self.g, self.p, self.saved, _stream(self.dev)
         N, B, Cc = d.N, d.B, d.C
         pd, pg, pp, ps = self.pd, C.byref(g.c), C.byref(p), C.byref(sv.c)
         L.check(lib.fegnn_graph_pre_forward(pd, pg, pp, L.ptr(Z), L.ptr(S), L.ptr(xsum), ps, st), "graph_pre_forward")
@@ -62,12 +70,12 @@ class LayerPhases:
         return h_new, x_new, Z_new, S_new, xsum_new
 
     # ---- backward
-    def backward(self, grads: L.LayerPtrs, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks=None,
-                 graph_grads: Optional[L.LayerPtrs] = None):
+    def _backward(self, grads: L.LayerPtrs, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, gxsum_next, hooks=None,
+                  graph_grads: Optional[L.LayerPtrs] = None):
         """gh_new is consumed in place (becomes dL/dh).  Returns (gh, gx, gZ, gS, gxsum).
         graph_grads: weight-gradient table for the per-graph phases (replicated when partitioned, so
         only one rank passes real pointers); defaults to `grads`."""
-        d, g, p, sv, st = self.d, self.g, self.p, self.saved, _stream()
+        d, g, p, sv, st = self.d, self.g, self.p, self.saved, _stream(self.dev)
         N, Nl, B, Cc = d.N, d.Nl, d.B, d.C
         pd, pg, pp, ps, pgr = self.pd, C.byref(g.c), C.byref(p), C.byref(sv.c), C.byref(grads)
         pgg = pgr if graph_grads is None else C.byref(graph_grads)
@@ -119,13 +127,15 @@ class _LayerFn(torch.autograd.Function):
         named = {n: p for (n, _), p in zip(_layer_named(layer), params)}
         ptrs = layer_ptrs(named, "")
         flags = (L.F_ATTENTION if layer.attention else 0) | (L.F_NORMALIZE if layer.normalize else 0) | \
-                (L.F_TANH if layer.tanh else 0) | (L.F_GRAVITY if layer.gravity is not None else 0)
+                (L.F_TANH if layer.tanh else 0) | (L.F_GRAVITY if layer.gravity is not None else 0) | \
+                (L.F_COORDS_SUM if layer.coords_agg == 'sum' else 0)
         grav = None if layer.gravity is None else [float(t) for t in layer.gravity.detach().cpu().tolist()]
         dims = make_dims(graph.N, graph.N, graph.E, graph.B, layer.virtual_channels, graph.Fe, flags, grav)
         ph = LayerPhases(dims, graph, ptrs, dev)
         xsum = torch.empty(graph.B, 3, device=dev, dtype=torch.float32)
-        L.check(lib.fegnn_graph_xsum(graph.N, graph.B, L.ptr(x), L.ptr(graph.batch), L.ptr(xsum), _stream()),
-                "graph_xsum")
+        with _on(dev):
+            L.check(lib.fegnn_graph_xsum(graph.N, graph.B, L.ptr(x), L.ptr(graph.batch), L.ptr(xsum), _stream(dev)),
+                    "graph_xsum")
         h_new, x_new, Z_new, S_new, _ = ph.forward(h, x, v, Z, S, xsum)
         ctx.ph, ctx.layer = ph, layer
         ctx.save_for_backward(h, x, v, Z, S)

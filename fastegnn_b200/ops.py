@@ -15,8 +15,15 @@ from . import _lib as L
 lib = L.lib
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None):
+    """cudaStream_t of torch's current stream ON THE TENSORS' DEVICE (not the thread's current device: the reference mains
+    take --device cuda:N without torch.cuda.set_device)."""
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _on(dev):
+    """Device guard for a C-ABI call: libfegnn launches on the CUDA runtime's current device."""
+    return torch.cuda.device(dev)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -57,14 +64,18 @@ class CsrGraph:
         self.inv_nb = torch.empty(n_graphs, **f32)
         nbytes = int(lib.fegnn_graph_prep_workspace_bytes(N, E))
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        L.check(lib.fegnn_graph_prep(N, E, n_graphs, Fe, L.ptr(ei), L.ptr(db), L.ptr(ea), L.ptr(self.perm),
-                                     L.ptr(self.rowptr), L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch),
-                                     L.ptr(self.gptr), L.ptr(self.edge_attr), L.ptr(self.dinv), L.ptr(self.inv_nb),
-                                     L.ptr(ws), nbytes, _stream()), "fegnn_graph_prep")
+        with _on(dev):
+            L.check(lib.fegnn_graph_prep(N, E, n_graphs, Fe, L.ptr(ei), L.ptr(db), L.ptr(ea), L.ptr(self.perm),
+                                         L.ptr(self.rowptr), L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch),
+                                         L.ptr(self.gptr), L.ptr(self.edge_attr), L.ptr(self.dinv), L.ptr(self.inv_nb),
+                                         L.ptr(ws), nbytes, _stream(dev)), "fegnn_graph_prep")
         self._ws = ws   # stream-ordered: keep alive until the kernels that use it have been enqueued
+        self.rebind()
+
+    def rebind(self) -> None:
+        """(Re)build the fegnn_graph pointer table from the current tensors (after slicing / renumbering them)."""
         self.c = L.Graph(L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch), L.ptr(self.edge_attr),
                          L.ptr(self.dinv), L.ptr(self.inv_nb))
-
 
     @classmethod
     def from_radius(cls, node_loc: torch.Tensor, data_batch: torch.Tensor, n_graphs: int, r: float,
@@ -100,10 +111,11 @@ class CsrGraph:
         counts = torch.zeros(2, **i32)                        # [n_cand, n_edges]
         nbytes = int(lib.fegnn_radius_graph_workspace_bytes(N, B))
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        st = _stream()
-        L.check(lib.fegnn_radius_graph_count(N, B, L.ptr(x), L.ptr(db), float(r), L.ptr(self.batch), L.ptr(self.gptr),
-                                             L.ptr(self.inv_nb), L.ptr(cand_rowptr), L.ptr(counts[0:1]), L.ptr(ws),
-                                             nbytes, st), "fegnn_radius_graph_count")
+        st = _stream(dev)
+        with _on(dev):
+            L.check(lib.fegnn_radius_graph_count(N, B, L.ptr(x), L.ptr(db), float(r), L.ptr(self.batch), L.ptr(self.gptr),
+                                                 L.ptr(self.inv_nb), L.ptr(cand_rowptr), L.ptr(counts[0:1]), L.ptr(ws),
+                                                 nbytes, st), "fegnn_radius_graph_count")
         n_cand = int(counts[0].item())
         keep_frac = 1.0 - float(cutoff_rate)                  # the reference's int(E * (1 - cutoff_rate)) in fp64
         cap = max(n_cand, 1)
@@ -113,19 +125,19 @@ class CsrGraph:
         row = torch.empty(cap, **i32)
         col = torch.empty(cap, **i32)
         ea = torch.empty(cap, max(Fe, 1), **f32)
-        L.check(lib.fegnn_radius_graph_fill(N, B, Fe, float(r), keep_frac, L.ptr(self.batch), L.ptr(self.gptr),
-                                            L.ptr(cand_rowptr), L.ptr(counts[0:1]), n_cand, L.ptr(ccol), L.ptr(cdist),
-                                            L.ptr(crow), cap, L.ptr(self.rowptr), L.ptr(row), L.ptr(col), L.ptr(ea),
-                                            L.ptr(self.dinv), L.ptr(counts[1:2]), L.ptr(ws), nbytes, st),
-                "fegnn_radius_graph_fill")
+        with _on(dev):
+            L.check(lib.fegnn_radius_graph_fill(N, B, Fe, float(r), keep_frac, L.ptr(self.batch), L.ptr(self.gptr),
+                                                L.ptr(cand_rowptr), L.ptr(counts[0:1]), n_cand, L.ptr(ccol), L.ptr(cdist),
+                                                L.ptr(crow), cap, L.ptr(self.rowptr), L.ptr(row), L.ptr(col), L.ptr(ea),
+                                                L.ptr(self.dinv), L.ptr(counts[1:2]), L.ptr(ws), nbytes, st),
+                    "fegnn_radius_graph_fill")
         E = int(counts[1].item())
         self.E = E
         self.n_candidates = n_cand
         self.row, self.col = row[:E], col[:E]
         self.edge_attr = ea[:E] if Fe else torch.empty(0, **f32)
         self._ws = ws
-        self.c = L.Graph(L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch), L.ptr(self.edge_attr),
-                         L.ptr(self.dinv), L.ptr(self.inv_nb))
+        self.rebind()
         return self
 
     def edge_index(self) -> torch.Tensor:
@@ -183,8 +195,9 @@ class _MmdFn(torch.autograd.Function):
         B, _, C_ = Z.shape
         ns = sample_idx.size(1)
         loss = torch.empty(1, device=x.device, dtype=torch.float32)
-        L.check(lib.fegnn_mmd_forward(B, C_, ns, float(sigma), float(scale_vv), float(scale_rv), L.ptr(x), L.ptr(Z),
-                                      L.ptr(sample_idx), L.ptr(loss), _stream()), "fegnn_mmd_forward")
+        with _on(x.device):
+            L.check(lib.fegnn_mmd_forward(B, C_, ns, float(sigma), float(scale_vv), float(scale_rv), L.ptr(x), L.ptr(Z),
+                                          L.ptr(sample_idx), L.ptr(loss), _stream(x.device)), "fegnn_mmd_forward")
         ctx.save_for_backward(x, Z, sample_idx)
         ctx.cfg = (float(sigma), float(scale_vv), float(scale_rv))
         return loss[0]
@@ -197,8 +210,9 @@ class _MmdFn(torch.autograd.Function):
         gx = torch.empty_like(x)
         gZ = torch.empty_like(Z)
         gl = g.reshape(1).contiguous().float()
-        L.check(lib.fegnn_mmd_backward(x.size(0), B, C_, idx.size(1), sigma, svv, srv, L.ptr(x), L.ptr(Z), L.ptr(idx),
-                                       L.ptr(gl), L.ptr(gx), L.ptr(gZ), _stream()), "fegnn_mmd_backward")
+        with _on(x.device):
+            L.check(lib.fegnn_mmd_backward(x.size(0), B, C_, idx.size(1), sigma, svv, srv, L.ptr(x), L.ptr(Z), L.ptr(idx),
+                                           L.ptr(gl), L.ptr(gx), L.ptr(gZ), _stream(x.device)), "fegnn_mmd_backward")
         return gx, gZ, None, None, None, None
 
 
@@ -213,3 +227,41 @@ def mmd_loss(node_loc: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx:
     if sample_idx.dtype != torch.int32:
         sample_idx = sample_idx.to(torch.int32)
     return _MmdFn.apply(node_loc, virtual_node_loc, sample_idx.contiguous(), sigma, scale_vv, scale_rv)
+
+
+# ----------------------------------------------------------------------------- unsorted_segment_sum / _mean
+class _SegmentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, ids, num_segments, mean):
+        _require_cuda(data, "data")
+        dev = data.device
+        if ids.dtype != torch.int64:
+            raise L.FegnnError("segment_ids must be int64 (as in the reference)")
+        d2 = data.contiguous().float()
+        E, K = int(d2.size(0)), int(d2.size(1))
+        ids = ids.contiguous()
+        out = torch.empty(num_segments, K, device=dev, dtype=torch.float32)
+        cnt = torch.empty(num_segments, device=dev, dtype=torch.float32) if mean else None
+        with _on(dev):
+            L.check(lib.fegnn_segment_reduce(E, K, int(num_segments), L.ptr(d2), L.ptr(ids), int(bool(mean)), L.ptr(out),
+                                             L.ptr(cnt), _stream(dev)), "fegnn_segment_reduce")
+        ctx.save_for_backward(ids, cnt) if mean else ctx.save_for_backward(ids)
+        ctx.cfg = (E, K, int(num_segments), bool(mean))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        E, K, S, mean = ctx.cfg
+        ids = ctx.saved_tensors[0]
+        cnt = ctx.saved_tensors[1] if mean else None
+        g = g.contiguous().float()
+        gd = torch.empty(E, K, device=g.device, dtype=torch.float32)
+        with _on(g.device):
+            L.check(lib.fegnn_segment_reduce_backward(E, K, S, L.ptr(g), L.ptr(ids), L.ptr(cnt), L.ptr(gd),
+                                                      _stream(g.device)), "fegnn_segment_reduce_backward")
+        return gd, None, None, None
+
+
+def segment_reduce(data: torch.Tensor, segment_ids: torch.Tensor, num_segments: int, mean: bool) -> torch.Tensor:
+    """unsorted_segment_sum / unsorted_segment_mean of models/FastEGNN.py:279-294 (2-D data, int64 ids)."""
+    return _SegmentFn.apply(data, segment_ids, int(num_segments), bool(mean))

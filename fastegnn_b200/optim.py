@@ -79,6 +79,7 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         group = self.param_groups[0]
         ps = group["params"]
+        self._readopt(ps)
         sig = tuple(p.grad is not None for p in ps)
         if not any(sig):
             return loss
@@ -106,7 +107,44 @@ class FusedAdam(torch.optim.Optimizer):
             gptr = self._gflat.data_ptr()
         b1, b2 = group["betas"]
         st = torch.cuda.current_stream(self._pflat.device).cuda_stream
-        L.check(lib.fegnn_adam_step(self._n, L.ptr(self._pflat), gptr, L.ptr(self._m), L.ptr(self._v), L.ptr(self._live),
-                                    L.ptr(self._step), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                    float(group["weight_decay"]), st), "fegnn_adam_step")
+        with torch.cuda.device(self._pflat.device):          # the C ABI launches on the runtime's current device
+            L.check(lib.fegnn_adam_step(self._n, L.ptr(self._pflat), gptr, L.ptr(self._m), L.ptr(self._v),
+                                        L.ptr(self._live), L.ptr(self._step), float(group["lr"]), float(b1), float(b2),
+                                        float(group["eps"]), float(group["weight_decay"]), st), "fegnn_adam_step")
         return loss
+
+    # -- checkpoint / resume: the kernel reads the flat buffers, so loaded state is copied INTO them (a plain
+    #    Optimizer.load_state_dict would leave fresh tensors in self.state that the kernel never sees)
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        ps = self.param_groups[0]["params"]
+        steps = set()
+        with torch.no_grad():
+            for p, o in zip(ps, self._offs):
+                st_p = self.state.get(p)
+                if not st_p:
+                    continue
+                m_view = self._m[o:o + p.numel()].view_as(p)
+                v_view = self._v[o:o + p.numel()].view_as(p)
+                m_view.copy_(st_p["exp_avg"])
+                v_view.copy_(st_p["exp_avg_sq"])
+                steps.add(float(st_p["step"]))
+                self.state[p] = dict(step=self._step, exp_avg=m_view, exp_avg_sq=v_view)
+            if len(steps) > 1:
+                raise L.FegnnError("FusedAdam.load_state_dict: parameters carry different step counts; one shared "
+                                   "device counter cannot represent that")
+            if steps:
+                self._step.fill_(steps.pop())
+
+    def _readopt(self, ps):
+        """model.to() / .float() / _apply after construction give the Parameters fresh storage; point them back into the
+        flat buffer (keeping their current values) so the kernel and the model keep seeing the same memory."""
+        base = self._pflat.data_ptr()
+        with torch.no_grad():
+            for p, o in zip(ps, self._offs):
+                if p.data_ptr() != base + 4 * o:
+                    if p.device != self._pflat.device or p.dtype != torch.float32:
+                        raise L.FegnnError("FusedAdam: a parameter left the optimizer's device / dtype")
+                    view = self._pflat[o:o + p.numel()].view_as(p)
+                    view.copy_(p)
+                    p.data = view

@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .layer_fn import LayerPhases
-from .ops import CsrGraph, _require_cuda, _stream, layer_ptrs, make_dims
+from .ops import CsrGraph, _on, _require_cuda, _stream, layer_ptrs, make_dims
 
 lib = L.lib
 
@@ -93,6 +93,109 @@ class SlabPlan:
         out.update({k: np.ascontiguousarray(np.asarray(v)[p["edge_ids"]]) for k, v in edge_arrays.items()})
         out["edge_index"] = np.stack([p["row"], p["col"]]).astype(np.int64)
         return out
+
+
+class DeviceSlabPlan:
+    """The slab partition of a point cloud + radius graph, built by EVERY RANK FOR ITS OWN SLAB on its own device
+     -- no rank ever holds the global edge list (3e7 edges at config 5).
+
+    All ranks hold the cloud x [N,3] (12 MB at 1e6 nodes).  It is sorted along its longest axis (stable), rank k owns the
+    sorted positions [N k / world, N (k+1) / world).  Rank k gathers its owned points plus every point whose axis
+    coordinate lies within r of its slab (the only possible remote neighbours -- two contiguous runs of the sorted
+    order), builds THAT sub-cloud's radius graph with fegnn_radius_graph_* (CsrGraph.from_radius; the CSR rows of the owned
+    points are its prefix), keeps the candidates that are actually referenced as its halo (ascending sorted position ==
+    ascending (owner rank, owner-local id)), and renumbers cols to [owned | halo].  The halo lists (a few 10^4 ids per
+    rank) are all-gathered so that every rank can derive what it must send and every peer-memory address table.
+    Node ids inside the plan are SORTED POSITIONS; `order` maps them to the caller's node ids.
+
+    Exposes the same fields as SlabPlan (`world`, `N`, `owner`, `local_id`, `parts[k]` with n_own / halo / recv_counts and,
+    for this rank, send_idx / send_counts), so HaloComm and the address-table builders work with either."""
+
+    def __init__(self, x: torch.Tensor, r: float, world: int, rank: int, group=None, edge_attr_nf: int = 2,
+                 build_graph=None):
+        dev = x.device
+        N = int(x.size(0))
+        self.world, self.rank, self.N, self.r = world, rank, N, float(r)
+        ext = x.max(0).values - x.min(0).values
+        self.axis = int(torch.argmax(ext))
+        key_all = x[:, self.axis].contiguous()
+        self.order = torch.argsort(key_all, stable=True)                    # sorted position -> caller's node id
+        xs = x[self.order].contiguous()
+        key = xs[:, self.axis].contiguous()
+        b = [N * k // world for k in range(world + 1)]
+        self.bounds = np.array(b, dtype=np.int64)
+        b0, b1 = b[rank], b[rank + 1]
+        n_own = b1 - b0
+        if n_own > 0:
+            pad = float(r) * (1.0 + 1e-5) + 1e-30                           # candidates may be a superset (strict d2 < r2 test later)
+            lo, hi = key[b0] - pad, key[b1 - 1] + pad
+            s_lo = int(torch.searchsorted(key, lo.reshape(1), right=False))
+            s_hi = int(torch.searchsorted(key, hi.reshape(1), right=True))
+            s_lo, s_hi = min(s_lo, b0), max(s_hi, b1)
+        else:
+            s_lo, s_hi = b0, b1
+        cand_gid = torch.cat([torch.arange(s_lo, b0, device=dev), torch.arange(b1, s_hi, device=dev)])
+        cloud = torch.cat([xs[b0:b1], xs[s_lo:b0], xs[b1:s_hi]]).contiguous()
+        if build_graph is None:
+            g = CsrGraph.from_radius(cloud, torch.zeros(cloud.size(0), dtype=torch.int64, device=dev), 1, r, 0.0,
+                                     edge_attr_nf)
+        else:
+            g = build_graph(cloud)                                           # CPU tests inject the numpy oracle here
+        E_own = int(g.rowptr[n_own]) if n_own > 0 else 0
+        col = g.col[:E_own].long()
+        used = torch.zeros(cand_gid.numel() + 1, dtype=torch.bool, device=dev)
+        remote = col >= n_own
+        used[(col[remote] - n_own)] = True
+        used = used[:cand_gid.numel()]
+        newid = torch.cumsum(used.to(torch.int64), 0) - 1 + n_own
+        if cand_gid.numel():
+            col = torch.where(remote, newid[(col - n_own).clamp(min=0)], col)
+        halo_gid = cand_gid[used]
+        n_halo = int(halo_gid.numel())
+        # ---- this rank's graph in kernel layout: rows = owned, cols = [owned | halo]
+        g.N, g.Nl, g.E = n_own, n_own + n_halo, E_own
+        g.row, g.col = g.row[:E_own].contiguous(), col.to(torch.int32).contiguous()
+        g.edge_attr = g.edge_attr[:E_own].contiguous() if g.Fe else g.edge_attr
+        g.batch, g.dinv, g.rowptr = g.batch[:n_own].contiguous(), g.dinv[:n_own].contiguous(), g.rowptr[:n_own + 1].contiguous()
+        g.inv_nb = torch.full((1,), 1.0 / max(1, N), device=dev, dtype=torch.float32)    # graph size is global
+        if hasattr(g, "rebind"):
+            g.rebind()
+        self.graph = g
+        self.local_rows = self.order[torch.cat([torch.arange(b0, b1, device=dev), halo_gid])]   # caller's ids: owned | halo
+        # ---- halo lists of every rank (small): all-gather, padded to the longest
+        if world > 1:
+            cnt = torch.tensor([n_halo], dtype=torch.int64, device=dev)
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt, group=group)
+            cnts = [int(c) for c in cnts]
+            m = max(max(cnts), 1)
+            mine = torch.full((m,), -1, dtype=torch.int64, device=dev)
+            mine[:n_halo] = halo_gid
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)
+            halos = [h[:c].cpu().numpy() for h, c in zip(allh, cnts)]
+        else:
+            halos = [halo_gid.cpu().numpy()]
+        ids = np.arange(N, dtype=np.int64)
+        self.owner = (np.searchsorted(self.bounds, ids, side="right") - 1).astype(np.int32)
+        self.local_id = ids - self.bounds[self.owner]
+        self.parts: List[Dict[str, np.ndarray]] = []
+        for k in range(world):
+            hg = halos[k]
+            self.parts.append(dict(n_own=int(b[k + 1] - b[k]), halo=hg,
+                                   recv_counts=np.bincount(self.owner[hg], minlength=world).astype(np.int64)))
+        send_idx, send_counts = [], []
+        for d in range(world):
+            hg = halos[d]
+            mine_ = hg[self.owner[hg] == rank] if hg.size else hg
+            send_idx.append(self.local_id[mine_])
+            send_counts.append(mine_.size)
+        self.parts[rank]["send_idx"] = np.concatenate(send_idx).astype(np.int64)
+        self.parts[rank]["send_counts"] = np.array(send_counts, dtype=np.int64)
+        for k in range(world):                                               # every rank's send_counts follow from recv_counts
+            if k != rank:
+                self.parts[k]["send_counts"] = np.array([int(self.parts[d]["recv_counts"][k]) for d in range(world)],
+                                                        dtype=np.int64)
 
 
 class HaloComm:
@@ -244,10 +347,154 @@ class P2PHaloComm(HaloComm):
         self.allreduce(gG1, gZ_part)
 
 
+def fused_halo_tables(plan, rank: int, n_layers: int, nl_max: int, recv_cap: int, base_q, base_x, base_rq, base_rx,
+                      row_bytes_q: int = 4 * L.H, row_bytes_x: int = 12):
+    """Address / index tables of the fused (payload + signal) halo kernels for `rank` -- pure integer logic, unit-tested on
+    the CPU against a simulated address space.  base_q / base_x [world]: every rank's symmetric Q [L, nl_max, 64] and
+    x [L, nl_max, 3]; base_rq / base_rx [world]: every rank's RECEIVE buffers [2, recv_cap, 64] / [2, recv_cap, 3] of the
+    reverse halo, whose slot k belongs to the owner's send entry k (entries grouped by user rank, in the user's halo order).
+    Returns
+        fwd_q, fwd_x [L][n_send]      where send entry k lands (the forward tables of p2p_address_tables),
+        bwd_q, bwd_x [2][n_recv]      the slot, in the owner's receive buffer of either parity, of each halo row of `rank`,
+        rows [n_b], ptr [n_b + 1], slots [n_send]   per owned boundary row: its receive slots in (user rank, halo order)
+                                      order -- the fixed summation order of fegnn_halo_reduce_apply."""
+    parts = plan.parts
+    fwd_q, fwd_x, _, _ = p2p_address_tables(plan, rank, n_layers, nl_max, base_q, base_x, base_q, base_x,
+                                            row_bytes_q, row_bytes_x)
+    hg = parts[rank]["halo"]
+    own = plan.owner[hg].astype(np.int64)
+    rc = parts[rank]["recv_counts"]
+    seg_start = np.concatenate([[0], np.cumsum(rc)[:-1]])                   # my halo rows are grouped by owner rank
+    t = np.arange(hg.size, dtype=np.int64) - seg_start[own] if hg.size else np.zeros(0, np.int64)
+    # owner o's send entries are grouped by destination d: offset of destination `rank` = sum_{d < rank} send_counts_o[d]
+    send_off = np.array([int(parts[o]["send_counts"][:rank].sum()) for o in range(plan.world)], dtype=np.int64)
+    slot = send_off[own] + t if hg.size else np.zeros(0, np.int64)
+    brq, brx = np.asarray(base_rq, dtype=np.int64)[own], np.asarray(base_rx, dtype=np.int64)[own]
+    bwd_q = [brq + (par * recv_cap + slot) * row_bytes_q for par in range(2)]
+    bwd_x = [brx + (par * recv_cap + slot) * row_bytes_x for par in range(2)]
+    send_idx = parts[rank]["send_idx"]
+    order = np.argsort(send_idx, kind="stable")                             # by row, ties keep (user rank, halo order)
+    rows, first = np.unique(send_idx[order], return_index=True)
+    ptr = np.concatenate([first, [send_idx.size]]).astype(np.int64)
+    return fwd_q, fwd_x, bwd_q, bwd_x, rows.astype(np.int64), ptr, order.astype(np.int64)
+
+
+class FusedHaloComm(HaloComm):
+    """Every exchange of the partitioned layer as ONE kernel over peer memory (csrc/halo.cu, second generation): payload
+    stores into the peers' symmetric arrays, then signal / wait on per-rank signal pads inside the same kernel -- no NCCL
+    call, no separate barrier launch, nothing the host has to order, so the whole partitioned training step can be one
+    CUDA graph.
+        forward   fegnn_halo_push_signal: owners' (Q_j, x_j) -> users' halo rows of this layer's symmetric Q / x;
+                  fegnn_p2p_allreduce:    (Dsum, Usum, xsum') per layer, one-shot over symmetric slots, rank-ordered sum
+        backward  fegnn_halo_push_signal: users' (dQ_j, dx_j) halo rows -> the owner's receive slots (plain stores);
+                  fegnn_halo_reduce_apply: owners add their slots in fixed (rank, row) order -- DETERMINISTIC, no atomics;
+                  fegnn_p2p_allreduce:    (dG1, dZ) per layer.
+    Only the per-step weight-gradient all-reduce (1.3-1.7 MB) stays on NCCL."""
+
+    AR_CAPACITY = 8192            # floats per rank and slot set: (3C + HC + 3) B <= 8192 covers C = 16 up to B = 7
+
+    def __init__(self, plan, rank: int, device, n_layers: int, group=None):
+        super().__init__(plan, rank, device, group)
+        import torch.distributed._symmetric_memory as symm
+        grp = dist.group.WORLD if group is None else group
+        parts, W = plan.parts, plan.world
+        if W > L.P2P_MAX_WORLD:
+            raise L.FegnnError(f"fused halo transport supports up to {L.P2P_MAX_WORLD} ranks")
+        self.n_layers = n_layers
+        self.Nl_max = Nm = max(int(p["n_own"] + p["halo"].size) for p in parts)
+        self.recv_cap = cap = max(1, max(int(np.sum(p["send_counts"])) for p in parts))
+        f32 = dict(dtype=torch.float32, device=device)
+        self.Qs, self.xs = symm.empty(n_layers, Nm, L.H, **f32), symm.empty(n_layers, Nm, 3, **f32)
+        self.rq, self.rx = symm.empty(2, cap, L.H, **f32), symm.empty(2, cap, 3, **f32)
+        self.ar = symm.empty(2, W, self.AR_CAPACITY, **f32)
+        self.sig = symm.empty(L.P2P_CHANNELS, L.P2P_MAX_WORLD, dtype=torch.int32, device=device)
+        for t in (self.Qs, self.xs, self.rq, self.rx, self.ar, self.sig):
+            t.zero_()
+        self.hQ, self.hx = symm.rendezvous(self.Qs, grp), symm.rendezvous(self.xs, grp)
+        self.hrq, self.hrx = symm.rendezvous(self.rq, grp), symm.rendezvous(self.rx, grp)
+        self.har, self.hsig = symm.rendezvous(self.ar, grp), symm.rendezvous(self.sig, grp)
+        self.epoch = torch.zeros(L.P2P_CHANNELS, dtype=torch.int32, device=device)
+        self.done = torch.zeros(L.P2P_CHANNELS, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.p2p = L.P2P()
+        for r in range(W):
+            self.p2p.sig_peer[r] = int(self.hsig.buffer_ptrs[r])
+            self.p2p.ar_peer[r] = int(self.har.buffer_ptrs[r])
+        self.p2p.epoch, self.p2p.done, self.p2p.err = self.epoch.data_ptr(), self.done.data_ptr(), self.err.data_ptr()
+        self.p2p.rank, self.p2p.world, self.p2p.ar_capacity = rank, W, self.AR_CAPACITY
+        i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+        fq, fx, bq, bx, rows, ptr, slots = fused_halo_tables(plan, rank, n_layers, Nm, cap, self.hQ.buffer_ptrs,
+                                                             self.hx.buffer_ptrs, self.hrq.buffer_ptrs,
+                                                             self.hrx.buffer_ptrs)
+        self.send_idx32 = self.send_idx.to(torch.int32)
+        self.fwd_q, self.fwd_x = [i64(a) for a in fq], [i64(a) for a in fx]
+        self.bwd_q, self.bwd_x = [i64(a) for a in bq], [i64(a) for a in bx]
+        self.b_rows, self.b_ptr, self.b_slots = i32(rows), i32(ptr), i32(slots)
+        self._par = 0
+        self._layer_of = {}
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)             # every rank has zeroed its pads / slots before anyone signals
+
+    def check(self) -> None:
+        """Host-side check of the sticky error word (a bounded wait timed out); synchronises."""
+        e = int(self.err.item())
+        if e:
+            raise L.FegnnError(f"peer-memory exchange timed out on channel {e - 1} (a rank did not arrive)")
+
+    # -- small all-reduces: one-shot over symmetric slots
+    def allreduce(self, *tensors: torch.Tensor) -> None:
+        tot = sum(t.numel() for t in tensors)
+        if tot > self.AR_CAPACITY or len(tensors) > 4 or any(not t.is_contiguous() for t in tensors):
+            return super().allreduce(*tensors)
+        n = len(tensors)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        cnts = (C.c_int32 * n)(*[t.numel() for t in tensors])
+        L.check(lib.fegnn_p2p_allreduce(C.byref(self.p2p), 2, n, ptrs, cnts, _stream(self.device)), "fegnn_p2p_allreduce")
+
+    # -- forward
+    def bind_layer(self, ph: LayerPhases, layer: int) -> None:
+        ph.saved.c.Q = self.Qs[layer].data_ptr()
+        self._layer_of[id(ph)] = layer
+
+    def layer_x(self, layer: int, x: torch.Tensor, rows: int) -> torch.Tensor:
+        xs = self.xs[layer, :self.Nl]
+        xs[:rows].copy_(x[:rows])
+        return xs
+
+    def after_node_pre(self, ph: LayerPhases, x: torch.Tensor) -> None:
+        l = self._layer_of[id(ph)]
+        L.check(lib.fegnn_halo_push_signal(C.byref(self.p2p), 0, self.n_send, L.ptr(self.send_idx32), 0,
+                                           L.ptr(self.fwd_q[l]), L.ptr(self.fwd_x[l]), L.ptr(self.Qs[l]), L.ptr(x),
+                                           _stream(self.device)), "fegnn_halo_push_signal")
+
+    # -- backward
+    def after_edge_backward(self, ph: LayerPhases, gQ, gx, gG1, gZ_part) -> None:
+        par = self._par
+        self._par ^= 1
+        st = _stream(self.device)
+        L.check(lib.fegnn_halo_push_signal(C.byref(self.p2p), 1, self.n_recv, None, self.N, L.ptr(self.bwd_q[par]),
+                                           L.ptr(self.bwd_x[par]), L.ptr(gQ), L.ptr(gx), st), "fegnn_halo_push_signal")
+        L.check(lib.fegnn_halo_reduce_apply(int(self.b_rows.numel()), L.ptr(self.b_rows), L.ptr(self.b_ptr),
+                                            L.ptr(self.b_slots), L.ptr(self.rq[par]), L.ptr(self.rx[par]), L.ptr(gQ),
+                                            L.ptr(gx), st), "fegnn_halo_reduce_apply")
+        self.allreduce(gG1, gZ_part)
+
+
 # ------------------------------------------------------------------------------------- autograd driver
 class _PartitionedStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner: "PartitionedFastEGNN", graph: CsrGraph, node_feat, x0, v, loc_mean, *params):
+        with _on(x0.device):                  # the C ABI launches on the runtime's current device
+            return _PartitionedStackFn._forward(ctx, runner, graph, node_feat, x0, v, loc_mean, *params)
+
+    @staticmethod
+    def backward(ctx, gx_out, gZ_out):
+        with _on(ctx.saved_tensors[1].device):
+            return _PartitionedStackFn._backward(ctx, gx_out, gZ_out)
+
+    @staticmethod
+    def _forward(ctx, runner: "PartitionedFastEGNN", graph: CsrGraph, node_feat, x0, v, loc_mean, *params):
         mod, comm = runner.model, runner.comm
         dev = x0.device
         N, Nl, B, Cc, Lyr = comm.N, comm.Nl, graph.B, mod.virtual_channels, mod.n_layers
@@ -258,8 +505,13 @@ class _PartitionedStackFn(torch.autograd.Function):
                                         L.ptr(mod.embedding_in.bias), L.ptr(h), st), "embed_forward")
         S = mod.virtual_node_feat.detach()[0].t().contiguous().unsqueeze(0).repeat(B, 1, 1).contiguous()
         Z = loc_mean
-        p2p = isinstance(comm, P2PHaloComm)
-        if p2p:
+        p2p = isinstance(comm, (P2PHaloComm, FusedHaloComm))
+        if runner._pending and p2p:
+            # the saved Q / x of every layer live in per-layer symmetric arrays that a second forward would overwrite
+            raise L.FegnnError("PartitionedFastEGNN: a forward started while the previous forward still waits for its "
+                               "backward (peer-memory halo arrays are single-buffered per layer)")
+        runner._pending = torch.is_grad_enabled()
+        if isinstance(comm, P2PHaloComm):
             comm.barrier()                                                 # peers are done reading last step's arrays
         x = x0.clone()                                                     # [Nl,3]; halo rows refreshed every layer
         xsum = torch.empty(B, 3, device=dev, dtype=torch.float32)
@@ -283,8 +535,9 @@ class _PartitionedStackFn(torch.autograd.Function):
         return x[:N].contiguous(), Z
 
     @staticmethod
-    def backward(ctx, gx_out, gZ_out):
+    def _backward(ctx, gx_out, gZ_out):
         runner, graph, phases, states = ctx.runner, ctx.graph, ctx.phases, ctx.states
+        runner._pending = False
         mod, comm = runner.model, runner.comm
         node_feat, v = ctx.saved_tensors
         dev = v.device
@@ -330,27 +583,44 @@ class PartitionedFastEGNN:
         """halo = "nccl": pack + all-to-all + unpack; "p2p": direct peer stores / remote atomics over NVLink
         (P2PHaloComm; needs torch symmetric memory, i.e. all ranks on one NVLink / NVSwitch domain)."""
         self.model, self.plan, self.rank = model, plan, rank
-        if halo == "p2p":
+        if halo == "fused":
+            self.comm = FusedHaloComm(plan, rank, device, model.n_layers, group)
+        elif halo == "p2p":
             self.comm = P2PHaloComm(plan, rank, device, model.n_layers, group)
         elif halo == "nccl":
             self.comm = HaloComm(plan, rank, device, group)
         else:
-            raise ValueError(f"halo must be 'nccl' or 'p2p', got {halo!r}")
+            raise ValueError(f"halo must be 'nccl', 'p2p' or 'fused', got {halo!r}")
         self.last_local_grads = None
+        self._pending = False
+        self._flat = None
 
     def __call__(self, node_feat, node_loc, node_vel, edge_index, loc_mean, edge_attr, n_global: int):
         """node_* hold this rank's owned rows followed by its halo rows ([Nl, .]); edge_index is local
-        (row < N owned, col < Nl); loc_mean [B,3,C] is replicated.  Returns (x' of the OWNED rows, Z')."""
+        (row < N owned, col < Nl) -- or this rank's prebuilt CsrGraph (DeviceSlabPlan.graph; edge_attr must then be None);
+        loc_mean [1,3,C] is replicated.  Returns (x' of the OWNED rows, Z')."""
         _require_cuda(node_loc, "node_loc")
         N = self.comm.N
         B = int(loc_mean.size(0))
-        batch = torch.zeros(N, dtype=torch.int64, device=node_loc.device)
-        graph = CsrGraph(edge_index, batch, edge_attr, B, n_local=self.comm.Nl)
-        graph.inv_nb.fill_(1.0 / max(1, n_global))                        # graph size is global, not the slab's
+        if B != 1:
+            raise L.FegnnError(f"the partitioned path runs ONE graph across the ranks (loc_mean has B={B}); batches of "
+                               "small graphs go whole to the ranks (data parallel)")
+        if isinstance(edge_index, CsrGraph):
+            graph = edge_index
+            if edge_attr is not None:
+                raise TypeError("edge_attr must be None when edge_index is a prebuilt CsrGraph (it carries its own)")
+            if graph.N != N or graph.Nl != self.comm.Nl:
+                raise L.FegnnError(f"prebuilt slab graph (N={graph.N}, Nl={graph.Nl}) does not match the plan "
+                                   f"(N={N}, Nl={self.comm.Nl})")
+        else:
+            batch = torch.zeros(N, dtype=torch.int64, device=node_loc.device)
+            graph = CsrGraph(edge_index, batch, edge_attr, B, n_local=self.comm.Nl)
+            graph.inv_nb.fill_(1.0 / max(1, n_global))                    # graph size is global, not the slab's
         params = [p for _, p in self.model.named_parameters()]
-        return _PartitionedStackFn.apply(self, graph, node_feat[:N].contiguous().float(),
-                                         node_loc.contiguous().float(), node_vel[:N].contiguous().float(),
-                                         loc_mean.contiguous().float(), *params)
+        with _on(node_loc.device):
+            return _PartitionedStackFn.apply(self, graph, node_feat[:N].contiguous().float(),
+                                             node_loc.contiguous().float(), node_vel[:N].contiguous().float(),
+                                             loc_mean.contiguous().float(), *params)
 
     def allreduce_gradients(self) -> None:
         """Sum the weight gradients over ranks (one collective on a flat buffer)."""

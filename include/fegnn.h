@@ -50,6 +50,10 @@ extern "C" {
                                  vel_w0 is [H,1] and the head is evaluated by fegnn_rf_vel_forward / _backward instead
                                  of fegnn_node_pre_*.  Understood by fegnn_node_pre_* and fegnn_model_*.            */
 
+#define FEGNN_F_COORDS_SUM 64u /* E_GCL_vel(coords_agg='sum') (:124-125): d_e * phi_x(m_e) is summed, not averaged, over
+                                 the edges of a row.  Understood by fegnn_virtual_forward / _backward (the phase that
+                                 applies 1/deg to tsum); FastEGNN itself never sets it (:261).                          */
+
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
   int32_t Nl;       /* rows of x / Q: owned + halo (== N on one GPU)                */
@@ -114,6 +118,7 @@ typedef struct fegnn_layer_saved {
   float *u;                 /* [N,C,H] real->virtual messages                             */
   float *zh1;               /* [N,H] phi_h pre-activation                                 */
   float *Dsum, *Usum;       /* [B,3,C] [B,C,H] per-graph partial sums (all-reduced when partitioned) */
+  float *scratch;           /* [16] words of per-layer kernel scratch (edge backward mode 5: the bound pre-pass)  */
 } fegnn_layer_saved;
 
 const char* fegnn_last_error(void);
@@ -123,7 +128,8 @@ unsigned long long fegnn_launch_count(void);
 /* Arithmetic mode of a phase.  "edge_forward": 0 = fp32 FMA kernel, 1 = tcgen05 single-pass TF32 tiles (default),
  * 3 = tcgen05 error-compensated 3xTF32 tiles (fp32-grade).  "edge_backward": 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with
  * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
- * 256 / 512 threads per 128-edge tile (4 is the default).  Layers with attention=True or Fe > 4 always take mode 0 in
+ * 256 / 512 threads per 128-edge tile, 5 = tcgen05 kind::f16 (fp16 operands with one power-of-two scale per launch and
+ * gradient tensor, fp32 accumulation; same 10-bit mantissa as TF32) with two 128-edge tiles in flight per SM.  Layers with attention=True or Fe > 4 always take mode 0 in
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
  * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels (default), 1 = tcgen05
  * TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's atol 1e-4 on
@@ -252,6 +258,39 @@ int fegnn_halo_push(int32_t n, const int32_t* src_row /*[n]*/, const uint64_t* d
 int fegnn_halo_reduce_push(int32_t n, int32_t first_halo_row, const uint64_t* dst_q /*[n]*/, const uint64_t* dst_x /*[n]*/,
                            const float* gQ /*[Nl,H]*/, const float* gx /*[Nl,3]*/, void* stream);
 
+/* Second generation: payload + inter-rank ordering in ONE kernel (no NCCL, no separate barrier launch).  Every rank owns
+ * a signal pad and a set of all-reduce slots in symmetric memory; fegnn_p2p carries the peers' addresses of both.
+ * A call stores its payload into the peers' memory, then its last CTA signals `epoch + 1` to every rank
+ * (st.release.sys) and waits for every rank's signal (ld.acquire.sys): when the kernel completes, everything destined for
+ * this rank has arrived, and stream order does the rest.  All ranks must issue the same sequence of calls per channel.
+ * A wait is bounded (~4 s); on timeout *err becomes 1 + channel and the kernel returns instead of hanging the GPU.
+ *   fegnn_halo_push_signal : src_row != NULL -> rows src_row[k] (forward: owners' (Q_j, x_j) into the users' halo rows);
+ *                            src_row == NULL -> rows row0 + k (backward: this rank's halo rows of dQ / dx into the OWNER's
+ *                            receive buffer, one slot per (user, row): plain stores, no remote atomics).
+ *   fegnn_halo_reduce_apply: local; owned boundary row rows[k] adds its received slots[ptr[k] .. ptr[k+1]) in that fixed
+ *                            order -> a deterministic reverse halo.
+ *   fegnn_p2p_allreduce    : one-shot sum over ranks, IN PLACE, of up to 4 device vectors (total <= ar_capacity floats;
+ *                            the <= 2 KB per-graph sums): slot [rank] of every peer is written, signal / wait, then the
+ *                            slots are added in rank order, so every rank gets bitwise the same result. */
+#define FEGNN_P2P_MAX_WORLD 16
+#define FEGNN_P2P_CHANNELS 4
+typedef struct fegnn_p2p {
+  uint64_t sig_peer[FEGNN_P2P_MAX_WORLD]; /* device address of rank p's signal pad: uint32 [CHANNELS][MAX_WORLD], zeroed once */
+  uint64_t ar_peer[FEGNN_P2P_MAX_WORLD];  /* device address of rank p's all-reduce slots: float [2][world][ar_capacity]       */
+  uint32_t* epoch;                        /* [CHANNELS] local device counters, zeroed once                                    */
+  uint32_t* done;                         /* [CHANNELS] local CTA counters, zeroed once                                       */
+  int32_t* err;                           /* [1] local sticky error word                                                      */
+  int32_t rank, world, ar_capacity;
+} fegnn_p2p;
+int fegnn_halo_push_signal(const fegnn_p2p* p, int32_t channel, int32_t n, const int32_t* src_row /*[n] or NULL*/,
+                           int32_t row0, const uint64_t* dst_q /*[n]*/, const uint64_t* dst_x /*[n]*/,
+                           const float* Q /*[.,H]*/, const float* x /*[.,3]*/, void* stream);
+int fegnn_halo_reduce_apply(int32_t n_rows, const int32_t* rows, const int32_t* ptr /*[n_rows+1]*/, const int32_t* slots,
+                            const float* recv_q /*[slots,H]*/, const float* recv_x /*[slots,3]*/, float* gQ, float* gx,
+                            void* stream);
+int fegnn_p2p_allreduce(const fegnn_p2p* p, int32_t channel, int32_t nseg, float* const* seg_host /*[nseg] device ptrs*/,
+                        const int32_t* count_host /*[nseg]*/, void* stream);
+
 /* FastRF's velocity head (models/FastRF.py:76-80,135,165): sv_i = w2 . silu(w0 |v_i| + b0) + b2 with
  * |v_i| = sqrt(vx^2 + vy^2 + vz^2) (detached data).  The backward accumulates (+=) into gr->vel_*. */
 int fegnn_rf_vel_forward(int32_t N, const float* v /*[N,3]*/, const fegnn_layer_params* p, float* sv /*[N]*/, void* stream);
@@ -295,6 +334,24 @@ int fegnn_mmd_forward(int32_t B, int32_t C, int32_t ns, float sigma, float scale
 int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float scale_vv, float scale_rv,
                        const float* x, const float* Z, const int32_t* sample_idx, const float* gloss /*[1]*/,
                        float* gx /*[N,3] zeroed here*/, float* gZ /*[B,3,C] =*/, void* stream);
+
+/* ------------------------------------------------------------------ roofline probes (measurement only)
+ * One launch of a micro-benchmark for the pipe a kernel of the path is bound by: kind 0 = tcgen05.mma kind::tf32
+ * (cta_group::1, M128 N256 K8, shared-memory operands), 1 = tcgen05.mma kind::f16 (K16), 2 = fp32 FMA, 3 = MUFU
+ * tanh.approx.  `iters` instructions per issuing thread; *ops_host (HOST pointer) receives the flops (kinds 0-2) or MUFU
+ * results (kind 3) of the launch.  The caller times the launch with CUDA events (bench.py: peak_*_measured). */
+int fegnn_peak_probe(int32_t kind, int32_t iters, float* sink /*[1] device*/, double* ops_host, void* stream);
+
+/* ------------------------------------------------------------------ segment helpers exported by the reference file
+ * unsorted_segment_sum (models/FastEGNN.py:279-284) and unsorted_segment_mean (:287-294) on int64 segment ids, as the
+ * reference passes them: out [S,K] (zeroed here) = sum of data rows [E,K] per segment; mean != 0 additionally divides by
+ * the per-segment row count clamped to >= 1 (count [S] is written).  The backward gathers g_out rows back to the edges
+ * (divided by the same clamped count when count != NULL).  The fused edge kernels do NOT go through these. */
+int fegnn_segment_reduce(int64_t E, int32_t K, int32_t S, const float* data /*[E,K]*/, const int64_t* segment_ids /*[E]*/,
+                         int32_t mean, float* out /*[S,K]*/, float* count /*[S] or NULL when mean == 0*/, void* stream);
+int fegnn_segment_reduce_backward(int64_t E, int32_t K, int32_t S, const float* g_out /*[S,K]*/,
+                                  const int64_t* segment_ids, const float* count /*[S] or NULL*/, float* g_data /*[E,K]*/,
+                                  void* stream);
 
 /* ------------------------------------------------------------------ optimizer step
  * torch.optim.Adam (amsgrad=False, maximize=False; utils/train.py:168-170, main_*.py optimizer construction) over ONE

@@ -56,6 +56,7 @@ class OracleConfig:
     tanh: bool = False
     gravity: Optional[Sequence[float]] = None
     eps: float = 1e-8                      # models/FastEGNN.py:21
+    coords_agg: str = "mean"               # E_GCL_vel kwarg (:12,:124-131); FastEGNN never passes it (:261)
 
 
 # --------------------------------------------------------------------------- parameters
@@ -208,8 +209,14 @@ def layer_forward(params: Dict[str, Tensor], p: str, cfg: OracleConfig,
                                        params[f"{p}.att_mlp_virtual.0.bias"]))
     u = u.permute(0, 2, 1)                                                                 # [N,H,C]
 
-    # coord_model_vel, :122-144 (coords_agg is always 'mean', :261 never passes it)
-    x_new = x + segment_mean_rows(d * _coord_head(params, f"{p}.coord_mlp_r", m, cfg.tanh), row, N)
+    # coord_model_vel, :122-144 (FastEGNN never passes coords_agg, :261: 'mean'; the layer class accepts 'sum', :124-131)
+    trans = d * _coord_head(params, f"{p}.coord_mlp_r", m, cfg.tanh)
+    if cfg.coords_agg == "sum":
+        x_new = x + segment_sum_rows(trans, row, N)
+    elif cfg.coords_agg == "mean":
+        x_new = x + segment_mean_rows(trans, row, N)
+    else:
+        raise Exception('Wrong coords_agg parameter')                                      # :131
     s_xv = _coord_head(params, f"{p}.coord_mlp_r_virtual", u.permute(0, 2, 1), cfg.tanh).permute(0, 2, 1)
     x_new = x_new + torch.mean(-D * s_xv, dim=-1)
     x_new = x_new + _mlp2(params, f"{p}.coord_mlp_vel", h, False) * v

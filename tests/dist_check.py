@@ -43,24 +43,41 @@ def main():
     t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
     x0 = t["loc_0"].clone().requires_grad_(True)
     lm = t["loc_mean"].clone().requires_grad_(True)
-    xr, Zr = model(node_feat=t["node_feat"], node_loc=x0, node_vel=t["vel_0"], edge_index=t["edge_index"],
-                   data_batch=t["batch"], loc_mean=lm, edge_attr=t["edge_attr"])
+    device_plan = os.environ.get("CHECK_PLAN", "host") == "device"
+    if device_plan:
+        # the graph is built ON THE DEVICE in both arms (the fp32 d2 < r2 test decides membership, not the KD-tree)
+        from fastegnn_b200 import CsrGraph
+        gfull = CsrGraph.from_radius(t["loc_0"], t["batch"], 1, data["radius"], 0.0, 2)
+        xr, Zr = model(node_feat=t["node_feat"], node_loc=x0, node_vel=t["vel_0"], edge_index=gfull,
+                       data_batch=t["batch"], loc_mean=lm)
+    else:
+        xr, Zr = model(node_feat=t["node_feat"], node_loc=x0, node_vel=t["vel_0"], edge_index=t["edge_index"],
+                       data_batch=t["batch"], loc_mean=lm, edge_attr=t["edge_attr"])
     ((xr * wx.to(dev)).sum() + (Zr * wz.to(dev)).sum()).backward()
     ref_grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()}
     ref_gx0, ref_glm = x0.grad.clone(), lm.grad.clone()
     model.zero_grad(set_to_none=True)
 
     # ---- partitioned
-    plan = SlabPlan(data["loc_0"].numpy(), data["edge_index"].numpy(), world)
-    loc = plan.localize(rank, dict(node_feat=data["node_feat"].numpy(), loc_0=data["loc_0"].numpy(),
-                                   vel_0=data["vel_0"].numpy(), wx=wx.numpy()),
-                        dict(edge_attr=data["edge_attr"].numpy()))
-    lt = {k: torch.from_numpy(v).to(dev) for k, v in loc.items()}
     halo = os.environ.get("CHECK_HALO", "nccl")
+    if device_plan:
+        from fastegnn_b200.partitioned import DeviceSlabPlan
+        plan = DeviceSlabPlan(t["loc_0"], data["radius"], world, rank)       # every rank builds ITS slab on its device
+        rows = plan.local_rows
+        lt = dict(node_feat=t["node_feat"][rows], loc_0=t["loc_0"][rows], vel_0=t["vel_0"][rows], wx=wx.to(dev)[rows],
+                  edge_index=plan.graph, edge_attr=None)
+        owned_ids = rows[:plan.parts[rank]["n_own"]]
+    else:
+        plan = SlabPlan(data["loc_0"].numpy(), data["edge_index"].numpy(), world)
+        loc = plan.localize(rank, dict(node_feat=data["node_feat"].numpy(), loc_0=data["loc_0"].numpy(),
+                                       vel_0=data["vel_0"].numpy(), wx=wx.numpy()),
+                            dict(edge_attr=data["edge_attr"].numpy()))
+        lt = {k: torch.from_numpy(v).to(dev) for k, v in loc.items()}
+        owned_ids = torch.from_numpy(plan.parts[rank]["owned"]).to(dev)
     runner = PartitionedFastEGNN(model, plan, rank, dev, halo=halo)
     N = runner.comm.N
-    # several steps through the same runner: the peer-memory path reuses its symmetric arrays from step to step
-    for it in range(3 if halo == "p2p" else 1):
+    # several steps through the same runner: the peer-memory paths reuse their symmetric arrays from step to step
+    for it in range(3 if halo in ("p2p", "fused") else 1):
         model.zero_grad(set_to_none=True)
         xl = lt["loc_0"].clone().requires_grad_(True)
         lm2 = t["loc_mean"].clone().requires_grad_(True)
@@ -73,10 +90,12 @@ def main():
         loss.backward()
         runner.allreduce_gradients()
     torch.cuda.synchronize()
+    if hasattr(runner.comm, "check"):
+        runner.comm.check()            # sticky error word of the fused exchange kernels (a bounded wait timed out)
 
     def rel(a, b):
         return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
-    owned = torch.from_numpy(plan.parts[rank]["owned"]).to(dev)
+    owned = owned_ids
     errs = dict(x=rel(xo, xr.detach()[owned]), Z=rel(Zo, Zr.detach()), gx0=rel(xl.grad[:N], ref_gx0[owned]),
                 gloc_mean=rel(lm2.grad, ref_glm))
     worst_w = 0.0
@@ -93,7 +112,7 @@ def main():
     ok = (errs["x"] < tol_out and errs["Z"] < tol_out and errs["gx0"] < tol_grad and errs["gloc_mean"] < tol_grad and
           worst_w < tol_grad and not bad_none)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{halo}_w{world}_c{C}_rank{rank}.txt"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{halo}{'_devplan' if device_plan else ''}_w{world}_c{C}_rank{rank}.txt"), "w") as f:
         f.write(f"world {world} rank {rank} N_owned {N} halo {runner.comm.Nl - N} ok {ok}\n")
         for k in ("x", "Z", "gx0", "gloc_mean"):
             f.write(f"{k}: {errs[k]:.3e}\n")

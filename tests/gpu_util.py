@@ -8,13 +8,26 @@ from tests.helpers import oracle_run
 
 import contextlib
 
-# Stated tolerances per arithmetic mode, relative to the largest entry of each tensor:
-#   fp32    every phase on the fp32 FMA kernels (observed ~1e-7 / ~1e-6)
-#   tf32x3  fused edge forward on 3xTF32 tensor-core tiles (fp32-grade), edge backward on TF32 tiles
-#   tf32    (product default) fused edge forward and backward on single-pass TF32 tiles with tanh.approx SiLU:
-#           10-bit-mantissa operands, fp32 accumulation (observed ~4e-3 outputs with coordinate heads scaled x1000,
-#           ~6e-3 gradients)
-TOLERANCES = {"fp32": (2e-5, 2e-4), "tf32x3": (2e-5, 2e-2), "tf32": (1e-2, 2e-2)}
+# Stated tolerances per arithmetic mode.  Outputs are judged on the UPDATE the stack computes (x' - x, Z' - Z), relative to
+# the largest entry of the reference update, plus the fp32 rounding of the absolute coordinate the update is added to
+# (4 ulp of max |x'|: that term is the fp32 reference's own distance from fp64 when the update is small, e.g. 1e-3 |x| under
+# the reference's default initialisation); gradients relative to the largest entry of each gradient tensor.  Each bound is
+# about twice the worst value observed on the B200 over every case of the suite (profiles/parity_report_r2.txt):
+#   fp32    every phase on the fp32 FMA kernels: summation order and ex2.approx in SiLU are the only differences
+#   tf32x3  fused edge forward on error-compensated 3xTF32 tiles (fp32-grade outputs), backward on TF32 tiles
+#   tf32    (default) edge + virtual phases on single-pass TF32 tiles (10-bit mantissa operands, fp32 accumulation,
+#           tanh.approx SiLU), forward and backward
+class Tol(tuple):
+    """(out, gin) for `tol_out, tol_grad = ...` unpacking, with .out / .gin / .gw (weight gradients) fields."""
+    def __new__(cls, out, gin, gw):
+        t = super().__new__(cls, (out, gin))
+        t.out, t.gin, t.gw = out, gin, gw
+        return t
+
+
+TOLERANCES = {"fp32": Tol(2e-6, 4e-6, 8e-5), "tf32x3": Tol(1e-5, 5e-3, 2.5e-2), "tf32": Tol(8e-3, 5e-3, 2.5e-2),
+              "tf32_all": Tol(8e-3, 5e-3, 2.5e-2)}
+EPS32 = 2.0 ** -23
 
 
 @contextlib.contextmanager
@@ -97,8 +110,19 @@ def rel_err(a, ref):
     return float((a - ref).abs().max() / (ref.abs().max() + 1e-30))
 
 
-def compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=""):
-    """GPU result vs the fp64 oracle, with the fp32 oracle's own distance to fp64 alongside."""
+def update_err(got, want64, base):
+    """Error of an output judged on the update: (max |got - want|  -  4 ulp of max |want|) / max |want - base|."""
+    got, want64, base = got.double(), want64.double(), base.double()
+    upd = float((want64 - base).abs().max())
+    diff = float((got - want64).abs().max())
+    return max(0.0, diff - 4 * EPS32 * float(want64.abs().max())) / (upd + 1e-30)
+
+
+def compare_with_oracles(cfg, params, inp, res, tol, tol_grad=None, label=""):
+    """GPU result vs the fp64 oracle, with the fp32 oracle's own distance to fp64 alongside.  `tol` is a Tol (outputs on
+    the update, input gradients, weight gradients); the legacy (tol_out, tol_grad) pair is still accepted."""
+    if not isinstance(tol, Tol):
+        tol = Tol(tol, tol_grad, tol_grad)
     p64 = {k: v.double() for k, v in params.items()}
     i64 = {k: (v.double() if v is not None and v.is_floating_point() else v) for k, v in inp.items()}
     r64 = oracle_run(cfg, p64, i64)
@@ -115,11 +139,14 @@ def compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=""):
         return ok
 
     bad = []
-    for k in ("x", "Z"):
-        if not chk(k, res[k], r64[k], r32[k], tol_out):
+    for k, base in (("x", inp["node_loc"]), ("Z", inp["loc_mean"])):
+        e_gpu, e_ref = update_err(res[k], r64[k], base), update_err(r32[k], r64[k], base)
+        report.append(f"{label}{k} (update): gpu {e_gpu:.2e}  oracle32 {e_ref:.2e}")
+        worst = max(worst, e_gpu / tol.out)
+        if e_gpu > tol.out:
             bad.append(k)
     for k in ("node_loc", "loc_mean", "node_feat"):
-        if not chk("gin." + k, res["gin"][k], r64["gin"][k], r32["gin"][k], tol_grad):
+        if not chk("gin." + k, res["gin"][k], r64["gin"][k], r32["gin"][k], tol.gin):
             bad.append(k)
     for k, g64 in r64["gp"].items():
         if g64 is None:
@@ -129,6 +156,6 @@ def compare_with_oracles(cfg, params, inp, res, tol_out, tol_grad, label=""):
         if res["gp"][k] is None:
             bad.append(k + " (missing grad)")
             continue
-        if not chk("gp." + k, res["gp"][k], g64, r32["gp"][k], tol_grad):
+        if not chk("gp." + k, res["gp"][k], g64, r32["gp"][k], tol.gw):
             bad.append(k)
     return bad, report

@@ -62,3 +62,17 @@ def oracle_run(cfg, params, inp, want_grads=True):
         res["gin"] = {k: t.grad for k, t in leaf.items()}
         res["gp"] = {k: t.grad for k, t in p.items()}
     return res
+
+
+LAYER_CASES = ["layer_sum", "layer_mean_gravity"]
+
+
+def load_layer_case(name):
+    """Golden vectors of ONE reference layer (oracle/make_golden_layer.py): returns (cfg, params keyed 'gcl_0.*', arrays)."""
+    arr = dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+    grav = arr["gravity"].tolist() or None
+    C = int(arr["in_S"].shape[2])
+    cfg = orc.OracleConfig(node_feat_nf=2, edge_attr_nf=int(arr["in_edge_attr"].shape[1]), hidden_nf=64,
+                           virtual_channels=C, n_layers=1, gravity=grav, coords_agg=str(arr["coords_agg"]))
+    params = {"gcl_0." + k[2:]: torch.from_numpy(v) for k, v in arr.items() if k.startswith("p_")}
+    return cfg, params, arr

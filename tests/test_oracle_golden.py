@@ -105,3 +105,43 @@ def test_equivariance_property_of_oracle():
     a = run(x, v) @ R + t
     b = run(x @ R + t, v @ R)
     assert torch.allclose(a, b, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["layer_sum", "layer_mean_gravity"])
+def test_layer_forward_matches_reference_layer(name):
+    """E_GCL_vel called directly (oracle/make_golden_layer.py), which pins coords_agg='sum' (models/FastEGNN.py:124-125)."""
+    from tests.helpers import load_layer_case
+    torch.set_num_threads(1)
+    cfg, params, arr = load_layer_case(name)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    t = lambda k: torch.from_numpy(arr[k])
+    h, x, Z, S = (t(k).clone().requires_grad_(True) for k in ("in_h", "in_node_loc", "in_loc_mean", "in_S"))
+    ho, xo, So, Zo = orc.layer_forward(p, "gcl_0", cfg, h, t("in_edge_index"), x, t("in_node_vel"), Z, S,
+                                       t("in_data_batch"), t("in_edge_attr"))
+    ((ho * t("wh")).sum() + (xo * t("in_wx")).sum() + (So * t("wS")).sum() + (Zo * t("in_wz")).sum()).backward()
+    for got, key in ((ho, "out_h"), (xo, "out_x"), (So, "out_S"), (Zo, "out_Z")):
+        np.testing.assert_allclose(got.detach().numpy(), arr[key], rtol=RTOL, atol=ATOL, err_msg=key)
+    for got, key in ((h, "g_h"), (x, "g_x"), (S, "g_S"), (Z, "g_Z")):
+        scale = np.abs(arr[key]).max() + 1e-30
+        np.testing.assert_allclose(got.grad.numpy(), arr[key], rtol=1e-4, atol=2e-5 * scale, err_msg=key)
+    for k, v in p.items():
+        ref = arr["gp_" + k[len("gcl_0."):]]
+        scale = np.abs(ref).max() + 1e-30
+        np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-3, atol=2e-5 * scale, err_msg=k)
+
+
+def test_wrong_coords_agg_raises_like_the_reference():
+    from tests.helpers import load_layer_case
+    cfg, params, arr = load_layer_case("layer_sum")
+    cfg.coords_agg = "max"
+    t = lambda k: torch.from_numpy(arr[k])
+    with pytest.raises(Exception, match="Wrong coords_agg parameter"):
+        orc.layer_forward(params, "gcl_0", cfg, t("in_h"), t("in_edge_index"), t("in_node_loc"), t("in_node_vel"),
+                          t("in_loc_mean"), t("in_S"), t("in_data_batch"), t("in_edge_attr"))
+
+
+def test_segment_helpers_match_reference():
+    arr = dict(np.load(os.path.join(GOLDEN, "segment_helpers.npz")))
+    data, ids, n = torch.from_numpy(arr["data"]), torch.from_numpy(arr["ids"]), int(arr["num"])
+    np.testing.assert_allclose(orc.segment_sum_rows(data, ids, n).numpy(), arr["sum"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(orc.segment_mean_rows(data, ids, n).numpy(), arr["mean"], rtol=1e-6, atol=1e-6)

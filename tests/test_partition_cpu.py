@@ -188,3 +188,137 @@ def test_peer_memory_address_tables_in_a_simulated_address_space(world):
                 np.testing.assert_allclose(outQ[k][:p["n_own"]], gQ[k][:p["n_own"]] + accQ[p["owned"]], rtol=0, atol=1e-12)
             np.testing.assert_allclose(outX[k][slot, :p["n_own"]], gX[k][slot, :p["n_own"]] + accX[p["owned"]], rtol=0,
                                        atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------- device-built slab plan (host logic)
+class _FakeGraph:
+    """What CsrGraph.from_radius returns, from the numpy oracle (the CPU tests have no GPU to build it on)."""
+
+    def __init__(self, cloud: torch.Tensor, r: float):
+        from oracle import radius_graph_oracle as rgo
+        n = cloud.size(0)
+        o = rgo.radius_graph_csr(cloud.numpy(), np.array([0, n]), r, 0.0)
+        self.N = self.Nl = n
+        self.B, self.Fe = 1, 2
+        self.E = int(o["row"].shape[0])
+        self.row, self.col = torch.from_numpy(o["row"].astype(np.int32)), torch.from_numpy(o["col"].astype(np.int32))
+        deg = np.bincount(o["row"], minlength=n)
+        self.rowptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]).astype(np.int32))
+        self.edge_attr = torch.from_numpy(np.stack([o["length"], o["length"]], 1))
+        self.batch = torch.zeros(n, dtype=torch.int32)
+        self.dinv = torch.from_numpy((1.0 / np.maximum(deg, 1)).astype(np.float32))
+        self.inv_nb = torch.ones(1)
+
+
+def _device_plan_worker(rank, world, port, x, r, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fastegnn_b200.partitioned import DeviceSlabPlan
+        plan = DeviceSlabPlan(torch.from_numpy(x), r, world, rank, build_graph=lambda c: _FakeGraph(c, r))
+        g = plan.graph
+        rows = plan.local_rows.numpy()
+        out[rank] = dict(rows=rows, n_own=g.N, row=rows[g.row.numpy()], col=rows[g.col.numpy()],
+                         length=g.edge_attr[:, 0].numpy(), dinv=g.dinv.numpy(), order=plan.order.numpy(),
+                         parts=[dict(p) for p in plan.parts], owner=plan.owner, local_id=plan.local_id)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_device_slab_plan_reassembles_the_global_radius_graph(world):
+    """DeviceSlabPlan: every rank builds its own slab's graph from (owned + candidate) points; together the slabs must
+    hold exactly the global radius graph, each edge once at the owner of its row, with halo lists / send lists that
+    mirror each other -- the same invariants test_slab_plan_reassembles_the_global_graph checks for the numpy plan."""
+    from oracle import radius_graph_oracle as rgo
+    rng = np.random.default_rng(4)
+    n, r = 600, 0.2
+    x = (rng.random((n, 3)) * np.array([3.0, 1.0, 1.0])).astype(np.float32)
+    ref = rgo.radius_graph_csr(x, np.array([0, n]), r, 0.0)
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    if world == 1:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(_free_port())
+        _device_plan_worker(0, 1, int(os.environ["MASTER_PORT"]), x, r, out)
+    else:
+        mp.spawn(_device_plan_worker, args=(world, _free_port(), x, r, out), nprocs=world, join=True)
+    got = set()
+    owned_all = []
+    for k in range(world):
+        o = out[k]
+        owned_all.append(o["rows"][:o["n_own"]])
+        assert np.isin(o["row"], o["rows"][:o["n_own"]]).all()                   # rows are owned
+        pairs = set(zip(o["row"].tolist(), o["col"].tolist()))
+        assert len(pairs) == o["row"].size and not (pairs & got)
+        got |= pairs
+        d = np.linalg.norm(x[o["row"]] - x[o["col"]], axis=1)
+        np.testing.assert_allclose(o["length"], d, rtol=1e-5, atol=1e-7)
+        deg = np.bincount(np.searchsorted(o["rows"][:o["n_own"]], o["row"], sorter=np.argsort(o["rows"][:o["n_own"]])),
+                          minlength=o["n_own"])
+        halo_rows = o["rows"][o["n_own"]:]
+        assert np.array_equal(np.unique(o["col"][~np.isin(o["col"], o["rows"][:o["n_own"]])]), np.unique(halo_rows))
+        parts, owner = o["parts"], o["owner"]
+        assert np.array_equal(o["order"][parts[k]["halo"]], halo_rows)            # halo in (owner rank, owner-local id) order
+        assert np.all(np.diff(parts[k]["halo"]) > 0) and (owner[parts[k]["halo"]] != k).all()
+        assert parts[k]["recv_counts"].sum() == parts[k]["halo"].size
+    assert got == set(zip(ref["row"].tolist(), ref["col"].tolist()))
+    assert sorted(np.concatenate(owned_all).tolist()) == list(range(n))
+    for k in range(world):                                                        # send lists mirror the receivers' halos
+        pk = out[k]["parts"][k]
+        for d in range(world):
+            o0 = int(pk["send_counts"][:d].sum())
+            sent = out[k]["order"][out[k]["parts"][k]["send_idx"][o0:o0 + int(pk["send_counts"][d])] + int(n * k // world)]
+            hd = out[d]["parts"][d]["halo"]
+            want = out[d]["order"][hd[out[d]["owner"][hd] == k]]
+            assert np.array_equal(sent, want), (k, d)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_fused_halo_tables_in_a_simulated_address_space(world):
+    """Tables of the fused (payload + signal) halo kernels: forward stores land in the users' halo rows; the reverse halo
+    stores every user's halo-gradient row into a distinct slot of the owner's receive buffer, and the owner's (rows, ptr,
+    slots) lists add exactly those slots -- in a FIXED order -- to the right owned rows."""
+    from fastegnn_b200.partitioned import SlabPlan, fused_halo_tables
+    x, ei = _cloud(n=500, deg=10, seed=3)
+    plan = SlabPlan(x, ei, world)
+    Lyr, H = 2, 64
+    nl = [p["n_own"] + p["halo"].size for p in plan.parts]
+    nm = max(nl)
+    cap = max(1, max(int(p["send_counts"].sum()) for p in plan.parts))
+    mk = lambda j: [((r + 1) << 40) + (j << 36) for r in range(world)]
+    base_q, base_x, base_rq, base_rx = mk(0), mk(1), mk(2), mk(3)
+    rng = np.random.default_rng(2)
+    gQ = [rng.standard_normal((nm, H)) for _ in range(world)]
+    gX = [rng.standard_normal((nm, 3)) for _ in range(world)]
+    for par in range(2):
+        RQ = [np.full((2, cap, H), np.nan) for _ in range(world)]
+        RX = [np.full((2, cap, 3), np.nan) for _ in range(world)]
+        tabs = [fused_halo_tables(plan, k, Lyr, nm, cap, base_q, base_x, base_rq, base_rx) for k in range(world)]
+        for k, p in enumerate(plan.parts):                                        # every user pushes its halo rows
+            _, _, bq, bx, _, _, _ = tabs[k]
+            for j in range(p["halo"].size):
+                o = int(bq[par][j] >> 40) - 1
+                off = int(bq[par][j]) - base_rq[o]
+                assert off % (4 * H) == 0 and o == plan.owner[p["halo"][j]]
+                slot = off // (4 * H)
+                assert par * cap <= slot < (par + 1) * cap
+                assert int(bx[par][j]) - base_rx[o] == slot * 12
+                assert np.isnan(RQ[o].reshape(-1, H)[slot]).all()                  # no two rows share a slot
+                RQ[o].reshape(-1, H)[slot] = gQ[k][p["n_own"] + j]
+                RX[o].reshape(-1, 3)[slot] = gX[k][p["n_own"] + j]
+        accQ, accX = np.zeros((x.shape[0], H)), np.zeros((x.shape[0], 3))
+        for k, p in enumerate(plan.parts):
+            np.add.at(accQ, p["halo"], gQ[k][p["n_own"]:nl[k]])
+            np.add.at(accX, p["halo"], gX[k][p["n_own"]:nl[k]])
+        for k, p in enumerate(plan.parts):                                        # every owner applies its slots
+            _, _, _, _, rows, ptr, slots = tabs[k]
+            outQ, outX = gQ[k].copy(), gX[k].copy()
+            assert ptr[0] == 0 and ptr[-1] == slots.size == int(p["send_counts"].sum())
+            for i, rrow in enumerate(rows):
+                sl = slots[ptr[i]:ptr[i + 1]]
+                assert np.all(np.diff(sl) > 0)                                     # (user rank, halo order): fixed order
+                for s_ in sl:
+                    outQ[rrow] += RQ[k][par, s_]
+                    outX[rrow] += RX[k][par, s_]
+            np.testing.assert_allclose(outQ[:p["n_own"]], gQ[k][:p["n_own"]] + accQ[p["owned"]], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(outX[:p["n_own"]], gX[k][:p["n_own"]] + accX[p["owned"]], rtol=0, atol=1e-12)
