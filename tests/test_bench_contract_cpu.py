@@ -27,7 +27,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and abs(d["value"] - d["cpu_baseline"]["value"]) < 1e-6 * d["value"]
 
 
-@pytest.mark.parametrize("name,nodes", [("water3d", 700), ("water3d_b20", 300), ("nbody100", 0), ("protein", 0), ("large", 3000)])
+@pytest.mark.parametrize("name,nodes", [("water3d", 700), ("water3d_b20", 300), ("nbody5", 0), ("nbody100", 0), ("protein", 0), ("large", 3000)])
 def test_workloads_have_reference_shaped_batches(name, nodes):
     """What utils/train.py:32-53 hands to the model: int64 edge_index without self loops, non-decreasing int64 batch whose
     last entry is B-1, loc_mean [B,3,C], edge_attr [E,2] = (length, length) (datasets + utils/train.py:41-43)."""
