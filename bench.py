@@ -1026,6 +1026,8 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     except Exception as exc:
         probes = dict(error=f"{type(exc).__name__}: {exc}"[:300])
     bwd_mode = L.get_mode("edge_backward")
+    if bwd_mode == 6:              # auto (fegnn.h): the fp16 two-stream kernel from 32 tiles per SM on
+        bwd_mode = 5 if (E + 127) // 128 >= 32 * torch.cuda.get_device_properties(dev).multi_processor_count else 4
     flop = 6 * 2 * H * H * E       # recompute 2 + dgrad 2 + wgrad 2 GEMMs of [E,64]x[64,64]; bias-sum GEMM columns not counted
     t_s = out["edge_bwd"] * 1e-3
     ach = flop / t_s / 1e12

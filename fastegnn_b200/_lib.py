@@ -166,7 +166,7 @@ def set_precision(name: str) -> None:
     "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual and node phases).
     "tf32_all": "tf32" plus the tcgen05 node_pre forward (h rounded to TF32: fastest, but equivariance only to ~3e-4 on
     equivariant_test.py's inputs)."""
-    table = {"fp32": (0, 0, 0, 0, 0), "tf32": (1, 4, 1, 1, 0), "tf32x3": (3, 4, 0, 1, 0), "tf32_all": (1, 4, 1, 1, 1)}
+    table = {"fp32": (0, 0, 0, 0, 0), "tf32": (1, 6, 1, 1, 0), "tf32x3": (3, 6, 0, 1, 0), "tf32_all": (1, 6, 1, 1, 1)}
     for phase, mode in zip(PHASES, table[name]):
         set_mode(phase, mode)
 

@@ -3,6 +3,7 @@
 // Single translation unit: the kernel files are included below.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -55,8 +56,11 @@ int fail(int code, const char* fmt, ...) {
 // 0 = fp32 FMA kernels, 1 = tcgen05 single-pass TF32, 3 = tcgen05 3xTF32 (fp32-grade)
 int g_edge_fwd_mode = 1;
 // 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands
-// and MN-major weight-gradient operands (256 / 512 threads per tile)
-int g_edge_bwd_mode = 4;
+// and MN-major weight-gradient operands (256 / 512 threads per tile), 5 = tcgen05 kind::f16 with two tile streams per CTA,
+// 6 = auto (default): 5 when there are enough 128-edge tiles to fill both streams of every SM many times over (the fp16
+// kernel runs 1.29x faster at 3.6 M edges but carries a bound pre-pass and twice the tile quantisation: slower at 1.8e5), else 4
+int g_edge_bwd_mode = 6;
+constexpr int kAutoTilesPerSm = 32;
 
 // 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
 int g_virt_fwd_mode = 1;
@@ -113,6 +117,8 @@ EdgeArgs edge_args(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_
   a.row = g->row; a.col = g->col; a.ea = g->edge_attr; a.x = x; a.P = sv->P; a.Q = sv->Q;
   a.w1 = p->edge_w0; a.W2 = p->edge_w2; a.b2 = p->edge_b2; a.W3 = p->cr_w0; a.b3 = p->cr_b0; a.w4 = p->cr_w2;
   a.wa = p->att_w; a.ba = p->att_b;
+  static const unsigned exp_bits = getenv("FEGNN_EXP") ? (unsigned)atoi(getenv("FEGNN_EXP")) : 0u;
+  a.exp = exp_bits;
   return a;
 }
 
@@ -200,8 +206,8 @@ int fegnn_set_mode(const char* phase, int mode) {
     return 0;
   }
   if (strcmp(phase, "edge_backward") == 0) {
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 5)
-      return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2, 4 or 5");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 5 && mode != 6)
+      return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2, 4, 5 or 6 (auto)");
     g_edge_bwd_mode = mode;
     return 0;
   }
@@ -447,11 +453,13 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
   CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
-  if (g_edge_bwd_mode == 5 && tc_ok && sv->scratch != nullptr)
+  int mode = g_edge_bwd_mode;
+  if (mode == 6) mode = ((d->E + kTM - 1) / kTM >= kAutoTilesPerSm * sm_count() && sv->scratch != nullptr) ? 5 : 4;
+  if (mode == 5 && tc_ok && sv->scratch != nullptr)
     CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
-  else if (g_edge_bwd_mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
-  else if (g_edge_bwd_mode == 4 && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
-  else if (g_edge_bwd_mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
+  else if (mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
+  else if ((mode == 4 || mode == 5) && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
+  else if (mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
   else CK(launch_edge_bwd(a, sm_count(), S(stream)));
   return 0;
 }

@@ -13,6 +13,7 @@ namespace fegnn {
 struct EdgeArgs {
   int N, Nl, E, Fe, ld1;
   unsigned flags;
+  unsigned exp;      // timing experiments only (env FEGNN_EXP; 0 in production): 1 no gQ scatter, 2 no gP / gx tail, 4 no P / Q gathers
   float eps;
   const int *row, *col;
   const float *ea, *x, *P, *Q;

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
           ri[j] = v->srow[rr];
           p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ri[j] >= 0) {
+          if (ri[j] >= 0 && !(a.exp & 4u)) {
             p[j] = *reinterpret_cast<const float4*>(a.P + (size_t)ri[j] * kH + 4 * l16);
             qv[j] = *reinterpret_cast<const float4*>(a.Q + (size_t)v->scol[rr] * kH + 4 * l16);
           }
@@ -492,12 +492,12 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
             gq = fmaf(g1v[j + 1], v->wq[c0 + j + 1], gq);
           }
         }
-#ifndef FEGNN_EXP_NO_GQ
+        if (!(a.exp & 1u)) {
 #pragma unroll
-        for (int ch = 0; ch < CPT / 4; ++ch)
-          atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
-                    make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
-#endif
+          for (int ch = 0; ch < CPT / 4; ++ch)
+            atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
+                      make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) g1v[j] = 0.f;
@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(128 * CG, 1) edge_bwd_tc2_kernel(EdgeArgs a) {
     first_tile = false;
     // ---- gP: row-segment sums of gz1 over TM ; gx: both ends of every edge.  Thread (c4, grp) owns the 16-byte column
     //      quad c4 of RPG4 consecutive rows: one LDS.128 per row, one red.global.add.v4.f32 per run of equal row ids.
+    if (a.exp & 2u) continue;
     {
       constexpr int GR4 = NT / 16, RPG4 = kTM / GR4;    // 32 groups x 4 rows (512 threads) / 16 groups x 8 rows (256)
       const int c4 = t & 15, grp = t >> 4;

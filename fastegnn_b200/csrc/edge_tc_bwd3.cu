@@ -162,10 +162,16 @@ __global__ void __launch_bounds__(256) edge_bwd_stats_kernel(int N, int Nl, cons
     mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  if ((threadIdx.x & 31) == 0) {             // non-negative floats order like their bit patterns
-    atomicMax(stats + 0, __float_as_uint(mt));
-    atomicMax(stats + 1, __float_as_uint(mm));
-    atomicMax(stats + 2, __float_as_uint(mx));
+  // one atomic per block and statistic (3 000 same-address atomics from every warp cost 11 us at 8 000 nodes)
+  __shared__ float red[3][8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = mt; red[1][w] = mm; red[2][w] = mx; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, red[threadIdx.x][i]);
+    atomicMax(stats + threadIdx.x, __float_as_uint(m));      // non-negative floats order like their bit patterns
   }
 }
 __device__ __forceinline__ float pow2_scale(float bound) {      // largest power of two s with bound * s <= 2^15
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
           ri[j] = v->srow[rr];
           p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ri[j] >= 0) {
+          if (ri[j] >= 0 && !(a.exp & 4u)) {
             p[j] = *reinterpret_cast<const float4*>(a.P + (size_t)ri[j] * kH + 4 * l16);
             qv[j] = *reinterpret_cast<const float4*>(a.Q + (size_t)v->scol[rr] * kH + 4 * l16);
           }
@@ -523,10 +529,12 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
           gq = fmaf(g1v[j], sv->wq[c0 + j], gq);
           gq = fmaf(g1v[j + 1], sv->wq[c0 + j + 1], gq);
         }
+        if (!(a.exp & 1u)) {
 #pragma unroll
-        for (int ch = 0; ch < kCPT / 4; ++ch)
-          atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
-                    make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
+          for (int ch = 0; ch < kCPT / 4; ++ch)
+            atomicAdd(reinterpret_cast<float4*>(a.gQ + (size_t)c * kH + c0 + ch * 4),
+                      make_float4(g1v[ch * 4], g1v[ch * 4 + 1], g1v[ch * 4 + 2], g1v[ch * 4 + 3]));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < kCPT; ++j) g1v[j] = 0.f;
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
     phase ^= 1;
     first_tile = false;
     // ---- gP: row-segment sums of gz1 over the fp16 tile: thread (c8, grp) owns the 16-byte chunk c8 of 4 consecutive rows
+    if (a.exp & 2u) continue;
     {
       const int c8 = tg & 7, grp = tg >> 3;      // 8 chunks x 32 groups of 4 rows
       int cur = -1;
@@ -621,18 +630,22 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
     const bool mine = (lane < 16) ? has0 : has1;
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
     float w[kCPT];
+    auto flush_rows = [&](float* base, const float (&w)[kCPT], float r) {
+      if (!mine || base == nullptr) return;
+      float* dst = base + (size_t)n * kH + c0;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < kCPT; j += 4)      // red.global.add.v4.f32
+          atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j] * r, w[j + 1] * r, w[j + 2] * r, w[j + 3] * r));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kCPT; ++j) atomicAdd(dst + j, w[j] * r);
+      }
+    };
     tmem_ld<kCPT>(tl + kR3 + c0, w);
-    if (mine && a.g_W3 != nullptr) {
-      float* dst = a.g_W3 + (size_t)n * kH + c0;
-#pragma unroll
-      for (int j = 0; j < kCPT; ++j) atomicAdd(dst + j, w[j] * r3);
-    }
+    flush_rows(a.g_W3, w, r3);
     tmem_ld<kCPT>(tl + kR2 + c0, w);
-    if (mine && a.g_W2 != nullptr) {
-      float* dst = a.g_W2 + (size_t)n * kH + c0;
-#pragma unroll
-      for (int j = 0; j < kCPT; ++j) atomicAdd(dst + j, w[j] * r2);
-    }
+    flush_rows(a.g_W2, w, r2);
     if (cg == 0) {
       float x3[16], x2[16], xz[16];
       tmem_ld<16>(tl + kR3 + 64, x3);          // only columns 64..71 were written; the rest of the x16 read is ignored
@@ -673,8 +686,8 @@ inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int s
   const int grid = pairs < sms ? pairs : sms;
   cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  int sblocks = (int)(((size_t)a.N * kH + 256 * 16 - 1) / (256 * 16));
-  sblocks = sblocks < 1 ? 1 : (sblocks > 4 * sms ? 4 * sms : sblocks);
+  int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
+  sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);
   bwd3::edge_bwd_stats_kernel<<<sblocks, 256, 0, st>>>(a.N, a.Nl, a.x, a.gt, a.gm, stats); ++g_launches;
   bwd3::edge_bwd_tc3_kernel<<<grid, bwd3::kThreads3, bytes, st>>>(a, stats); ++g_launches;
   return cudaGetLastError();

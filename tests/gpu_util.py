@@ -17,16 +17,27 @@ import contextlib
 #   tf32x3  fused edge forward on error-compensated 3xTF32 tiles (fp32-grade outputs), backward on TF32 tiles
 #   tf32    (default) edge + virtual phases on single-pass TF32 tiles (10-bit mantissa operands, fp32 accumulation,
 #           tanh.approx SiLU), forward and backward
+#   .gb     the first-Linear BIAS gradients of the two virtual coordinate heads (coord_mlp_r_virtual.0.bias,
+#           coord_mlp_v_virtual.0.bias): column sums of signed terms over all N*C (node, channel) rows that cancel almost
+#           completely (|sum| << sqrt(rows) * rms), taken by a TF32 MMA against a ones column in the tensor-core modes, so
+#           operand rounding shows up amplified by that cancellation.  Stated apart instead of loosening every tensor.
 class Tol(tuple):
-    """(out, gin) for `tol_out, tol_grad = ...` unpacking, with .out / .gin / .gw (weight gradients) fields."""
-    def __new__(cls, out, gin, gw):
+    """(out, gin) for `tol_out, tol_grad = ...` unpacking, with .out / .gin / .gw (weight gradients) / .gb fields."""
+    def __new__(cls, out, gin, gw, gb=None):
         t = super().__new__(cls, (out, gin))
-        t.out, t.gin, t.gw = out, gin, gw
+        t.out, t.gin, t.gw, t.gb = out, gin, gw, (gw if gb is None else gb)
         return t
 
+    def for_param(self, name):
+        return self.gb if (name.endswith("coord_mlp_r_virtual.0.bias") or name.endswith("coord_mlp_v_virtual.0.bias")) else self.gw
 
-TOLERANCES = {"fp32": Tol(2e-6, 4e-6, 8e-5), "tf32x3": Tol(1e-5, 5e-3, 2.5e-2), "tf32": Tol(8e-3, 5e-3, 2.5e-2),
-              "tf32_all": Tol(8e-3, 5e-3, 2.5e-2)}
+
+# Worst observed (all seeded cases + BASELINE configs 2 / 4 / 5-at-1/16 at full size, profiles/parity_report_r2.txt):
+#   fp32   out ~0 (inside the 4-ulp term)  gin 8.3e-7  gw 3.9e-5  gb 8.1e-6
+#   tf32x3 out 1.3e-6                      gin 2.5e-3  gw 5.9e-3  gb 5.5e-2
+#   tf32   out 4.5e-3                      gin 2.4e-3  gw 1.1e-2  gb 5.5e-2
+TOLERANCES = {"fp32": Tol(2e-6, 2e-6, 8e-5), "tf32x3": Tol(4e-6, 5e-3, 1.2e-2, 1.2e-1), "tf32": Tol(8e-3, 5e-3, 2.5e-2, 1.2e-1),
+              "tf32_all": Tol(8e-3, 5e-3, 2.5e-2, 1.2e-1)}
 EPS32 = 2.0 ** -23
 
 
@@ -113,8 +124,8 @@ def rel_err(a, ref):
 def update_err(got, want64, base):
     """Error of an output judged on the update: (max |got - want|  -  4 ulp of max |want|) / max |want - base|."""
     got, want64, base = got.double(), want64.double(), base.double()
-    upd = float((want64 - base).abs().max())
-    diff = float((got - want64).abs().max())
+    upd = float((want64 - base).detach().abs().max())
+    diff = float((got - want64).detach().abs().max())
     return max(0.0, diff - 4 * EPS32 * float(want64.abs().max())) / (upd + 1e-30)
 
 
@@ -156,6 +167,6 @@ def compare_with_oracles(cfg, params, inp, res, tol, tol_grad=None, label=""):
         if res["gp"][k] is None:
             bad.append(k + " (missing grad)")
             continue
-        if not chk("gp." + k, res["gp"][k], g64, r32["gp"][k], tol.gw):
+        if not chk("gp." + k, res["gp"][k], g64, r32["gp"][k], tol.for_param(k)):
             bad.append(k)
     return bad, report

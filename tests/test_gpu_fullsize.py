@@ -34,7 +34,7 @@ def _workload(name):
 
 def _oracle(cfg, params, data, wx, wz, dtype):
     p = {k: v.to(dtype).requires_grad_(True) for k, v in params.items()}
-    f = lambda k: data[k].to(dtype)
+    f = lambda k: data[k].detach().clone().to(dtype)
     x0, lm = f("loc_0").requires_grad_(True), f("loc_mean").requires_grad_(True)
     x, Z = orc.fastegnn_forward(p, cfg, f("node_feat"), x0, f("vel_0"), data["edge_index"], data["batch"], lm,
                                 f("edge_attr"))
@@ -78,20 +78,25 @@ def test_benchmarked_configs_against_oracle(name, gain):
         ex = update_err(x.detach().cpu(), ref["x"], data["loc_0"])
         ez = update_err(Z.detach().cpu(), ref["Z"], data["loc_mean"])
         egx, egl = rel_err(x0.grad.cpu(), ref["gx0"]), rel_err(lm.grad.cpu(), ref["glm"])
-        worst_w, worst_k = 0.0, ""
+        worst_w, worst_k, worst_b, over = 0.0, "", 0.0, []
         for k, p in m.named_parameters():
             if ref["gp"][k] is None:
                 assert p.grad is None, k
                 continue
             e = rel_err(p.grad.cpu(), ref["gp"][k])
-            if e > worst_w:
+            if tol.for_param(k) != tol.gw:               # the two cancellation-dominated head biases (tests/gpu_util.py)
+                worst_b = max(worst_b, e)
+            elif e > worst_w:
                 worst_w, worst_k = e, k
+            if e > tol.for_param(k) + 10 * slack:
+                over.append((k, e))
         lines.append(f"{name} gain={gain:g} [{prec}] N={N} E={data['edge_index'].size(1)} C={C} oracle={odt}: "
                      f"x'-x {ex:.2e}  Z'-Z {ez:.2e}  g_x0 {egx:.2e}  g_loc_mean {egl:.2e}  "
-                     f"weight grads {worst_w:.2e} ({worst_k})   stated {tol.out:g} / {tol.gin:g} / {tol.gw:g}")
+                     f"weight grads {worst_w:.2e} ({worst_k})  virtual-head biases {worst_b:.2e}   "
+                     f"stated {tol.out:g} / {tol.gin:g} / {tol.gw:g} / {tol.gb:g}")
         os.makedirs("gpurun_out", exist_ok=True)
         with open("gpurun_out/parity_fullsize.txt", "a") as f:
             f.write(lines[-1] + "\n")
         assert ex < tol.out + slack and ez < tol.out + slack, lines[-1]
         assert egx < tol.gin + 10 * slack and egl < tol.gin + 10 * slack, lines[-1]
-        assert worst_w < tol.gw + 10 * slack, lines[-1]
+        assert not over, (over, lines[-1])
