@@ -764,7 +764,7 @@ def partition_parity(world, rank, dev, halo, n=3000, C=8):
     loss.backward()
     runner.allreduce_gradients()
     torch.cuda.synchronize()
-    rel = lambda a, b: float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+    rel = lambda a, b: float((a.detach().double() - b.detach().double()).abs().max() / (b.detach().double().abs().max() + 1e-30))
     errs = [rel(xo, xr.detach()[rows[:Nn]]), rel(Zo, Zr.detach()), rel(xl.grad[:Nn], ref_gx0[rows[:Nn]])]
     errs += [rel(p.grad, ref[k]) for k, p in model.named_parameters() if ref[k] is not None]
     e = torch.tensor([max(errs)], device=dev, dtype=torch.float64)
@@ -839,6 +839,8 @@ def partitioned_block(args, world, rank, dev, flush, steps=5, warmup=3):
                 v = torch.tensor([s.elapsed_time(e) / 50 * 1e3], device=dev, dtype=torch.float64)
                 dist.all_reduce(v, op=dist.ReduceOp.MAX)
                 res[name] = round(float(v[0]), 2)
+            res["per_step_us"] = round(2 * LAYERS * res["halo_push_signal_us"] + (2 * LAYERS + 2) * res["p2p_allreduce_us"], 1)
+            res["limiting"] = "halo_push_signal (payload over NVLink + all-rank signal / wait)"
             res["what"] = ("one forward halo exchange of layer 0 (payload stores + signal + wait in ONE kernel) and one "
                            "one-shot all-reduce of 539 floats, 50 back-to-back calls each, max over ranks; a step has "
                            f"{2 * LAYERS} halo exchanges and {2 * LAYERS + 2} small all-reduces + one NCCL all-reduce of the "
