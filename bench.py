@@ -354,7 +354,7 @@ class StepBench:
         self.train_step = train_step
         # ---- the whole step (graph prep, 4-layer fwd, losses, bwd, collectives, Adam) as ONE CUDA graph:
         #      the C ABI never allocates or synchronises, so every launch of a step is capturable.
-        self.g, self.loss, self.why, self.per_step = None, None, None, None
+        self.g, self.loss, self.why, self.per_step, self.pipe = None, None, None, None, None
         if use_cuda_graph:
             try:
                 side = torch.cuda.Stream()
@@ -379,6 +379,17 @@ class StepBench:
             self.g.replay()
             return self.loss
         return self.train_step(self.dev_in, self.idx_dev)
+
+    def e2e_pipelined(self):
+        """End to end through fastegnn_b200.PipelinedStep: the pinned-host inputs of step k+1 travel on a copy stream
+        while step k computes (double-buffered device inputs, two captured graphs); the loss is read back every step."""
+        if self.pipe is None:
+            from fastegnn_b200 import PipelinedStep
+            host = dict(self.host, idx=self.idx_host)
+            self.pipe = PipelinedStep(lambda t: self.train_step(t, t["idx"]), host, self.dev)
+            self.pipe_host = host
+            self.pipe.prefetch(host)
+        return self.pipe.run(self.pipe_host).item()
 
     def e2e(self):
         if self.g is not None:
@@ -563,12 +574,24 @@ def main():
     ms = timed(sb.resident, args.steps, flush)
     barrier()
     launches = sb.launches(args.steps, _lib.lib.fegnn_launch_count() - launches0)
-    ms_e2e = timed(sb.e2e, args.steps, flush)
+    ms_e2e_serial = timed(sb.e2e, args.steps, flush)
+    barrier()
+    pipelined = not part and not args.no_graph
+    if pipelined:
+        for _ in range(args.warmup):
+            sb.e2e_pipelined()
+        barrier()
+        ms_e2e = timed(sb.e2e_pipelined, args.steps, flush)
+        if sb.pipe.graphs[0] is None:
+            pipelined = False
+    else:
+        ms_e2e = ms_e2e_serial
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, ms_e2e_serial], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e_serial = float(tt[2])
         ee = torch.tensor([E], device=dev, dtype=torch.float64)
         dist.all_reduce(ee)
         ms, ms_e2e, E_all = float(tt[0]), float(tt[1]), float(ee[0])    # partitioned: E is this rank's share of the edges
@@ -584,7 +607,15 @@ def main():
                     vs_baseline=None, dtype=DTYPE_DEFAULT if _lib.get_mode("edge_forward") else "f32 (fp32 FMA kernels)",
                     data="synthetic", config=config, clocks=clocks,
                     e2e=dict(value=E_all * LAYERS / (ms_e2e * 1e-3), unit="edges/s", ms_per_step=ms_e2e,
-                             h2d_bytes_per_step=sb.h2d_bytes(), d2h_bytes_per_step=4),
+                             h2d_bytes_per_step=sb.h2d_bytes(), d2h_bytes_per_step=4,
+                             ms_per_step_serial_copy=ms_e2e_serial,
+                             how=("fastegnn_b200.PipelinedStep: every step copies its batch from pinned host memory and reads "
+                                  "the loss back; the copy of step k+1's inputs runs on a copy stream while step k computes "
+                                  "(double-buffered device inputs, one captured graph per set) -- all copies lie inside the "
+                                  "timed region; ms_per_step_serial_copy is the same with the copy in front of the step on "
+                                  "the compute stream") if pipelined else
+                                 "pinned host -> device copy of every input on the compute stream, then the step, then the "
+                                 "loss read-back"),
                     gpu_launches=int(launches), cuda_graph=sb.g is not None,
                     modes={ph: _lib.get_mode(ph) for ph in _lib.PHASES})
         if part:
@@ -644,7 +675,7 @@ def single_gpu_extras(line, args, sb, data, hp, dev, flush, E, N, B, C, cores):
         finally:
             for ph, m in old.items():
                 _lib.set_mode(ph, m)
-    if args.rollout and has_edges:
+    if has_edges:
         try:
             line["rollout"] = rollout_profile(sb.model, sb.dev_in, dev, E, flush)
         except Exception as exc:
@@ -881,8 +912,41 @@ def partitioned_block(args, world, rank, dev, flush, steps=5, warmup=3):
     return out
 
 
-def rollout_profile(model, t, dev, E, flush):
-    raise NotImplementedError("rollout mode is built in a later commit")
+def rollout_profile(model, t, dev, E, flush, steps=20):
+    """SURVEY.md 8 f4 (utils/train.py:24-27,191-192: evaluation epochs, backprop=False): the forward-only stack
+    (fegnn_model_forward_inference: two ping-pong states + one shared block, nothing saved) as ONE CUDA graph, next to the
+    training forward of the same batch (what model.eval() ran before the forward-only stack existed)."""
+    kw = dict(node_feat=t["node_feat"], node_loc=t["loc_0"], node_vel=t["vel_0"], edge_index=t["edge_index"],
+              data_batch=t["batch"], loc_mean=t["loc_mean"], edge_attr=t["edge_attr"])
+    out = {}
+    was_training = model.training
+    try:
+        for name, keep in (("forward_only", False), ("training_forward", True)):
+            model.eval()
+            model.eval_keeps_graph = keep
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    model(**kw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats(dev)
+            base = torch.cuda.memory_allocated(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y = model(**kw)
+            for _ in range(3):
+                g.replay()
+            ms = timed(g.replay, steps, flush)
+            out[name] = dict(ms=round(ms, 4), layer_edges_per_s=E * LAYERS / (ms * 1e-3),
+                             graph_pool_mb=round((torch.cuda.max_memory_allocated(dev) - base) / 2 ** 20, 1))
+            del g, y
+    finally:
+        model.eval_keeps_graph = False
+        model.train(was_training)
+    out["what"] = "one captured 4-layer forward of the benchmark batch incl. graph prep, L2 flushed; graph_pool_mb = peak memory of the capture"
+    return out
 
 
 def graph_build_profile(data, t, dev, B, flush):

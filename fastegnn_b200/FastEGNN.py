@@ -159,8 +159,35 @@ class _StackFn(torch.autograd.Function):
         return (None, None, g_nf, g_x0, None, g_lm) + grads
 
 
+def _stack_inference(mod: "FastEGNN", graph: CsrGraph, node_feat, x0, v, loc_mean):
+    """FastEGNN.forward without autograd: fegnn_model_forward_inference (two ping-pong states + one shared block of
+    per-layer intermediates; nothing is kept for a backward)."""
+    dev = x0.device
+    N, B, Cc, Lyr = graph.N, graph.B, mod.virtual_channels, mod.n_layers
+    dims = make_dims(N, N, graph.E, B, Cc, graph.Fe, mod._flag_word, mod._gravity)
+    pd = C.byref(dims)
+    table, _ = mod._param_table()
+    ws_floats = int(lib.fegnn_model_inference_workspace_floats(pd))
+    ws = torch.empty(ws_floats, device=dev, dtype=torch.float32)
+    x_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
+    Z_out = torch.empty(B, 3, Cc, device=dev, dtype=torch.float32)
+    with _on(dev):
+        L.check(lib.fegnn_model_forward_inference(pd, Lyr, node_feat.size(1), C.byref(graph.c), table,
+                                                  L.ptr(mod.embedding_in.weight), L.ptr(mod.embedding_in.bias),
+                                                  L.ptr(mod.virtual_node_feat), L.ptr(node_feat), L.ptr(x0), L.ptr(v),
+                                                  L.ptr(loc_mean), L.ptr(x_out), L.ptr(Z_out), L.ptr(ws), ws_floats,
+                                                  _stream(dev)), "fegnn_model_forward_inference")
+    return x_out, Z_out
+
+
 class FastEGNN(nn.Module):
-    """Drop-in for the reference FastEGNN (:226-276)."""
+    """Drop-in for the reference FastEGNN (:226-276).
+
+    eval_keeps_graph (attribute, default False): the reference's evaluation epochs (utils/train.py:24-27,191-192) run the
+    model under model.eval() WITHOUT torch.no_grad(), building an autograd graph nobody uses.  Here a forward in eval mode
+    -- or under torch.no_grad() -- takes the forward-only stack (fegnn_model_forward_inference): same outputs, no saved
+    activations, outputs without grad_fn.  Set eval_keeps_graph = True to get the training forward in eval mode."""
+    eval_keeps_graph = False
 
     def __init__(self, node_feat_nf, node_attr_nf, edge_attr_nf, hidden_nf, virtual_channels, device='cpu',
                  act_fn=nn.SiLU(), n_layers=4, residual=True, attention=False, normalize=False, tanh=False,
@@ -249,9 +276,7 @@ class FastEGNN(nn.Module):
             if graph.Fe != self._edge_attr_nf or graph.N != node_loc.size(0) or graph.B != loc_mean.size(0):
                 raise RuntimeError(f"prebuilt graph (N={graph.N}, B={graph.B}, Fe={graph.Fe}) does not match the inputs "
                                    f"(N={node_loc.size(0)}, B={loc_mean.size(0)}, edge_attr_nf={self._edge_attr_nf})")
-            params = [p for _, p in self.named_parameters()]
-            return _StackFn.apply(self, graph, node_feat.contiguous().float(), node_loc.contiguous().float(),
-                                  node_vel.contiguous().float(), loc_mean.contiguous().float(), *params)
+            return self._run_stack(graph, node_feat, node_loc, node_vel, loc_mean)
         if edge_attr is None:
             if self._edge_attr_nf != 0:
                 raise TypeError("edge_attr is required when edge_attr_nf > 0 (the reference's torch.cat fails on None, "
@@ -261,9 +286,15 @@ class FastEGNN(nn.Module):
                                f"{self._edge_attr_nf}")
         B = int(loc_mean.size(0))
         graph = CsrGraph(edge_index, data_batch, edge_attr, B)
+        return self._run_stack(graph, node_feat, node_loc, node_vel, loc_mean)
+
+    def _run_stack(self, graph, node_feat, node_loc, node_vel, loc_mean):
+        args = (node_feat.contiguous().float(), node_loc.contiguous().float(), node_vel.contiguous().float(),
+                loc_mean.contiguous().float())
+        if not torch.is_grad_enabled() or (not self.training and not self.eval_keeps_graph):
+            return _stack_inference(self, graph, *[a.detach() for a in args])
         params = [p for _, p in self.named_parameters()]
-        return _StackFn.apply(self, graph, node_feat.contiguous().float(), node_loc.contiguous().float(),
-                              node_vel.contiguous().float(), loc_mean.contiguous().float(), *params)
+        return _StackFn.apply(self, graph, *args, *params)
 
 
 def unsorted_segment_sum(data, segment_ids, num_segments):

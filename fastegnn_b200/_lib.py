@@ -137,6 +137,8 @@ SIGNATURES = {
     "fegnn_model_workspace_floats": (C.c_size_t, [_PD, i32]),
     "fegnn_model_backward_scratch_floats": (C.c_size_t, [_PD]),
     "fegnn_model_forward": (C.c_int, [_PD, i32, i32, _PG, _PP] + [vp] * 9 + [vp, C.c_size_t, vp]),
+    "fegnn_model_inference_workspace_floats": (C.c_size_t, [_PD]),
+    "fegnn_model_forward_inference": (C.c_int, [_PD, i32, i32, _PG, _PP] + [vp] * 9 + [vp, C.c_size_t, vp]),
     "fegnn_model_backward": (C.c_int, [_PD, i32, i32, _PG, _PP, _PP] + [vp] * 11 + [vp, vp, C.c_size_t, vp]),
     "fegnn_peak_probe": (C.c_int, [i32, i32, vp, C.POINTER(C.c_double), vp]),
     "fegnn_segment_reduce": (C.c_int, [C.c_int64, i32, i32, vp, vp, i32, vp, vp, vp]),

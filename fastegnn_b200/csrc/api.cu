@@ -738,6 +738,81 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   return 0;
 }
 
+// ------------------------------------------------------------------ forward-only stack (rollout / evaluation)
+// utils/train.py:24-27,191-192: validation and test run the model with backprop=False.  Nothing is kept for a backward:
+// the layers ping-pong between two state sets and share ONE block of per-layer intermediates, so the workspace is
+// 2 states + 1 block instead of (L + 1) states + L blocks (3.4 GB instead of 13.4 GB at 1 M nodes, C = 8, L = 4).
+size_t fegnn_model_inference_workspace_floats(const fegnn_dims* d) {
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  const size_t per_state = al4(N * kH) + al4(Nl * 3) + al4(B * 3 * C) + al4(B * C * kH) + al4(B * 3);
+  return 3 * per_state + fegnn_layer_saved_floats(d);      // two ping-pong states + the (h, S) of the embedding (FastRF)
+}
+
+int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                                  const fegnn_layer_params* layers, const float* embed_w, const float* embed_b,
+                                  const float* vnf, const float* node_feat, const float* x0, const float* v,
+                                  const float* loc_mean, float* x_out, float* Z_out, float* workspace,
+                                  size_t workspace_floats, void* stream) {
+  TRY(check_dims(d));
+  RQ(L >= 1 && L <= 32 && g && layers && embed_w && embed_b && vnf && workspace && x_out && Z_out);
+  RQ(d->Nl == d->N);
+  if (workspace_floats < fegnn_model_inference_workspace_floats(d))
+    return fail(FEGNN_ENOMEM, "inference workspace %zu < %zu floats", workspace_floats, fegnn_model_inference_workspace_floats(d));
+  cudaStream_t st = S(stream);
+  const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
+  float* p = workspace;
+  auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  float *h[3], *x[3], *Z[3], *Sx[3], *xsum[3];
+  for (int i = 0; i < 3; ++i) {
+    h[i] = take(N * kH); x[i] = take(Nl * 3); Z[i] = take(B * 3 * C); Sx[i] = take(B * C * kH); xsum[i] = take(B * 3);
+  }
+  fegnn_layer_saved sv_;
+  fegnn_layer_saved_bind(d, p, &sv_);
+  fegnn_layer_saved* sv = &sv_;
+  // slot 2 keeps the embedding state (h0, S0): FastRF reads it in every layer; slots 0 / 1 ping-pong
+  TRY(fegnn_embed_forward(d->N, Fin, node_feat, embed_w, embed_b, h[2], stream));
+  CK(cudaMemcpyAsync(x[2], x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(Z[2], loc_mean, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
+  if (B > 0) {
+    broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, Sx[2]); ++g_launches;
+    CK(cudaGetLastError());
+  }
+  TRY(fegnn_graph_xsum(d->N, d->B, x[2], g->batch, xsum[2], stream));
+  SideStream* sd = side_stream();
+  RQ(sd != nullptr);
+  void* side = sd->st;
+  FORK(sd, st);
+  const bool rf = d->flags & FEGNN_F_RF;
+  int cur = 2;                                    // state entering the layer
+  for (int l = 0; l < L; ++l) {
+    fegnn_dims dl = *d;
+    const bool last = rf || l == L - 1;
+    if (last) dl.flags |= FEGNN_F_LAST;
+    const fegnn_layer_params* pl = &layers[l];
+    const int nxt = cur == 2 ? 0 : (cur ^ 1);
+    const int hs = rf ? 2 : cur;                  // layer whose (h, S) this layer reads
+    TRY(fegnn_graph_pre_forward(&dl, g, pl, Z[cur], Sx[hs], xsum[cur], sv, side));
+    TRY(fegnn_node_pre_forward(&dl, pl, h[hs], sv, stream));
+    if (rf) TRY(fegnn_rf_vel_forward(d->N, v, pl, sv->sv, stream));
+    TRY(fegnn_edge_forward(&dl, g, pl, x[cur], sv, stream));
+    JOIN(sd, st);
+    TRY(fegnn_virtual_forward(&dl, g, pl, x[cur], v, Z[cur], sv, x[nxt], xsum[nxt], stream));
+    FORK(sd, st);
+    if (!last) TRY(fegnn_node_h_forward(&dl, g, pl, h[cur], sv, h[nxt], stream));
+    TRY(fegnn_graph_post_forward(&dl, g, pl, Z[cur], Sx[hs], sv, Z[nxt], Sx[nxt], side));
+    // the shared block is rewritten by the next layer: its per-graph kernels (side) must not start before this layer's
+    // node_h (main) has read u / msum, and its main-stream kernels not before this layer's graph_post (side) has read
+    // Dsum / Usum
+    JOIN(sd, st);
+    FORK(sd, st);
+    cur = nxt;
+  }
+  JOIN(sd, st);
+  CK(cudaMemcpyAsync(x_out, x[cur], sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(Z_out, Z[cur], sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
                          const fegnn_layer_params* layers, fegnn_layer_grads* grads, const float* embed_w,
                          float* g_embed_w, float* g_embed_b, float* g_vnf, const float* node_feat, const float* v,

@@ -314,6 +314,15 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
                         const float* node_feat /*[N,Fin]*/, const float* x0 /*[N,3]*/, const float* v /*[N,3]*/,
                         const float* loc_mean /*[B,3,C]*/, float* x_out /*[N,3]*/, float* Z_out /*[B,3,C]*/,
                         float* workspace, size_t workspace_floats, void* stream);
+/* Forward-only stack for evaluation / rollout (utils/train.py:24-27,191-192: backprop=False): same arguments and results
+ * as fegnn_model_forward, but nothing is kept for a backward -- the layers ping-pong between two state sets and share ONE
+ * block of per-layer intermediates (workspace = 3 states + 1 block instead of (L + 1) states + L blocks). */
+size_t fegnn_model_inference_workspace_floats(const fegnn_dims* d);
+int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
+                                  const fegnn_layer_params* layers_host, const float* embed_w, const float* embed_b,
+                                  const float* virtual_node_feat, const float* node_feat, const float* x0, const float* v,
+                                  const float* loc_mean, float* x_out, float* Z_out, float* workspace,
+                                  size_t workspace_floats, void* stream);
 int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
                          const fegnn_layer_params* layers_host, fegnn_layer_grads* grads_host /*[L]*/,
                          const float* embed_w, float* g_embed_w, float* g_embed_b, float* g_virtual_node_feat,

@@ -429,11 +429,31 @@ def test_eval_forward_without_autograd_matches_training_forward():
         with precision(prec):
             m.train()
             x_tr, Z_tr = m(**kw)
+            assert x_tr.grad_fn is not None
             m.eval()
             with torch.no_grad():
                 x_ev, Z_ev = m(**kw)
+            x_e2, Z_e2 = m(**kw)                 # the reference's evaluation epochs do NOT disable grad (utils/train.py:24-27)
+            m.eval_keeps_graph = True
+            x_e3, _ = m(**kw)
+            m.eval_keeps_graph = False
         assert not x_ev.requires_grad and not Z_ev.requires_grad
-        assert rel_err(x_ev.cpu(), x_tr.detach().cpu()) < tol and rel_err(Z_ev.cpu(), Z_tr.detach().cpu()) < tol, prec
+        assert x_e2.grad_fn is None and Z_e2.grad_fn is None          # eval mode: forward-only stack, no saved activations
+        assert x_e3.grad_fn is not None                                # opt-out: the training forward in eval mode
+        for xe, Ze in ((x_ev, Z_ev), (x_e2, Z_e2)):
+            assert rel_err(xe.cpu(), x_tr.detach().cpu()) < tol and rel_err(Ze.cpu(), Z_tr.detach().cpu()) < tol, prec
+
+
+def test_forward_only_stack_needs_a_fraction_of_the_training_workspace():
+    """fegnn_model_inference_workspace_floats: 3 states + ONE block of per-layer intermediates, against (L + 1) states + L
+    blocks for the training forward -- and the FastRF sibling takes the same path (every layer reads the embedding state)."""
+    import ctypes as Ct
+    from fastegnn_b200 import _lib as L_
+    from fastegnn_b200.ops import make_dims
+    d = make_dims(1_000_000, 1_000_000, 30_000_000, 1, 8, 2, 0, None)
+    train = int(L_.lib.fegnn_model_workspace_floats(Ct.byref(d), 4))
+    infer = int(L_.lib.fegnn_model_inference_workspace_floats(Ct.byref(d)))
+    assert infer * 3 < train, (infer, train)
 
 
 def test_full_size_water3d_properties():
