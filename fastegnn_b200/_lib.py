@@ -16,7 +16,7 @@ H = 64
 MAX_C = 16
 MAX_FE = 8
 
-F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF, F_COORDS_SUM = 1, 2, 4, 8, 16, 32, 64
+F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF, F_COORDS_SUM, F_NODE_SUM = 1, 2, 4, 8, 16, 32, 64, 128
 
 fp = C.POINTER(C.c_float)
 ip = C.POINTER(C.c_int32)
@@ -155,11 +155,11 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 def set_mode(phase: str, mode: int) -> None:
-    """0 = fp32 FMA kernels, 1 = tcgen05 TF32, 3 = tcgen05 3xTF32 (see fegnn_set_mode in fegnn.h)."""
+    """0 = fp32 FMA kernels, 1 = tcgen05 TF32, 3 = tcgen05 3xTF32, ... (see fegnn_set_mode in fegnn.h)."""
     check(lib.fegnn_set_mode(phase.encode(), int(mode)), "fegnn_set_mode")
 
 
-PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward", "node_forward")
+PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward", "node_forward", "node_backward")
 
 
 def set_precision(name: str) -> None:
@@ -168,7 +168,7 @@ def set_precision(name: str) -> None:
     "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual and node phases).
     "tf32_all": "tf32" plus the tcgen05 node_pre forward (h rounded to TF32: fastest, but equivariance only to ~3e-4 on
     equivariant_test.py's inputs)."""
-    table = {"fp32": (0, 0, 0, 0, 0), "tf32": (1, 6, 1, 1, 0), "tf32x3": (3, 6, 0, 1, 0), "tf32_all": (1, 6, 1, 1, 1)}
+    table = {"fp32": (0, 0, 0, 0, 0, 0), "tf32": (1, 6, 1, 1, 0, 2), "tf32x3": (3, 6, 0, 1, 0, 2), "tf32_all": (1, 6, 1, 1, 1, 2)}
     for phase, mode in zip(PHASES, table[name]):
         set_mode(phase, mode)
 

@@ -22,6 +22,7 @@
 #include "virtual_kernels.cu"
 #include "virtual_tc.cu"
 #include "node_tc.cu"
+#include "dense_tc.cu"
 #include "segment.cu"
 #include "peak_probe.cu"
 
@@ -70,6 +71,13 @@ int g_virt_bwd_mode = 1;
 // TF32 turns fp32-level noise between a rotated and an unrotated run into 2^-11 |h| jumps in P / Q / Av / Uh -- measured
 // 2.2e-4 on equivariant_test.py's U(0,10) inputs against its atol of 1e-4.
 int g_node_fwd_mode = 0;
+// per-node dense phases of the BACKWARD pass (node_pre_backward, node_h_backward): 0 = fp32 FMA kernels, 1 = tcgen05 TF32
+// (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default): tcgen05 from kNodeTcMinN nodes on.
+// Below that the phase is a latency chain of 1-2 tiles per CTA and the fp32 kernels (more, smaller work items) are as
+// fast or faster: measured at 8 000 nodes 54 + 46 us (fp32) against 63 + 49 us (tcgen05) per layer.
+int g_node_bwd_mode = 2;
+constexpr int kNodeTcMinN = 32768;
+inline bool node_bwd_tc(int N) { return g_node_bwd_mode == 1 || (g_node_bwd_mode == 2 && N >= kNodeTcMinN); }
 
 int sm_count() {
   static int sms[64] = {};                  // per device ordinal (a process may drive several GPUs)
@@ -211,9 +219,11 @@ int fegnn_set_mode(const char* phase, int mode) {
     g_edge_bwd_mode = mode;
     return 0;
   }
-  if (strcmp(phase, "node_forward") == 0) {
-    if (mode != 0 && mode != 1) return fail(FEGNN_EINVAL, "%s mode must be 0 or 1", phase);
-    g_node_fwd_mode = mode;
+  if (strcmp(phase, "node_forward") == 0 || strcmp(phase, "node_backward") == 0) {
+    const bool fwd = phase[5] == 'f';
+    if (mode != 0 && mode != 1 && !(mode == 2 && !fwd))
+      return fail(FEGNN_EINVAL, "%s mode must be 0 or 1%s", phase, fwd ? "" : " or 2 (auto)");
+    (fwd ? g_node_fwd_mode : g_node_bwd_mode) = mode;
     return 0;
   }
   if (strcmp(phase, "virtual_forward") == 0 || strcmp(phase, "virtual_backward") == 0) {
@@ -227,6 +237,7 @@ int fegnn_get_mode(const char* phase) {
   if (phase != nullptr && strcmp(phase, "edge_forward") == 0) return g_edge_fwd_mode;
   if (phase != nullptr && strcmp(phase, "edge_backward") == 0) return g_edge_bwd_mode;
   if (phase != nullptr && strcmp(phase, "node_forward") == 0) return g_node_fwd_mode;
+  if (phase != nullptr && strcmp(phase, "node_backward") == 0) return g_node_bwd_mode;
   if (phase != nullptr && strcmp(phase, "virtual_forward") == 0) return g_virt_fwd_mode;
   if (phase != nullptr && strcmp(phase, "virtual_backward") == 0) return g_virt_bwd_mode;
   return -1;
@@ -363,7 +374,8 @@ int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_
   NodeHArgs a;
   memset(&a, 0, sizeof(a));
   a.N = d->N; a.C = d->C; a.ldn = ldn(d);
-  a.h = h; a.Uh = sv->Uh; a.msum = sv->msum; a.dinv = g->dinv; a.u = sv->u;
+  a.h = h; a.Uh = sv->Uh; a.msum = sv->msum; a.u = sv->u;
+  a.dinv = (d->flags & FEGNN_F_NODE_SUM) ? nullptr : g->dinv;     // VNEGNN's A2A stage sums the messages (models/VNEGNN.py:87)
   a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
   a.zh1 = sv->zh1; a.h_new = h_new;
   CK(launch_node_h_fwd(a, sm_count(), S(stream)));
@@ -404,10 +416,39 @@ int fegnn_node_h_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
   NodeHArgs a;
   memset(&a, 0, sizeof(a));
   a.N = d->N; a.C = d->C; a.ldn = ldn(d);
-  a.msum = sv->msum; a.dinv = g->dinv; a.u = sv->u; a.zh1 = sv->zh1;
+  a.msum = sv->msum; a.u = sv->u; a.zh1 = sv->zh1;
+  a.dinv = (d->flags & FEGNN_F_NODE_SUM) ? nullptr : g->dinv;
   a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
   a.gh_new = gh_new; a.gzh1 = gzh1; a.gm = gm; a.gu = gu;
   a.g_node_w0 = gr->node_w0; a.g_node_w2 = gr->node_w2; a.g_node_b2 = gr->node_b2;
+  if (node_bwd_tc(d->N)) {
+    // tcgen05: (1) gzh1 = (gh' U2) * silu'(zh1), dU2 += gh'^T silu(zh1), de2 += sum gh' ; (2) per K-block of the first
+    // Linear: gm = (gzh1 U1a) / deg, gu_c = gzh1 U1u_c, dU1 blocks += gzh1^T [msum / deg | u_c]
+    dtc::Args t1;
+    memset(&t1, 0, sizeof(t1));
+    t1.N = d->N; t1.nblk = 1;
+    dtc::Blk& b = t1.blk[0];
+    b.X = gh_new; b.ldx = kH; b.Y = sv->zh1; b.ldy = kH; b.ysilu = 1; b.W = p->node_w2; b.ldw = kH; b.wks = 1;
+    b.D = gzh1; b.ldd = kH; b.dmode = 1; b.dz = sv->zh1; b.gW = gr->node_w2; b.gb = gr->node_b2;
+    CK(launch_dense_bwd_tc(t1, sm_count(), S(stream)));
+    dtc::Args t2;
+    memset(&t2, 0, sizeof(t2));
+    t2.N = d->N; t2.nblk = d->C + 1;
+    for (int k = 0; k <= d->C; ++k) {
+      dtc::Blk& q = t2.blk[k];
+      q.X = gzh1; q.ldx = kH; q.ldw = a.ldn; q.dmode = 1;
+      if (k == 0) {
+        q.Y = sv->msum; q.ldy = kH; q.yscale = a.dinv; q.W = p->node_w0 + kH; q.wks = 1;
+        q.D = gm; q.ldd = kH; q.dscale = a.dinv; q.gW = gr->node_w0 ? gr->node_w0 + kH : nullptr;
+      } else {
+        const int c = k - 1;
+        q.Y = sv->u + (size_t)c * kH; q.ldy = d->C * kH; q.W = p->node_w0 + 2 * kH + c; q.wks = d->C;
+        q.D = gu + (size_t)c * kH; q.ldd = d->C * kH; q.gW = gr->node_w0 ? gr->node_w0 + 2 * kH + c : nullptr;
+      }
+    }
+    CK(launch_dense_bwd_tc(t2, sm_count(), S(stream)));
+    return 0;
+  }
   CK(launch_node_h_bwd(a, sm_count(), S(stream)));
   return 0;
 }
@@ -489,6 +530,33 @@ int fegnn_node_pre_backward(const fegnn_dims* d, const fegnn_layer_params* p, fe
   a.g_node_w0 = gr->node_w0; a.g_node_b0 = gr->node_b0;
   a.g_vel_w0 = gr->vel_w0; a.g_vel_b0 = gr->vel_b0; a.g_vel_w2 = gr->vel_w2; a.g_vel_b2 = gr->vel_b2;
   a.g_grav_w0 = gr->grav_w0; a.g_grav_b0 = gr->grav_b0; a.g_grav_w2 = gr->grav_w2; a.g_grav_b2 = gr->grav_b2;
+  if (node_bwd_tc(d->N)) {
+    // tcgen05: gh += G_blk W_blk (red.add), dW_blk += G_blk^T h, db_blk += sum G_blk for P, Q, Av [, Uh] and the phi_v
+    // [/ phi_g] heads (whose G is recomputed on the tensor core from h)
+    dtc::Args t;
+    memset(&t, 0, sizeof(t));
+    t.N = d->N;
+    auto plain = [&](const float* G, const float* W, int ldw, float* gW, float* gb) {
+      dtc::Blk& q = t.blk[t.nblk++];
+      q.X = G; q.ldx = kH; q.Y = h; q.ldy = kH; q.W = W; q.ldw = ldw; q.wks = 1;
+      q.D = gh; q.ldd = kH; q.dmode = 2; q.gW = gW; q.gb = gb;
+    };
+    auto head = [&](const float* gs, const float* W, const float* hb, const float* hw2, float* gW, float* gb, float* gw2,
+                    float* gb2) {
+      dtc::Blk& q = t.blk[t.nblk++];
+      q.head = 1; q.Y = h; q.ldy = kH; q.W = W; q.ldw = kH; q.wks = 1; q.gs = gs; q.hb = hb; q.hw2 = hw2;
+      q.D = gh; q.ldd = kH; q.dmode = 2; q.gW = gW; q.gb = gb; q.g_hw2 = gw2; q.g_hb2 = gb2;
+    };
+    plain(gP, p->edge_w0, a.ld1, gr->edge_w0, gr->edge_b0);
+    plain(gQ, p->edge_w0 + kH, a.ld1, gr->edge_w0 ? gr->edge_w0 + kH : nullptr, nullptr);
+    plain(gAv, p->edgev_w0, a.ldv, gr->edgev_w0, gr->edgev_b0);
+    if (gUh != nullptr) plain(gUh, p->node_w0, a.ldn, gr->node_w0, gr->node_b0);
+    if (!(d->flags & FEGNN_F_RF)) head(gsv, p->vel_w0, p->vel_b0, p->vel_w2, gr->vel_w0, gr->vel_b0, gr->vel_w2, gr->vel_b2);
+    if (d->flags & FEGNN_F_GRAVITY)
+      head(gsg, p->grav_w0, p->grav_b0, p->grav_w2, gr->grav_w0, gr->grav_b0, gr->grav_w2, gr->grav_b2);
+    CK(launch_dense_bwd_tc(t, sm_count(), S(stream)));
+    return 0;
+  }
   CK(launch_node_pre_bwd(a, sm_count(), S(stream)));
   return 0;
 }

@@ -1,0 +1,310 @@
+// dense_tc.cu -- the per-node dense phases of the BACKWARD pass on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// node_pre_backward (models/FastEGNN.py:104,115,139,142,162, h-side halves of every first Linear) and node_h_backward
+// (phi_h, :153-166) are sums of [128 x 64] x [64 x 64] products per node tile and weight block:
+//     D_b   = X_b W_b                      data gradient   (gh += gP Ws, gm = gzh1 U1a, gu_c = gzh1 U1u_c, gzh1 = gh' U2 ...)
+//     dW_b += X_b^T Y_b ,  db_b += sum X_b  weight gradient (Y_b = h, msum / deg, u_c, silu(zh1))
+// They were fp32-FMA kernels (19 TFLOP/s at Water-3D: 8.6 % + 7.5 % of the step's kernel time, 24 % at 1 M nodes).  Here ONE
+// generic kernel runs any list of such blocks: work item = (node tile, block); the row owner thread (one TMEM lane) loads
+// its X and Y rows from global memory straight into registers, writes X to tensor memory (the TS-form A operand of the data
+// gradient, as in edge_tc_bwd2.cu) and both rows to row-major SWIZZLE_128B_BASE32B tiles, which the weight-gradient GEMM
+// reads as MN-major operands (no transposed copies); dW accumulates in tensor memory across the CTA's tiles.  Backward-only:
+// TF32 rounding of gradients does not touch the forward equivariance.
+// Head blocks (phi_v / phi_g, :139,:142) first recompute z = h W^T on the tensor core and form X = gs w2 silu'(z + b).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace fegnn {
+namespace dtc {
+
+using bwd2::desc_advance;
+using bwd2::gemm_ts_kmajor;
+using bwd2::gemm_ts_mn;
+using bwd2::idesc_tf32;
+using bwd2::make_desc_mn;
+using bwd2::mn_chunk_off;
+using bwd2::mn_off;
+using bwd2::mn_store_row;
+using bwd2::tmem_ld;
+using bwd2::tmem_st;
+using bwd2::tmem_st_wait;
+
+constexpr int kMaxBlk = FEGNN_MAX_C + 2;
+
+struct Blk {
+  // X rows [N][64] (row stride ldx floats), optional per-row scale: the gradient-side operand
+  const float* X;
+  const float* xscale;
+  // Y rows [N][64] (row stride ldy), optional per-row scale, ysilu: Y = silu(rows)
+  const float* Y;
+  const float* yscale;
+  // weight block: element (n, k) = W[n * ldw + k * wks]   (n = output feature of the forward Linear, k = input feature)
+  const float* W;
+  // D = X W (rows [N][64], stride ldd): dmode 0 none, 1 store, 2 red.add ; optional D *= silu'(dz row) ; D *= dscale[row]
+  float* D;
+  const float* dz;
+  const float* dscale;
+  float* gW;     // += X^T Y   (same ldw / wks addressing)
+  float* gb;     // += column sums of X (or nullptr)
+  // head block (phi_v / phi_g): X = gs[row] * hw2 * silu'(Y W^T + hb) ; g_hw2 += sum gs silu(z) ; g_hb2 += sum gs
+  const float *gs, *hb, *hw2;
+  float *g_hw2, *g_hb2;
+  int ldx, ldy, ldd, ldw, wks, dmode, ysilu, head;
+};
+
+struct Args {
+  int N, nblk;
+  Blk blk[kMaxBlk];
+};
+
+struct Vec {
+  float hb[kH], hw2[kH];
+  float cb[kH], cw2[kH];          // per-CTA column sums (bias gradient, head output-weight gradient)
+  float cb2;
+  uint64_t bar[3];
+  uint32_t tmem_slot;
+};
+struct Smem {
+  static constexpr int kW = kH * kH * 4, kT = kTM * kH * 4;
+  static constexpr int off_Wm = 0, off_Wk = kW, off_TY = 2 * kW, off_TX = 2 * kW + kT, off_vec = 2 * kW + 2 * kT;
+  static constexpr size_t bytes = off_vec + sizeof(Vec) + 1024;
+};
+constexpr uint32_t kACC = 0, kOPA = 64, kRW = 128;      // tensor-memory columns (256 allocated: two CTAs per SM)
+
+template <int CG>
+__global__ void __launch_bounds__(128 * CG, 2) dense_bwd_tc_kernel(const __grid_constant__ Args a) {
+  constexpr int NT = 128 * CG, CPT = kH / CG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  Vec* v = reinterpret_cast<Vec*>(smem + Smem::off_vec);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
+  const int bid = blockIdx.x % a.nblk, cta = blockIdx.x / a.nblk, nctas = gridDim.x / a.nblk;
+  const Blk& b = a.blk[bid];
+  uint8_t *Wm = smem + Smem::off_Wm, *Wk = smem + Smem::off_Wk, *TY = smem + Smem::off_TY, *TX = smem + Smem::off_TX;
+
+  // ---- prologue: weight block in both layouts (MN-major for X W; K-major only for the head recompute), vectors
+  for (int i = t; i < kH * kH; i += NT) {
+    const int n = i >> 6, k = i & 63;
+    const float w = b.W[(size_t)n * b.ldw + (size_t)k * b.wks];
+    *reinterpret_cast<float*>(Wm + mn_off(n, k, kH)) = w;
+    if (b.head) *reinterpret_cast<float*>(Wk + umma::tile_off(n, k, kH)) = w;
+  }
+  for (int i = t; i < kH; i += NT) {
+    v->hb[i] = b.head ? b.hb[i] : 0.f;
+    v->hw2[i] = b.head ? b.hw2[i] : 0.f;
+    v->cb[i] = 0.f;
+    v->cw2[i] = 0.f;
+  }
+  if (t == 0) {
+    v->cb2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) umma::mbar_init(&v->bar[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<256>(&v->tmem_slot);
+  umma::fence_smem_to_async();
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem = v->tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
+  const uint32_t id_ts_k = idesc_tf32(128, 64, 0, 0), id_ts_mn = idesc_tf32(128, 64, 0, 1), id_wg = idesc_tf32(64, 64, 1, 1);
+  const uint64_t dWm = make_desc_mn(umma::smem_u32(Wm), kH * 128), dWk = umma::make_desc(umma::smem_u32(Wk));
+  const uint64_t dTX = make_desc_mn(umma::smem_u32(TX), kTM * 128), dTY = make_desc_mn(umma::smem_u32(TY), kTM * 128);
+  uint32_t ph_r = 0, ph_d = 0, ph_w = 0;
+  bool first = true;
+  const bool want_w = b.gW != nullptr;
+
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  for (int tile = cta; tile < ntiles; tile += nctas) {
+    const int i0 = tile * kTM, r = i0 + row;
+    const bool valid = r < a.N;
+    if (!first && want_w) {                       // the previous tile's weight-gradient GEMM still reads TX / TY
+      umma::mbar_wait(&v->bar[2], ph_w);
+      umma::fence_after();
+      ph_w ^= 1;
+    }
+    // ---- Y row -> registers -> TY (and tensor memory for the head recompute)
+    float y[CPT], x[CPT];
+    if (valid) {
+      const float4* src = reinterpret_cast<const float4*>(b.Y + (size_t)r * b.ldy + c0);
+      const float s = b.yscale != nullptr ? b.yscale[r] : 1.f;
+#pragma unroll
+      for (int ch = 0; ch < CPT / 4; ++ch) {
+        const float4 q = src[ch];
+        y[ch * 4] = q.x * s; y[ch * 4 + 1] = q.y * s; y[ch * 4 + 2] = q.z * s; y[ch * 4 + 3] = q.w * s;
+      }
+      if (b.ysilu) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) y[j] = silu_f(y[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) y[j] = 0.f;
+    }
+    mn_store_row<CPT>(TY, row, cg, y);
+    if (b.head) {
+      tmem_st<CPT>(tlane + kOPA, y);
+      tmem_st_wait();
+      umma::fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        umma::fence_after();
+        if (umma::elect_one()) {
+          gemm_ts_kmajor(tmem + kACC, tmem + kOPA, dWk, id_ts_k);           // z = Y W^T
+          umma::commit(&v->bar[0]);
+        }
+        __syncwarp();
+      }
+      umma::mbar_wait(&v->bar[0], ph_r);
+      umma::fence_after();
+      ph_r ^= 1;
+      tmem_ld<CPT>(tlane + kACC, x);
+      const float g = valid ? b.gs[r] : 0.f;
+      float aw[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        float av, d;
+        silu_grad_f(x[j] + v->hb[c0 + j], av, d);
+        aw[j] = g * av;
+        x[j] = g * v->hw2[c0 + j] * d;
+      }
+      // g_hw2 += sum_rows gs * silu(z): warp-reduce over the 32 rows of this warp, one shared-memory atomic per column
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        float s = aw[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(&v->cw2[c0 + j], s);
+      }
+      if (cg == 0) {
+        float s = g;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(&v->cb2, s);
+      }
+    } else if (valid) {
+      const float4* src = reinterpret_cast<const float4*>(b.X + (size_t)r * b.ldx + c0);
+      const float s = b.xscale != nullptr ? b.xscale[r] : 1.f;
+#pragma unroll
+      for (int ch = 0; ch < CPT / 4; ++ch) {
+        const float4 q = src[ch];
+        x[ch * 4] = q.x * s; x[ch * 4 + 1] = q.y * s; x[ch * 4 + 2] = q.z * s; x[ch * 4 + 3] = q.w * s;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) x[j] = 0.f;
+    }
+    if (b.gb != nullptr) {                         // bias gradient: column sums of X in fp32 (not through the TF32 MMA)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        float s = x[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(&v->cb[c0 + j], s);
+      }
+    }
+    tmem_st<CPT>(tlane + kOPA, x);
+    mn_store_row<CPT>(TX, row, cg, x);
+    tmem_st_wait();
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      umma::fence_after();
+      if (umma::elect_one()) {
+        if (b.dmode != 0) {
+          gemm_ts_mn(tmem + kACC, tmem + kOPA, dWm, id_ts_mn);               // D = X W
+          umma::commit(&v->bar[1]);
+        }
+        if (want_w) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)                                     // dW (+)= X^T Y over the 128 rows
+            umma::mma_tf32(tmem + kRW, desc_advance(dTX, ks * 1024), desc_advance(dTY, ks * 1024), id_wg,
+                           (ks > 0 || !first) ? 1u : 0u);
+          umma::commit(&v->bar[2]);
+        }
+      }
+      __syncwarp();
+    }
+    if (b.dmode != 0) {
+      umma::mbar_wait(&v->bar[1], ph_d);
+      umma::fence_after();
+      ph_d ^= 1;
+      float d[CPT];
+      tmem_ld<CPT>(tlane + kACC, d);
+      if (valid) {
+        if (b.dz != nullptr) {
+          const float4* zr = reinterpret_cast<const float4*>(b.dz + (size_t)r * kH + c0);
+#pragma unroll
+          for (int ch = 0; ch < CPT / 4; ++ch) {
+            const float4 z = zr[ch];
+            float av, e0, e1, e2, e3;
+            silu_grad_f(z.x, av, e0); silu_grad_f(z.y, av, e1); silu_grad_f(z.z, av, e2); silu_grad_f(z.w, av, e3);
+            d[ch * 4] *= e0; d[ch * 4 + 1] *= e1; d[ch * 4 + 2] *= e2; d[ch * 4 + 3] *= e3;
+          }
+        }
+        const float s = b.dscale != nullptr ? b.dscale[r] : 1.f;
+        float4* dst = reinterpret_cast<float4*>(b.D + (size_t)r * b.ldd + c0);
+#pragma unroll
+        for (int ch = 0; ch < CPT / 4; ++ch) {
+          const float4 q = make_float4(d[ch * 4] * s, d[ch * 4 + 1] * s, d[ch * 4 + 2] * s, d[ch * 4 + 3] * s);
+          if (b.dmode == 2) atomicAdd(dst + ch, q);
+          else dst[ch] = q;
+        }
+      }
+      umma::fence_before();                        // ACC / OPA are rewritten by the next tile
+    }
+    first = false;
+  }
+  // ---- flush: weight gradient (M = 64 layout: row n in lane (n / 16) * 32 + n % 16), bias sums
+  if (!first && want_w) {
+    umma::mbar_wait(&v->bar[2], ph_w);
+    umma::fence_after();
+  }
+  __syncthreads();
+  if (!first && want_w) {
+    float w[CPT];
+    tmem_ld<CPT>(tlane + kRW, w);
+    if (lane < 16) {
+      const int n = quarter * 16 + lane;
+      float* dst = b.gW + (size_t)n * b.ldw + (size_t)c0 * b.wks;
+      if (b.wks == 1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; j += 4) atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) atomicAdd(dst + (size_t)j * b.wks, w[j]);
+      }
+    }
+  }
+  if (!first && t < kH) {
+    if (b.gb != nullptr) atomicAdd(b.gb + t, v->cb[t]);
+    if (b.head && b.g_hw2 != nullptr) atomicAdd(b.g_hw2 + t, v->cw2[t]);
+    if (b.head && t == 0 && b.g_hb2 != nullptr) atomicAdd(b.g_hb2, v->cb2);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace dtc
+
+cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
+  static DevOnce attr;
+  if (!attr.get()) {
+    cudaError_t e = cudaFuncSetAttribute(dtc::dense_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dtc::Smem::bytes);
+    if (e != cudaSuccess) return e;
+    attr.set();
+  }
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if (ntiles == 0 || a.nblk == 0) return cudaSuccess;
+  int per = (2 * sms) / a.nblk;                   // CTAs per block at 2 CTAs / SM
+  per = per < 1 ? 1 : (per > ntiles ? ntiles : per);
+  dtc::dense_bwd_tc_kernel<2><<<per * a.nblk, 256, dtc::Smem::bytes, st>>>(a); ++g_launches;
+  return cudaGetLastError();
+}
+
+}  // namespace fegnn

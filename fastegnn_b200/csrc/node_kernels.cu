@@ -290,7 +290,7 @@ __device__ __forceinline__ void load_tile_rowscaled(float* __restrict__ T, const
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nvalid) {
       v = *reinterpret_cast<const float4*>(g + (size_t)r * ld + c4 * 4);
-      float s = rowscale[r];
+      float s = rowscale != nullptr ? rowscale[r] : 1.f;       // nullptr: plain sums (FEGNN_F_NODE_SUM)
       v.x *= s; v.y *= s; v.z *= s; v.w *= s;
     }
     *reinterpret_cast<float4*>(T + r * kH + c4 * 4) = v;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_z_kernel(NodeHArgs a) {
   for (int tile = cta; tile < ntiles; tile += nctas) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
-    if (blk == 0) load_tile_rowscaled(T0, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
+    if (blk == 0) load_tile_rowscaled(T0, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv != nullptr ? a.dinv + i0 : nullptr);
     else load_tile(T0, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
     __syncthreads();
     float acc[kRT][4];
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_bwd2_kernel(NodeHArgs a) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
     load_tile(T0, a.gzh1 + (size_t)i0 * kH, kH, nvalid);
-    if (blk == 0) load_tile_rowscaled(T1, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv + i0);
+    if (blk == 0) load_tile_rowscaled(T1, a.msum + (size_t)i0 * kH, kH, nvalid, a.dinv != nullptr ? a.dinv + i0 : nullptr);
     else load_tile(T1, a.u + ((size_t)i0 * a.C + (blk - 1)) * kH, (size_t)a.C * kH, nvalid);
     __syncthreads();
     float acc[kRT][4];
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_bwd2_kernel(NodeHArgs a) {
       const int r = ty * kRT + i;
       if (r < nvalid) {
         if (blk == 0) {
-          const float sc = a.dinv[i0 + r];
+          const float sc = a.dinv != nullptr ? a.dinv[i0 + r] : 1.f;
           *reinterpret_cast<float4*>(a.gm + (size_t)(i0 + r) * kH + tx * 4) =
               make_float4(acc[i][0] * sc, acc[i][1] * sc, acc[i][2] * sc, acc[i][3] * sc);
         } else {

@@ -113,48 +113,54 @@ class LayerPhases:
         return gh_new, gx, gZ, gS, gxsum
 
 
-_PARAM_ORDER = None
-
-
 def _layer_named(layer):
     return [(n, p) for n, p in layer.named_parameters()]
 
 
 class _LayerFn(torch.autograd.Function):
+    """One layer through the phase calls, as a function of NAMED WEIGHT TENSORS (reference state_dict suffixes, any
+    autograd history): E_GCL_vel.forward passes a layer's parameters; the VNEGNN sibling passes tensors it assembles from
+    its own parameters (fastegnn_b200/VNEGNN.py).  spec = (names, flag word, gravity list or None, virtual channels)."""
+
     @staticmethod
-    def forward(ctx, layer, graph, h, x, v, Z, S, *params):
+    def forward(ctx, spec, graph, h, x, v, Z, S, *params):
+        names, flags, grav, Cc = spec
         dev = x.device
-        named = {n: p for (n, _), p in zip(_layer_named(layer), params)}
+        named = dict(zip(names, params))
         ptrs = layer_ptrs(named, "")
-        flags = (L.F_ATTENTION if layer.attention else 0) | (L.F_NORMALIZE if layer.normalize else 0) | \
-                (L.F_TANH if layer.tanh else 0) | (L.F_GRAVITY if layer.gravity is not None else 0) | \
-                (L.F_COORDS_SUM if layer.coords_agg == 'sum' else 0)
-        grav = None if layer.gravity is None else [float(t) for t in layer.gravity.detach().cpu().tolist()]
-        dims = make_dims(graph.N, graph.N, graph.E, graph.B, layer.virtual_channels, graph.Fe, flags, grav)
+        dims = make_dims(graph.N, graph.N, graph.E, graph.B, Cc, graph.Fe, flags, grav)
         ph = LayerPhases(dims, graph, ptrs, dev)
         xsum = torch.empty(graph.B, 3, device=dev, dtype=torch.float32)
         with _on(dev):
             L.check(lib.fegnn_graph_xsum(graph.N, graph.B, L.ptr(x), L.ptr(graph.batch), L.ptr(xsum), _stream(dev)),
                     "graph_xsum")
         h_new, x_new, Z_new, S_new, _ = ph.forward(h, x, v, Z, S, xsum)
-        ctx.ph, ctx.layer = ph, layer
-        ctx.save_for_backward(h, x, v, Z, S)
-        ctx.names = [n for n, _ in _layer_named(layer)]
+        ctx.ph = ph
+        ctx.save_for_backward(h, x, v, Z, S, *params)
+        ctx.names = names
         return h_new, x_new, S_new, Z_new
 
     @staticmethod
     def backward(ctx, gh_new, gx_new, gS_new, gZ_new):
-        ph, layer = ctx.ph, ctx.layer
-        h, x, v, Z, S = ctx.saved_tensors
-        dev = x.device
+        ph = ctx.ph
+        h, x, v, Z, S = ctx.saved_tensors[:5]
+        params = ctx.saved_tensors[5:]
         z = lambda t, ref: torch.zeros_like(ref) if t is None else t.contiguous().float()
         gh_new = z(gh_new, h).clone()
         gx_new, gS_new, gZ_new = z(gx_new, x), z(gS_new, S), z(gZ_new, Z)
-        views = {n: torch.zeros_like(p) for n, p in _layer_named(layer)}
+        views = {n: torch.zeros_like(p) for n, p in zip(ctx.names, params)}
         gptrs = layer_ptrs(views, "")
         gh, gx, gZ, gS, gxsum = ph.backward(gptrs, h, x, v, Z, S, gh_new, gx_new, gZ_new, gS_new, None)
         gx = gx + gxsum[ph.g.batch.long()]       # xbar of this layer comes from its own input coordinates
         return (None, None, gh, gx, None, gZ, gS) + tuple(views[n] for n in ctx.names)
+
+
+def layer_call(named, flags: int, gravity, virtual_channels: int, graph: CsrGraph, h, x, v, Z, S):
+    """(h', x', S', Z') of one layer from a dict of weight tensors keyed by the reference's state_dict suffixes
+    (edge_mlp.0.weight, ...); S / S' in kernel layout [B,C,H].  Tensors must be contiguous fp32 CUDA."""
+    names = tuple(named.keys())
+    spec = (names, int(flags), gravity, int(virtual_channels))
+    return _LayerFn.apply(spec, graph, _f32(h), _f32(x), _f32(v), _f32(Z), _f32(S), *[named[n] for n in names])
 
 
 def layer_forward(layer, node_feat, edge_index, coord, node_vel, virtual_coord, virtual_node_feat, data_batch,
@@ -164,7 +170,11 @@ def layer_forward(layer, node_feat, edge_index, coord, node_vel, virtual_coord, 
     B = int(virtual_coord.size(0))
     graph = CsrGraph(edge_index, data_batch, edge_attr, B)
     S = virtual_node_feat.permute(0, 2, 1).contiguous()        # [B,H,C] -> [B,C,H]
-    params = [p for _, p in _layer_named(layer)]
-    h_new, x_new, S_new, Z_new = _LayerFn.apply(layer, graph, _f32(node_feat), _f32(coord), _f32(node_vel),
-                                                _f32(virtual_coord), S.float(), *params)
+    flags = (L.F_ATTENTION if layer.attention else 0) | (L.F_NORMALIZE if layer.normalize else 0) | \
+            (L.F_TANH if layer.tanh else 0) | (L.F_GRAVITY if layer.gravity is not None else 0) | \
+            (L.F_COORDS_SUM if layer.coords_agg == 'sum' else 0)
+    grav = None if layer.gravity is None else [float(t) for t in layer.gravity.detach().cpu().tolist()]
+    named = dict(_layer_named(layer))
+    h_new, x_new, S_new, Z_new = layer_call(named, flags, grav, layer.virtual_channels, graph, node_feat, coord, node_vel,
+                                            virtual_coord, S.float())
     return h_new, x_new, S_new.permute(0, 2, 1), Z_new

@@ -54,6 +54,9 @@ extern "C" {
                                  the edges of a row.  Understood by fegnn_virtual_forward / _backward (the phase that
                                  applies 1/deg to tsum); FastEGNN itself never sets it (:261).                          */
 
+#define FEGNN_F_NODE_SUM 128u  /* phi_h takes the SUM of a row's messages instead of their mean (the A2A stage of the VNEGNN
+                                 sibling, models/VNEGNN.py:85-96).  Understood by fegnn_node_h_forward / _backward.            */
+
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
   int32_t Nl;       /* rows of x / Q: owned + halo (== N on one GPU)                */
@@ -134,7 +137,8 @@ unsigned long long fegnn_launch_count(void);
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
  * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels (default), 1 = tcgen05
  * TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's atol 1e-4 on
- * its U(0,10) inputs).  Process-wide. */
+ * its U(0,10) inputs).  "node_backward": 0 = fp32 FMA kernels, 1 = tcgen05 TF32, 2 = auto (default: tcgen05 from 32 768 nodes on)
+ * for fegnn_node_pre_backward and fegnn_node_h_backward (gradients do not enter the forward equivariance).  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
 

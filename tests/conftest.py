@@ -14,8 +14,10 @@ def _ensure_library():
     """libfegnn.so is a build artefact (git-ignored): a fresh checkout has none.  Build it once (nvcc cross-compiles
     sm_100a without a GPU, ~40 s) so that importing fastegnn_b200 -- which has no fallback -- works in the tests."""
     lib = os.path.join(ROOT, "fastegnn_b200", "_C", "libfegnn.so")
-    if os.path.exists(lib):
-        return
+    src = os.path.join(ROOT, "fastegnn_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src))
+    if os.path.exists(lib) and os.path.getmtime(lib) >= newest:
+        return                          # up to date (a stale library silently tests yesterday's kernels)
     try:
         import __graft_entry__ as entry
         entry.build()

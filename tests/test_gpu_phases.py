@@ -65,7 +65,25 @@ def test_phases(name, layer):
         _lib.set_precision("tf32")
 
 
-def _phases(name, layer):
+NODE_BWD_TC_TOL = 4e-3      # tcgen05 TF32 tiles of node_pre_backward / node_h_backward (outputs and their weight gradients)
+
+
+@pytest.mark.parametrize("name", list(PHASE_CASES))
+@pytest.mark.parametrize("layer", [0, 1])
+def test_node_backward_tensor_core_mode(name, layer):
+    """fegnn_node_pre_backward / fegnn_node_h_backward on the tcgen05 TF32 kernel (dense_tc.cu, "node_backward" mode 1),
+    every other phase on the fp32 kernels: the same staged inputs, TF32-grade bound on the two phases' outputs and on
+    the weight gradients they produce (first-Linear blocks, phi_h, the phi_v / phi_g heads)."""
+    from fastegnn_b200 import _lib
+    _lib.set_precision("fp32")
+    _lib.set_mode("node_backward", 1)
+    try:
+        _phases(name, layer, tc_node_bwd=True)
+    finally:
+        _lib.set_precision("tf32")
+
+
+def _phases(name, layer, tc_node_bwd=False):
     s = _setup(name)
     L, lib = s["L"], s["L"].lib
     cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
@@ -210,6 +228,13 @@ def _phases(name, layer):
     with open(f"gpurun_out/phases_{name}_l{l}.txt", "w") as fh:
         for n_, e, t in errs:
             fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    if tc_node_bwd:
+        touched = ("node_h_bwd.", "node_pre_bwd.", "wgrad.")
+        errs = [(n_, e, NODE_BWD_TC_TOL if n_.startswith(touched) else t) for n_, e, t in errs]
+        with open(f"gpurun_out/node_bwd_tc_{name}_l{l}.txt", "w") as fh:
+            for n_, e, t in errs:
+                if n_.startswith(touched):
+                    fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
     bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
     assert not bad, bad
 
