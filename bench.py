@@ -982,6 +982,53 @@ def graph_build_profile(data, t, dev, B, flush):
     return out
 
 
+def edge_bwd_at_scale(model, dev, flush, peak_tf, probes, peaks, name="water3d_b20"):
+    """The same kernel on the reference's training batch (20 Water-3D graphs per step, main_simulation.py:46: 3.6e6 edges),
+    where a launch is 190 tiles per SM instead of 9.6: the tile rate without the per-launch fixed costs."""
+    import ctypes as Ct
+    from fastegnn_b200 import _lib as L
+    from fastegnn_b200.ops import CsrGraph, SavedBlock, layer_ptrs, make_dims
+    data, _ = make_workload(name, 0, 0)
+    t = {k: v.to(dev) for k, v in data.items() if torch.is_tensor(v)}
+    N, E, B, C = t["loc_0"].size(0), t["edge_index"].size(1), data["n_graphs"], data["C"]
+    graph = CsrGraph(t["edge_index"], t["batch"], t["edge_attr"], B)
+    dims = make_dims(N, N, E, B, C, 2, L.F_GRAVITY if data["gravity"] is not None else 0, data["gravity"])
+    named = dict(model.named_parameters())
+    ptrs = layer_ptrs(named, "gcl_0")
+    sv = SavedBlock(dims, dev)
+    sv.view("P", (N, H)).normal_()
+    sv.view("Q", (N, H)).normal_()
+    gv = {k: torch.zeros_like(p) for k, p in named.items() if k.startswith("gcl_0.")}
+    gr = layer_ptrs(gv, "gcl_0")
+    gm, gt = torch.randn(N, H, device=dev), torch.randn(N, 3, device=dev)
+    gP, gQ, gx = torch.empty(N, H, device=dev), torch.empty(N, H, device=dev), torch.zeros(N, 3, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    run = lambda: L.check(L.lib.fegnn_edge_backward(Ct.byref(dims), Ct.byref(graph.c), Ct.byref(ptrs), Ct.byref(gr), L.ptr(t["loc_0"]),
+                                                    Ct.byref(sv.c), L.ptr(gm), L.ptr(gt), L.ptr(gP), L.ptr(gQ), L.ptr(gx), st))
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(); run(); e_.record()
+        torch.cuda.synchronize()
+        ts.append(s_.elapsed_time(e_))
+    t_s = sum(ts) / len(ts) * 1e-3
+    flop = 6 * 2 * H * H * E
+    out = dict(workload=f"{name}: N={N} nodes, E={E} edges (random P / Q / upstream gradients)", us=round(t_s * 1e6, 1),
+               achieved=flop / t_s / 1e12, unit="TFLOP/s", frac=flop / t_s / 1e12 / peak_tf,
+               edges_per_s=E / t_s)
+    if "error" not in probes:
+        algo_bytes = E * (4 + 4 + 4 * 2 + 2 * 256 + 24 + 12 + 256 + 2 * 268)
+        t_model = max(flop / (probes["tcgen05_f16_tflops"] * 1e12), 3 * H * E / (probes["mufu_tanh_gops"] * 1e9),
+                      algo_bytes / (peaks.get("hbm_gbs", 6650.0) * 1e9))
+        out["frac_of_model"] = t_model / t_s
+    del sv, graph, t
+    torch.cuda.empty_cache()
+    return out
+
+
 def phase_profile(model, t, dev, data, E, N, B, C, flush):
     """CUDA-event time of every phase of layer 0 (one C-ABI call each), and the roofline of the
     dominant kernel (edge backward)."""
@@ -990,6 +1037,7 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     from fastegnn_b200.layer_fn import LayerPhases
     from fastegnn_b200.ops import CsrGraph, layer_ptrs, make_dims
     lib = L.lib
+    net = model
     st = torch.cuda.current_stream().cuda_stream
     graph = CsrGraph(t["edge_index"], t["batch"], t["edge_attr"], B)
     flags = L.F_GRAVITY if data["gravity"] is not None else 0
@@ -1050,7 +1098,7 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     npre_fn = dict(calls)["node_pre_fwd"]
     calls += [(f"node_pre_fwd[mode={m}]", with_mode("node_forward", m, npre_fn)) for m in (0, 1)]
     edge_bwd_fn = dict(calls)["edge_bwd"]
-    calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4, 5)]
+    calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4, 5, 7, 8)]
     for name, fn in calls:
         for _ in range(3):
             fn()
@@ -1092,8 +1140,8 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     except Exception as exc:
         probes = dict(error=f"{type(exc).__name__}: {exc}"[:300])
     bwd_mode = L.get_mode("edge_backward")
-    if bwd_mode == 6:              # auto (fegnn.h): the fp16 two-stream kernel from 32 tiles per SM on
-        bwd_mode = 5 if (E + 127) // 128 >= 32 * torch.cuda.get_device_properties(dev).multi_processor_count else 4
+    if bwd_mode == 6:              # auto (fegnn.h): the packed-fp16 two-stream kernel wherever the tensor-core form applies
+        bwd_mode = 7
     flop = 6 * 2 * H * H * E       # recompute 2 + dgrad 2 + wgrad 2 GEMMs of [E,64]x[64,64]; bias-sum GEMM columns not counted
     t_s = out["edge_bwd"] * 1e-3
     ach = flop / t_s / 1e12
@@ -1104,12 +1152,14 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     except Exception:
         pass
     algo_bytes = E * (4 + 4 + 4 * 2 + 2 * 256 + 24 + 12 + 256 + 2 * 268)    # no-reuse model, SURVEY.md 8(d): ~1.35 KB/edge
-    kname = {5: "bwd3::edge_bwd_tc3_kernel (tcgen05 kind::f16, two 128-edge tiles in flight per SM)",
+    kname = {7: "bwd4::edge_bwd_tc4_kernel<2> (tcgen05 kind::f16 operands, packed-fp16 epilogues, two 128-edge tiles in flight per SM)",
+             8: "bwd4::edge_bwd_tc4_kernel<4> (as <2> with 512 threads per tile)",
+             5: "bwd3::edge_bwd_tc3_kernel (tcgen05 kind::f16, two 128-edge tiles in flight per SM)",
              4: "bwd2::edge_bwd_tc2_kernel<4> (tcgen05 TF32)", 2: "bwd2::edge_bwd_tc2_kernel<2> (tcgen05 TF32)",
              1: "edge_bwd_tc_kernel (tcgen05 TF32)", 0: "edge_bwd_kernel (fp32 FMA)"}[bwd_mode]
     model = None
     if "error" not in probes:
-        pk = probes["tcgen05_f16_tflops"] if bwd_mode == 5 else (probes["tcgen05_tf32_tflops"] if bwd_mode else probes["ffma_fp32_tflops"])
+        pk = probes["tcgen05_f16_tflops"] if bwd_mode in (5, 7, 8) else (probes["tcgen05_tf32_tflops"] if bwd_mode else probes["ffma_fp32_tflops"])
         t_tensor = flop / (pk * 1e12)
         t_mufu = 3 * H * E / (probes["mufu_tanh_gops"] * 1e9)            # one tanh.approx per SiLU': z1, z2, z3 of every edge
         t_mem = algo_bytes / (peaks.get("hbm_gbs", 6650.0) * 1e9)
@@ -1118,12 +1168,17 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
                      t_measured_us=round(t_s * 1e6, 2), frac_of_model=t_model / t_s,
                      what="SURVEY.md 8(d): max(t_tensor, t_mufu, t_mem) / t_measured with the tensor and MUFU rates "
                           "measured by the probes above and the no-reuse byte model against the measured HBM copy rate")
+    at_scale = None
+    try:
+        at_scale = edge_bwd_at_scale(net, dev, flush, peak_tf, probes, peaks)
+    except Exception as exc:
+        at_scale = dict(error=f"{type(exc).__name__}: {exc}"[:300])
     roof = dict(kernel=f"{kname}, one launch = all E edges of one layer; CUDA events around the C-ABI call incl. its two "
                        "output memsets, L2 flushed",
                 bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
                 peak_source=which, peaks_measured=probes,
                 peak_tf32_measured=probes.get("tcgen05_tf32_tflops"), peak_f16_measured=probes.get("tcgen05_f16_tflops"),
-                peak_mufu_measured=probes.get("mufu_tanh_gops"), model=model,
+                peak_mufu_measured=probes.get("mufu_tanh_gops"), model=model, at_scale=at_scale,
                 note="algorithmic flops = 6 GEMMs x 2*64*64 = 49152 per edge (the per-edge MLP recompute, its data gradient "
                      f"and its weight gradient); the no-reuse byte model is {algo_bytes / 1e6:.0f} MB per launch = "
                      f"{algo_bytes / t_s / 1e9:.0f} GB/s at this duration, under the HBM roof, and P/Q/x rows are L2-resident "

@@ -13,6 +13,7 @@
 #include "edge_tc_bwd.cu"
 #include "edge_tc_bwd2.cu"
 #include "edge_tc_bwd3.cu"
+#include "edge_tc_bwd4.cu"
 #include "graph_kernels.cu"
 #include "graph_prep.cu"
 #include "radius_graph.cu"
@@ -58,10 +59,11 @@ int fail(int code, const char* fmt, ...) {
 int g_edge_fwd_mode = 1;
 // 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands
 // and MN-major weight-gradient operands (256 / 512 threads per tile), 5 = tcgen05 kind::f16 with two tile streams per CTA,
-// 6 = auto (default): 5 when there are enough 128-edge tiles to fill both streams of every SM many times over (the fp16
-// kernel runs 1.29x faster at 3.6 M edges but carries a bound pre-pass and twice the tile quantisation: slower at 1.8e5), else 4
+// 7 / 8 = the same operand format with packed-fp16 epilogue arithmetic, coalesced scatter and next-tile prefetch
+// (edge_tc_bwd4.cu; 256 / 512 threads per tile), 6 = auto (default): 7 wherever the tensor-core form applies (measured on
+// the B200, per launch: 98 us at 1.8e5 edges and 1.03 ms at 3.6e6 against 116 us / 1.82 ms for mode 4 and 120 us / 1.42 ms
+// for mode 5), else 4 / 0
 int g_edge_bwd_mode = 6;
-constexpr int kAutoTilesPerSm = 32;
 
 // 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
 int g_virt_fwd_mode = 1;
@@ -214,8 +216,8 @@ int fegnn_set_mode(const char* phase, int mode) {
     return 0;
   }
   if (strcmp(phase, "edge_backward") == 0) {
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 5 && mode != 6)
-      return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2, 4, 5 or 6 (auto)");
+    if (mode != 0 && mode != 1 && mode != 2 && (mode < 4 || mode > 8))
+      return fail(FEGNN_EINVAL, "edge_backward mode must be 0, 1, 2, 4, 5, 6 (auto), 7 or 8");
     g_edge_bwd_mode = mode;
     return 0;
   }
@@ -495,8 +497,11 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
   int mode = g_edge_bwd_mode;
-  if (mode == 6) mode = ((d->E + kTM - 1) / kTM >= kAutoTilesPerSm * sm_count() && sv->scratch != nullptr) ? 5 : 4;
-  if (mode == 5 && tc_ok && sv->scratch != nullptr)
+  if (mode == 6) mode = (tc_ok && sv->scratch != nullptr) ? 7 : 4;      // auto: the packed-fp16 kernel wherever it applies
+  if ((mode == 7 || mode == 8) && (!tc_ok || sv->scratch == nullptr)) mode = 4;
+  if (mode == 7) CK(launch_edge_bwd_tc4<2>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
+  else if (mode == 8) CK(launch_edge_bwd_tc4<4>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
+  else if (mode == 5 && tc_ok && sv->scratch != nullptr)
     CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
   else if (mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
   else if ((mode == 4 || mode == 5) && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));

@@ -132,8 +132,9 @@ unsigned long long fegnn_launch_count(void);
  * 3 = tcgen05 error-compensated 3xTF32 tiles (fp32-grade).  "edge_backward": 0 = fp32 FMA kernel, 1 = tcgen05 TF32 with
  * shared-memory operands, 2 / 4 = tcgen05 TF32 with tensor-memory A operands and MN-major weight-gradient operands,
  * 256 / 512 threads per 128-edge tile, 5 = tcgen05 kind::f16 (fp16 operands with one power-of-two scale per launch and
- * gradient tensor, fp32 accumulation; same 10-bit mantissa as TF32) with two 128-edge tiles in flight per SM, 6 = auto
- * (default): 5 for launches with at least 32 tiles per SM, else 4.  Layers with attention=True or Fe > 4 always take mode 0 in
+ * gradient tensor, fp32 accumulation; same 10-bit mantissa as TF32) with two 128-edge tiles in flight per SM, 7 / 8 = the
+ * same operands with packed-fp16 epilogue arithmetic (SiLU on fp16 pairs), 256 / 512 threads per tile, 6 = auto (default):
+ * 7 wherever the tensor-core form applies, else 4 / 0.  Layers with attention=True or Fe > 4 always take mode 0 in
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
  * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels (default), 1 = tcgen05
  * TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's atol 1e-4 on

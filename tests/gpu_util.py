@@ -34,9 +34,11 @@ class Tol(tuple):
 
 # Worst observed (all seeded cases + BASELINE configs 2 / 4 / 5-at-1/16 at full size, profiles/parity_report_r2.txt):
 #   fp32   out ~0 (inside the 4-ulp term)  gin 3.3e-6 (g_loc_mean of config 4: [1,3,3] sums over 8 000 nodes; 8.3e-7 elsewhere)  gw 3.9e-5  gb 8.1e-6
-#   tf32x3 out 1.3e-6                      gin 2.5e-3  gw 5.9e-3  gb 5.5e-2
+#   tf32x3 out 1.3e-6                      gin 2.5e-3  gw 1.3e-2  gb 5.5e-2   (same backward kernels as tf32: the packed-fp16
+#          epilogues of edge_tc_bwd4.cu round silu' to fp16 after 3 packed operations instead of once -- gw was 5.9e-3 with
+#          the fp32-epilogue kernel, edge_backward mode 5, which stays selectable)
 #   tf32   out 4.5e-3                      gin 2.4e-3  gw 1.1e-2  gb 5.5e-2
-TOLERANCES = {"fp32": Tol(2e-6, 8e-6, 8e-5), "tf32x3": Tol(4e-6, 5e-3, 1.2e-2, 1.2e-1), "tf32": Tol(8e-3, 5e-3, 2.5e-2, 1.2e-1),
+TOLERANCES = {"fp32": Tol(2e-6, 8e-6, 8e-5), "tf32x3": Tol(4e-6, 5e-3, 2.5e-2, 1.2e-1), "tf32": Tol(8e-3, 5e-3, 2.5e-2, 1.2e-1),
               "tf32_all": Tol(8e-3, 5e-3, 2.5e-2, 1.2e-1)}
 EPS32 = 2.0 ** -23
 

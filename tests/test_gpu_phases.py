@@ -275,13 +275,14 @@ def test_edge_forward_modes(name, mode):
     assert e_m <= EDGE_MODE_TOL[mode] and e_t <= EDGE_MODE_TOL[mode], (e_m, e_t)
 
 
-EDGE_BWD_TOL = {0: (3e-5, 2e-4), 1: (6e-3, 6e-3), 2: (6e-3, 6e-3), 4: (6e-3, 6e-3), 5: (6e-3, 6e-3)}     # (per-node outputs, weight gradients), relative to tensor max
+EDGE_BWD_TOL = {0: (3e-5, 2e-4), 1: (6e-3, 6e-3), 2: (6e-3, 6e-3), 4: (6e-3, 6e-3), 5: (6e-3, 6e-3), 7: (6e-3, 6e-3), 8: (6e-3, 6e-3)}     # (per-node outputs, weight gradients), relative to tensor max
 # modes: 0 fp32 FMA; 1 tcgen05 TF32 (operands in shared memory); 2 / 4 tcgen05 TF32, A operands in tensor memory,
 # MN-major weight-gradient operands, 256 / 512 threads per tile; 5 tcgen05 kind::f16 (fp16 operands, one power-of-two scale per
-# launch and gradient tensor, same 10-bit mantissa as TF32), two tile streams per CTA
+# launch and gradient tensor, same 10-bit mantissa as TF32), two tile streams per CTA; 7 / 8 the same operand format with
+# packed-fp16 epilogue arithmetic (edge_tc_bwd4.cu), 256 / 512 threads per tile
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 4, 5])
+@pytest.mark.parametrize("mode", [0, 1, 2, 4, 5, 7, 8])
 @pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
 @pytest.mark.parametrize("layer", [0, 1])
 def test_edge_backward_modes(name, mode, layer):

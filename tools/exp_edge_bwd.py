@@ -32,7 +32,7 @@ gP, gQ, gx = torch.empty(N, 64, device=dev), torch.empty(N, 64, device=dev), tor
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 res = []
-for mode in (2, 4, 5):
+for mode in tuple(int(m) for m in os.environ.get("FEGNN_EXP_MODES", "4,5,7,8").split(",")):
     L.set_mode("edge_backward", mode)
     run = lambda: L.check(L.lib.fegnn_edge_backward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), C.byref(gr), L.ptr(t["loc_0"]),
                                                     C.byref(sv.c), L.ptr(gm), L.ptr(gt), L.ptr(gP), L.ptr(gQ), L.ptr(gx), st))
