@@ -16,7 +16,7 @@ H = 64
 MAX_C = 16
 MAX_FE = 8
 
-F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF, F_COORDS_SUM, F_NODE_SUM = 1, 2, 4, 8, 16, 32, 64, 128
+F_ATTENTION, F_NORMALIZE, F_TANH, F_GRAVITY, F_LAST, F_RF, F_COORDS_SUM, F_NODE_SUM, F_PREZEROED = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 fp = C.POINTER(C.c_float)
 ip = C.POINTER(C.c_int32)
@@ -133,6 +133,7 @@ SIGNATURES = {
     "fegnn_rf_vel_forward": (C.c_int, [i32, vp, _PP, vp, vp]),
     "fegnn_rf_vel_backward": (C.c_int, [i32, vp, _PP, _PP, vp, vp]),
     "fegnn_layer_saved_floats": (C.c_size_t, [_PD]),
+    "fegnn_layer_saved_accum_floats": (C.c_size_t, [_PD]),
     "fegnn_layer_saved_bind": (C.c_int, [_PD, vp, _PS]),
     "fegnn_model_workspace_floats": (C.c_size_t, [_PD, i32]),
     "fegnn_model_backward_scratch_floats": (C.c_size_t, [_PD]),

@@ -346,7 +346,7 @@ int fegnn_edge_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_la
   RQ(g && x && sv);
   EdgeArgs a = edge_args(d, g, p, x, sv);
   a.msum = sv->msum; a.tsum = sv->tsum;
-  CK(zero_pair(sv->msum, kH * (size_t)d->N, sv->tsum, 3 * (size_t)d->N, S(stream)));
+  if (!(d->flags & FEGNN_F_PREZEROED)) CK(zero_pair(sv->msum, kH * (size_t)d->N, sv->tsum, 3 * (size_t)d->N, S(stream)));
   const int mode = d->Fe <= kTcMaxFe ? g_edge_fwd_mode : 0;
   if (mode == 3) CK(launch_edge_fwd_tc<3>(a, sm_count(), S(stream)));
   else if (mode == 1) CK(launch_edge_fwd_tc<1>(a, sm_count(), S(stream)));
@@ -362,8 +362,10 @@ int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
   RQ(g && x && v && Z && sv && x_new && xsum_new);
   VirtArgs a = virt_args(d, g, p, x, v, Z, sv);
   a.u = sv->u; a.x_new = x_new; a.Dsum = sv->Dsum; a.Usum = sv->Usum; a.xsum_new = xsum_new;
-  CK(zero_pair(sv->Dsum, 3 * d->C * (size_t)d->B, sv->Usum, kH * d->C * (size_t)d->B, S(stream)));
-  CK(cudaMemsetAsync(xsum_new, 0, sizeof(float) * 3 * (size_t)d->B, S(stream)));
+  if (!(d->flags & FEGNN_F_PREZEROED)) {
+    CK(zero_pair(sv->Dsum, 3 * d->C * (size_t)d->B, sv->Usum, kH * d->C * (size_t)d->B, S(stream)));
+    CK(cudaMemsetAsync(xsum_new, 0, sizeof(float) * 3 * (size_t)d->B, S(stream)));
+  }
   if (g_virt_fwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION)) CK(launch_virtual_fwd_tc<2>(a, sm_count(), S(stream)));
   else CK(launch_virtual_fwd(a, sm_count(), S(stream)));
   return 0;
@@ -380,7 +382,7 @@ int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_
   a.dinv = (d->flags & FEGNN_F_NODE_SUM) ? nullptr : g->dinv;     // VNEGNN's A2A stage sums the messages (models/VNEGNN.py:87)
   a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
   a.zh1 = sv->zh1; a.h_new = h_new;
-  CK(launch_node_h_fwd(a, sm_count(), S(stream)));
+  CK(launch_node_h_fwd(a, sm_count(), S(stream), !(d->flags & FEGNN_F_PREZEROED)));
   return 0;
 }
 
@@ -471,7 +473,7 @@ int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegn
   a.g_Wxv = gr->crv_w0; a.g_bxv = gr->crv_b0; a.g_wxv = gr->crv_w2;
   a.g_WX = gr->cvv_w0; a.g_bX = gr->cvv_b0; a.g_wX = gr->cvv_w2;
   a.g_wav = gr->attv_w; a.g_bav = gr->attv_b;
-  CK(zero_pair(gG1, kH * d->C * (size_t)d->B, gx, 3 * (size_t)d->Nl, S(stream)));
+  if (!(d->flags & FEGNN_F_PREZEROED)) CK(zero_pair(gG1, kH * d->C * (size_t)d->B, gx, 3 * (size_t)d->Nl, S(stream)));
   // tensor-core form: two kernels; `gu` doubles as the [N,C,H] scratch that carries the total dL/du between them
   if (d->flags & FEGNN_F_LAST) a.gu = nullptr;        // last layer: phi_h is discarded, a gu buffer holds no input
   if (g_virt_bwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION) && gu != nullptr) {
@@ -494,15 +496,16 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   a.gm = gm; a.gt = gt; a.gP = gP; a.gQ = gQ; a.gx = gx;
   a.g_w1 = gr->edge_w0; a.g_W2 = gr->edge_w2; a.g_b2 = gr->edge_b2;
   a.g_W3 = gr->cr_w0; a.g_b3 = gr->cr_b0; a.g_w4 = gr->cr_w2; a.g_wa = gr->att_w; a.g_ba = gr->att_b;
-  CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
+  const bool zero = !(d->flags & FEGNN_F_PREZEROED);
+  if (zero) CK(zero_pair(gP, kH * (size_t)d->N, gQ, kH * (size_t)d->Nl, S(stream)));
   const bool tc_ok = d->Fe <= kTcMaxFe && !(d->flags & FEGNN_F_ATTENTION);
   int mode = g_edge_bwd_mode;
   if (mode == 6) mode = (tc_ok && sv->scratch != nullptr) ? 7 : 4;      // auto: the packed-fp16 kernel wherever it applies
   if ((mode == 7 || mode == 8) && (!tc_ok || sv->scratch == nullptr)) mode = 4;
-  if (mode == 7) CK(launch_edge_bwd_tc4<2>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
-  else if (mode == 8) CK(launch_edge_bwd_tc4<4>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
+  if (mode == 7) CK(launch_edge_bwd_tc4<2>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
+  else if (mode == 8) CK(launch_edge_bwd_tc4<4>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
   else if (mode == 5 && tc_ok && sv->scratch != nullptr)
-    CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream)));
+    CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
   else if (mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
   else if ((mode == 4 || mode == 5) && tc_ok) CK(launch_edge_bwd_tc2<4>(a, sm_count(), S(stream)));
   else if (mode == 1 && tc_ok) CK(launch_edge_bwd_tc(a, sm_count(), S(stream)));
@@ -662,13 +665,19 @@ int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved*
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   float* p = block;
   auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  // accumulators first and contiguous (one zero-fill per layer and step, fegnn_layer_saved_accum_floats words from msum)
+  out->msum = take(N * kH); out->tsum = take(N * 3); out->zh1 = take(N * kH);
+  out->Dsum = take(B * 3 * C); out->Usum = take(B * C * kH);
+  out->scratch = take(16);
   out->P = take(N * kH); out->Av = take(N * kH); out->Uh = take(N * kH); out->Q = take(Nl * kH);
   out->sv = take(N); out->sg = take(N);
   out->M = take(B * C * C); out->Zc = take(B * 3 * C); out->G1 = take(B * C * kH);
-  out->msum = take(N * kH); out->tsum = take(N * 3); out->u = take(N * C * kH); out->zh1 = take(N * kH);
-  out->Dsum = take(B * 3 * C); out->Usum = take(B * C * kH);
-  out->scratch = take(16);
+  out->u = take(N * C * kH);
   return 0;
+}
+size_t fegnn_layer_saved_accum_floats(const fegnn_dims* d) {
+  const size_t N = d->N, B = d->B, C = d->C;
+  return al4(N * kH) + al4(N * 3) + al4(N * kH) + al4(B * 3 * C) + al4(B * C * kH) + 16;
 }
 
 }  // extern "C"
@@ -719,9 +728,9 @@ void model_ws_bind(const fegnn_dims* d, int L, float* base, ModelWs* w) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   float* p = base;
   auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
+  for (int l = 0; l <= L; ++l) w->xsum[l] = take(B * 3);       // contiguous: ONE zero-fill per step for all of them
   for (int l = 0; l <= L; ++l) {
     w->h[l] = take(N * kH); w->x[l] = take(Nl * 3); w->Z[l] = take(B * 3 * C); w->Sx[l] = take(B * C * kH);
-    w->xsum[l] = take(B * 3);
   }
   for (int l = 0; l < L; ++l) {
     fegnn_layer_saved_bind(d, p, &w->saved[l]);
@@ -730,20 +739,22 @@ void model_ws_bind(const fegnn_dims* d, int L, float* base, ModelWs* w) {
 }
 
 struct BwdScratch {
-  float *gh, *gx[2], *gZ[2], *gS[2], *gxsum[2], *gDsum, *gUsum, *gzh1, *gm, *gu, *gAv, *gG1, *gsv, *gsg, *gt, *gP, *gQ;
+  float *gh, *gx[2], *gZ[2], *gS[2], *gxsum[2], *gDsum, *gUsum, *gzh1, *gm, *gu, *gAv, *gG1[2], *gsv, *gsg, *gt, *gP[2], *gQ[2];
+  size_t set_a_floats, set_b_floats;      // [gG1 | gx] and [gP | gQ] of one set, each contiguous (one zero-fill)
 };
 size_t bwd_scratch_floats(const fegnn_dims* d) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   return al4(N * kH) + 2 * al4(Nl * 3) + 2 * al4(B * 3 * C) + 2 * al4(B * C * kH) + 2 * al4(B * 3) + al4(B * 3 * C) +
-         al4(B * C * kH) + 2 * al4(N * kH) + al4(N * C * kH) + al4(N * kH) + al4(B * C * kH) + 2 * al4(N) +
-         al4(N * 3) + al4(N * kH) + al4(Nl * kH);
+         al4(B * C * kH) + 2 * al4(N * kH) + al4(N * C * kH) + al4(N * kH) + 2 * al4(B * C * kH) + 2 * al4(N) +
+         al4(N * 3) + 2 * (al4(N * kH) + al4(Nl * kH));
 }
 void bwd_scratch_bind(const fegnn_dims* d, float* base, BwdScratch* s) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   float* p = base;
   auto take = [&](size_t n) { float* r = p; p += al4(n); return r; };
   s->gh = take(N * kH);
-  s->gx[0] = take(Nl * 3); s->gG1 = take(B * C * kH); s->gx[1] = take(Nl * 3);   // gG1 next to either gx: one memset node
+  for (int k = 0; k < 2; ++k) { s->gG1[k] = take(B * C * kH); s->gx[k] = take(Nl * 3); }    // set k: [gG1 | gx] contiguous
+  s->set_a_floats = al4(B * C * kH) + Nl * 3;
   s->gZ[0] = take(B * 3 * C); s->gZ[1] = take(B * 3 * C);
   s->gS[0] = take(B * C * kH); s->gS[1] = take(B * C * kH);
   s->gxsum[0] = take(B * 3); s->gxsum[1] = take(B * 3);
@@ -751,7 +762,8 @@ void bwd_scratch_bind(const fegnn_dims* d, float* base, BwdScratch* s) {
   s->gzh1 = take(N * kH); s->gm = take(N * kH); s->gu = take(N * C * kH);
   s->gAv = take(N * kH);
   s->gsv = take(N); s->gsg = take(N); s->gt = take(N * 3);
-  s->gP = take(N * kH); s->gQ = take(Nl * kH);
+  for (int k = 0; k < 2; ++k) { s->gP[k] = take(N * kH); s->gQ[k] = take(Nl * kH); }        // set k: [gP | gQ] contiguous
+  s->set_b_floats = al4(N * kH) + Nl * kH;
 }
 
 }  // namespace
@@ -782,7 +794,12 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
     broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, w.Sx[0]); ++g_launches;
     CK(cudaGetLastError());
   }
-  TRY(fegnn_graph_xsum(d->N, d->B, w.x[0], g->batch, w.xsum[0], stream));
+  // every accumulator of the step is zero-filled here, ahead of the kernel chain (the phases then skip their own fills):
+  // the per-graph coordinate sums of all states, and the accumulator head of every layer's saved block
+  CK(cudaMemsetAsync(w.xsum[0], 0, sizeof(float) * ((size_t)L * al4(B * 3) + B * 3), st));
+  for (int l = 0; l < L; ++l)
+    CK(cudaMemsetAsync(w.saved[l].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+  CK(launch_graph_xsum(d->N, w.x[0], g->batch, w.xsum[0], st));
   SideStream* sd = side_stream();
   RQ(sd != nullptr);
   void* side = sd->st;
@@ -790,6 +807,7 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   const bool rf = d->flags & FEGNN_F_RF;          // FastRF: h and S pass through every layer (models/FastRF.py:186)
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
+    dl.flags |= FEGNN_F_PREZEROED;
     const bool last = rf || l == L - 1;
     if (last) dl.flags |= FEGNN_F_LAST;
     const fegnn_layer_params* p = &layers[l];
@@ -904,6 +922,11 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
   bwd_scratch_bind(d, scratch, &s);
   const size_t N = d->N, B = d->B, C = d->C;
   CK(cudaMemsetAsync(s.gh, 0, sizeof(float) * kH * N, st));
+  // [gG1 | gx] and [gP | gQ] exist twice: layer l accumulates into set `cur` while the side stream zero-fills the other set
+  // (whose last readers, virtual_backward(l) and node_pre_backward(l + 1), lie before the fork) for layer l - 1 -- no fill
+  // stands between two kernels of the main chain
+  CK(cudaMemsetAsync(s.gG1[0], 0, sizeof(float) * s.set_a_floats, st));
+  CK(cudaMemsetAsync(s.gP[0], 0, sizeof(float) * s.set_b_floats, st));
   const float* gx_new = gx_out;
   const float* gZ_new = gZ_out;
   const float* gS_new = nullptr;
@@ -916,6 +939,7 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
   const bool rf = d->flags & FEGNN_F_RF;
   for (int l = L - 1; l >= 0; --l) {
     fegnn_dims dl = *d;
+    dl.flags |= FEGNN_F_PREZEROED;
     const bool last = rf || l == L - 1;
     if (last) dl.flags |= FEGNN_F_LAST;
     const fegnn_layer_params* p = &layers[l];
@@ -928,13 +952,17 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     if (!last) TRY(fegnn_node_h_backward(&dl, g, p, gr, sv, s.gh, s.gzh1, s.gm, s.gu, stream));
     JOIN(sd, st);
     TRY(fegnn_virtual_backward(&dl, g, p, gr, w.x[l], v, w.Z[l], sv, gx_new, gxsum_next, s.gDsum,
-                               last ? nullptr : s.gUsum, s.gu, s.gAv, s.gG1, s.gx[cur], s.gZ[cur],
+                               last ? nullptr : s.gUsum, s.gu, s.gAv, s.gG1[cur], s.gx[cur], s.gZ[cur],
                                s.gsv, s.gsg, s.gt, stream));
     FORK(sd, st);                                 // side: graph_pre_bwd(l) -> graph_post_bwd(l-1), under edge_bwd, node_pre_bwd
-    TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[ls], sv, s.gG1, s.gS[cur], s.gZ[cur], s.gxsum[cur], side));
-    TRY(fegnn_edge_backward(&dl, g, p, gr, w.x[l], sv, last ? nullptr : s.gm, s.gt, s.gP, s.gQ, s.gx[cur], stream));
+    TRY(fegnn_graph_pre_backward(&dl, g, p, gr, w.Sx[ls], sv, s.gG1[cur], s.gS[cur], s.gZ[cur], s.gxsum[cur], side));
+    if (l > 0) {                                  // side: the other set, for layer l - 1
+      CK(cudaMemsetAsync(s.gG1[cur ^ 1], 0, sizeof(float) * s.set_a_floats, S(side)));
+      CK(cudaMemsetAsync(s.gP[cur ^ 1], 0, sizeof(float) * s.set_b_floats, S(side)));
+    }
+    TRY(fegnn_edge_backward(&dl, g, p, gr, w.x[l], sv, last ? nullptr : s.gm, s.gt, s.gP[cur], s.gQ[cur], s.gx[cur], stream));
     if (rf) TRY(fegnn_rf_vel_backward(d->N, v, p, gr, s.gsv, stream));
-    TRY(fegnn_node_pre_backward(&dl, p, gr, w.h[ls], s.gP, s.gQ, s.gAv, last ? nullptr : s.gzh1, s.gsv, s.gsg, s.gh,
+    TRY(fegnn_node_pre_backward(&dl, p, gr, w.h[ls], s.gP[cur], s.gQ[cur], s.gAv, last ? nullptr : s.gzh1, s.gsv, s.gsg, s.gh,
                                 stream));
     gx_new = s.gx[cur]; gZ_new = s.gZ[cur]; gS_new = s.gS[cur]; gxsum_next = s.gxsum[cur];
     cur ^= 1;

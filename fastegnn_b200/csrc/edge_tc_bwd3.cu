@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(kThreads3, 1) edge_bwd_tc3_kernel(EdgeArgs a, 
 }  // namespace bwd3
 
 // stats: 4 unsigned of caller scratch (device)
-inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st) {
+inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st, bool zero_stats = true) {
   static DevOnce attr;
   const size_t bytes = bwd3::Smem3::bytes;
   if (!attr.get()) {
@@ -684,7 +684,9 @@ inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int s
   if (ntiles == 0) return cudaSuccess;
   const int pairs = (ntiles + bwd3::kGroups - 1) / bwd3::kGroups;
   const int grid = pairs < sms ? pairs : sms;
-  cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st);
+  // the bound pre-pass takes maxima: stale (larger) entries only make the scales more conservative, so a caller that zeroed
+  // the scratch words once per step (FEGNN_F_PREZEROED) may run the backward again on the same block
+  cudaError_t e = zero_stats ? cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
   sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);

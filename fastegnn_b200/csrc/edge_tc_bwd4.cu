@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
 
 // stats: 4 unsigned of caller scratch (device)
 template <int CG>
-inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st) {
+inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st, bool zero_stats = true) {
   static DevOnce attr;
   const size_t bytes = bwd4::Smem4<CG>::bytes;
   if (!attr.get()) {
@@ -725,7 +725,9 @@ inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int s
   if (ntiles == 0) return cudaSuccess;
   const int pairs = (ntiles + 1) / 2;
   const int grid = pairs < sms ? pairs : sms;
-  cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st);
+  // the bound pre-pass takes maxima: stale (larger) entries only make the scales more conservative, so a caller that zeroed
+  // the scratch words once per step (FEGNN_F_PREZEROED) may run the backward again on the same block
+  cudaError_t e = zero_stats ? cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
   sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);

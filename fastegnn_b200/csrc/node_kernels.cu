@@ -521,7 +521,7 @@ cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   node_pre_bwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreBwdSmem, st>>>(a, nactive); ++g_launches;
   return cudaGetLastError();
 }
-cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
+cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st, bool zero = true) {
   FEGNN_SET_SMEM(node_h_z_kernel, kNodeHSmem);
   {
     static DevOnce done2_;
@@ -533,7 +533,7 @@ cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   }
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(a.zh1, 0, sizeof(float) * kH * (size_t)a.N, st);
+  cudaError_t e = zero ? cudaMemsetAsync(a.zh1, 0, sizeof(float) * kH * (size_t)a.N, st) : cudaSuccess;
   if (e != cudaSuccess) return e;
   node_h_z_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
   node_h_out_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;

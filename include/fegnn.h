@@ -57,6 +57,11 @@ extern "C" {
 #define FEGNN_F_NODE_SUM 128u  /* phi_h takes the SUM of a row's messages instead of their mean (the A2A stage of the VNEGNN
                                  sibling, models/VNEGNN.py:85-96).  Understood by fegnn_node_h_forward / _backward.            */
 
+#define FEGNN_F_PREZEROED 256u /* the caller has already zero-filled every accumulator a phase adds into (msum | tsum | zh1 | Dsum |
+                                 Usum | scratch of the saved block -- contiguous from .msum, fegnn_layer_saved_accum_floats() words --
+                                 xsum_new, gG1, gx, gP, gQ): the phase skips its own fills.  fegnn_model_forward / _backward set it
+                                 and issue the fills once per step, off the kernel chain.                                         */
+
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
   int32_t Nl;       /* rows of x / Q: owned + halo (== N on one GPU)                */
@@ -113,7 +118,7 @@ typedef struct fegnn_layer_grads {
 /* Per-layer activations kept from forward for backward (all device, caller-owned;
  * fegnn_layer_saved_floats() gives the size of one contiguous block and
  * fegnn_layer_saved_bind() carves it). */
-typedef struct fegnn_layer_saved {
+typedef struct fegnn_layer_saved {   /* the accumulators msum, tsum, zh1, Dsum, Usum, scratch lie first and contiguously */
   float *P, *Q, *Av, *Uh;   /* [N,H] [Nl,H] [N,H] [N,H] first-layer products of h        */
   float *sv, *sg;           /* [N] phi_v(h), phi_g(h)                                     */
   float *M, *Zc, *G1;       /* [B,C,C] [B,3,C] [B,C,H] per-graph terms                    */
@@ -309,6 +314,8 @@ int fegnn_rf_vel_backward(int32_t N, const float* v, const fegnn_layer_params* p
  * FastRF.forward (models/FastRF.py:228-240): every layer reads the embedding h and the initial S.
  * Workspace layout is private; sizes come from the *_floats queries.            */
 size_t fegnn_layer_saved_floats(const fegnn_dims* d);
+/* words of the accumulator head of a saved block (from .msum): what FEGNN_F_PREZEROED expects zero-filled */
+size_t fegnn_layer_saved_accum_floats(const fegnn_dims* d);
 int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out);
 size_t fegnn_model_workspace_floats(const fegnn_dims* d, int32_t L);
 size_t fegnn_model_backward_scratch_floats(const fegnn_dims* d);
