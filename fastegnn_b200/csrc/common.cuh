@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/fegnn.h"
 
@@ -294,5 +295,33 @@ struct DevOnce {
 
 // Number of kernels this library has launched (host counter; read through fegnn_launch_count()).
 inline unsigned long long g_launches = 0;
+
+// Programmatic dependent launch.  Every kernel of the main chain starts with pdl_trigger() (the next kernel of the stream
+// may begin its prologue: weight staging, barrier init, tensor-memory allocation) and calls pdl_wait() before it touches
+// anything a predecessor produced -- or anything a predecessor may still read (griddepcontrol.wait returns when every
+// prerequisite grid has completed and flushed).  Before the wait a kernel reads layer weights only (written by the optimizer,
+// never inside a forward / backward).  Both are no-ops in a launch without the attribute.  FEGNN_PDL=0 disables it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("FEGNN_PDL") && atoi(getenv("FEGNN_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ++g_launches;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace fegnn

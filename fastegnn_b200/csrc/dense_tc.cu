@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(128 * CG, 2) dense_bwd_tc_kernel(const __grid_
   constexpr int NT = 128 * CG, CPT = kH / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
   Vec* v = reinterpret_cast<Vec*>(smem + Smem::off_vec);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(128 * CG, 2) dense_bwd_tc_kernel(const __grid_
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  pdl_wait();
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
   const uint32_t id_ts_k = idesc_tf32(128, 64, 0, 0), id_ts_mn = idesc_tf32(128, 64, 0, 1), id_wg = idesc_tf32(64, 64, 1, 1);
@@ -303,7 +305,7 @@ cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
   if (ntiles == 0 || a.nblk == 0) return cudaSuccess;
   int per = (2 * sms) / a.nblk;                   // CTAs per block at 2 CTAs / SM
   per = per < 1 ? 1 : (per > ntiles ? ntiles : per);
-  dtc::dense_bwd_tc_kernel<2><<<per * a.nblk, 256, dtc::Smem::bytes, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(dtc::dense_bwd_tc_kernel<2>, per * a.nblk, 256, dtc::Smem::bytes, st, a)) return e_;
   return cudaGetLastError();
 }
 

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B, derived from the __shared__ symbol so that accesses stay LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
   EdgeTcVec* v = reinterpret_cast<EdgeTcVec*>(smem + SM::off_vec);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   // thread (warp, lane) owns row (warp&3)*32 + lane (a TMEM lane) and the 32 columns of half `half`
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  pdl_wait();
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 32;
   const uint32_t idesc = umma::make_idesc_tf32(128, 64);
@@ -337,7 +339,7 @@ cudaError_t launch_edge_fwd_tc(const EdgeArgs& a, int sms, cudaStream_t st) {
   if (ntiles == 0) return cudaSuccess;
   const int per_sm = EdgeTcSmem<SPLIT>::ctas_per_sm;
   const int grid = ntiles < per_sm * sms ? ntiles : per_sm * sms;
-  edge_fwd_tc_kernel<SPLIT><<<grid, kTcThreads, bytes, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(edge_fwd_tc_kernel<SPLIT>, grid, kTcThreads, bytes, st, a)) return e_;
   return cudaGetLastError();
 }
 

@@ -149,6 +149,8 @@ constexpr uint32_t kR3 = 256, kR2 = 336, kDXZ = 416;        // [dW3 64 | aux 8],
 __global__ void __launch_bounds__(256) edge_bwd_stats_kernel(int N, int Nl, const float* __restrict__ x,
                                                              const float* __restrict__ gt, const float* __restrict__ gm,
                                                              unsigned* __restrict__ stats /*[4], zeroed by the caller*/) {
+  pdl_trigger();
+  pdl_wait();
   float mt = 0.f, mm = 0.f, mx = 0.f;
   const float x0 = x[0], x1 = x[1], x2 = x[2];
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -160,7 +160,7 @@ __device__ __forceinline__ float pow2_to(float bound, int e_target) {   // large
 }
 
 template <int CG>
-__global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, const unsigned* __restrict__ stats) {
+__global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, const unsigned* stats) {
   constexpr int NTG = 128 * CG, NT = 2 * NTG, CPT = kH / CG, NP = CPT / 2, NWG = NTG / 32, RPW = kTM / NWG;
   using SM = Smem4<CG>;
   using GV = GroupVec<CG>;
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
   uint8_t *TA = gs + SM::g_TA, *TM = gs + SM::g_TM, *AUX = gs + SM::g_AUX, *TG = gs + SM::g_TG, *T3 = gs + SM::g_T3;
   const bool use_tanh = a.flags & FEGNN_F_TANH, norm = a.flags & FEGNN_F_NORMALIZE;
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(1 + G), "n"(NTG) : "memory"); };
+  pdl_trigger();
 
   // ---- prologue (whole CTA): fp16 weight tiles (+ their max magnitudes), fp32 vectors, zero AUX, barriers, tensor memory
   float mw2 = 0.f, mw3 = 0.f;
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     atomicMax(&sv->mw[1], __float_as_uint(mw3));
   }
   __syncthreads();
+  pdl_wait();                                    // everything above read weights only; `stats` comes from the pre-pass
   // ---- per-launch power-of-two scales (every thread, identical arithmetic).  Bounds from the pre-pass `stats`:
   //      |gs| <= dmax * sqrt3 * max|gt|  ->  sa ;  |w4| -> sb ;  g3 is stored times s3 = sa sb (<= 2^14)
   //      |g2| <= (max|gm| + 64 |g3| max|W3|) -> s2 ;  |gz1| <= 64 |g2| max|W2| -> s1   (stored values <= 2^15)
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       mw4 = fmaxf(mw4, fabsf(sv->w4f[i]));
       mwq = fmaxf(mwq, fabsf(sv->wqf[i]));
     }
-    const float mgt = __uint_as_float(stats[0]), mgm = __uint_as_float(stats[1]), ext = 2.f * __uint_as_float(stats[2]);
+    // (no const __restrict__ / ld.global.nc on `stats`: the compiler would hoist those loads above griddepcontrol.wait)
+    const float mgt = __uint_as_float(__ldcg(stats)), mgm = __uint_as_float(__ldcg(stats + 1)), ext = 2.f * __uint_as_float(__ldcg(stats + 2));
     const float dmax = norm ? 1.f : ext * 1.7320508f;
     const float bgs = dmax * mgt * 1.7320508f * 1.05f;
     sa = pow2_to(bgs, 7);
@@ -731,8 +734,10 @@ inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int s
   if (e != cudaSuccess) return e;
   int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
   sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);
-  bwd3::edge_bwd_stats_kernel<<<sblocks, 256, 0, st>>>(a.N, a.Nl, a.x, a.gt, a.gm, stats); ++g_launches;
-  bwd4::edge_bwd_tc4_kernel<CG><<<grid, 256 * CG, bytes, st>>>(a, stats); ++g_launches;
+  e = launch_pdl(bwd3::edge_bwd_stats_kernel, sblocks, 256, 0, st, a.N, a.Nl, a.x, a.gt, a.gm, stats);
+  if (e != cudaSuccess) return e;
+  e = launch_pdl(bwd4::edge_bwd_tc4_kernel<CG>, grid, 256 * CG, bytes, st, a, (const unsigned*)stats);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

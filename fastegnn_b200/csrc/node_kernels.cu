@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(kThreads, 2) node_pre_fwd_kernel(NodePreArgs a
   const int cta = blockIdx.x / nactive, nctas = gridDim.x / nactive;
   const float* wsrc = blk <= 1 ? a.edge_w0 : blk == 2 ? a.edgev_w0 : blk == 3 ? a.node_w0 : blk == 4 ? a.vel_w0 : a.grav_w0;
   const int ld = blk <= 1 ? a.ld1 : blk == 2 ? a.ldv : blk == 3 ? a.ldn : kH;
+  pdl_trigger();
   stage_weight(Ws, wsrc, ld, blk == 1 ? kH : 0, 1);
   if (blk >= 4) {
     stage_vec(vec, blk == 4 ? a.vel_b0 : a.grav_b0, kH);
     stage_vec(vec + kH, blk == 4 ? a.vel_w2 : a.grav_w2, kH);
   }
+  pdl_wait();
   const int ntiles = (a.N + kTM - 1) / kTM;
   for (int tile = cta; tile < ntiles; tile += nctas) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
@@ -214,11 +216,13 @@ __global__ void __launch_bounds__(kThreads, 2) node_pre_bwd_kernel(NodePreArgs a
   float* gb = blk == 0 ? a.g_edge_b0 : blk == 2 ? a.g_edgev_b0 : blk == 3 ? a.g_node_b0
               : blk == 4 ? a.g_vel_b0 : blk == 5 ? a.g_grav_b0 : nullptr;
   const float* gs = blk == 4 ? a.gsv : a.gsg;
+  pdl_trigger();
   stage_weight(Ws, wsrc, ld, off, 1);
   if (head) {
     stage_vec(vec, blk == 4 ? a.vel_b0 : a.grav_b0, kH);
     stage_vec(vec + kH, blk == 4 ? a.vel_w2 : a.grav_w2, kH);
   }
+  pdl_wait();
   float wg[4][4], bs[4] = {0, 0, 0, 0}, cw2[4] = {0, 0, 0, 0};
   float cb2 = 0.f;
   zero_wg(wg);
@@ -309,8 +313,10 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_z_kernel(NodeHArgs a) {
   const int nblk = a.C + 1;
   const int blk = blockIdx.x % nblk, cta = blockIdx.x / nblk, nctas = gridDim.x / nblk;
   const int ntiles = (a.N + kTM - 1) / kTM;
+  pdl_trigger();
   if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
   else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
+  pdl_wait();
   for (int tile = cta; tile < ntiles; tile += nctas) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
@@ -343,7 +349,9 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_out_kernel(NodeHArgs a) {
   float* T0 = Ws + kWFloats;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int ntiles = (a.N + kTM - 1) / kTM;
+  pdl_trigger();
   stage_weight(Ws, a.node_w2, kH, 0, 1);
+  pdl_wait();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int i0 = tile * kTM, nvalid = min(kTM, a.N - i0);
     __syncthreads();
@@ -382,7 +390,9 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_bwd1_kernel(NodeHArgs a) {
   float* T1 = T0 + kTileFloats;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int ntiles = (a.N + kTM - 1) / kTM;
+  pdl_trigger();
   stage_weight(Ws, a.node_w2, kH, 0, 1);
+  pdl_wait();
   float wg[4][4], bs[4] = {0, 0, 0, 0};
   zero_wg(wg);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -429,8 +439,10 @@ __global__ void __launch_bounds__(kThreads, 2) node_h_bwd2_kernel(NodeHArgs a) {
   const int nblk = a.C + 1;
   const int blk = blockIdx.x % nblk, cta = blockIdx.x / nblk, nctas = gridDim.x / nblk;
   const int ntiles = (a.N + kTM - 1) / kTM;
+  pdl_trigger();
   if (blk == 0) stage_weight(Ws, a.node_w0, a.ldn, kH, 1);
   else stage_weight(Ws, a.node_w0, a.ldn, 2 * kH + (blk - 1), a.C);
+  pdl_wait();
   float wg[4][4];
   zero_wg(wg);
   for (int tile = cta; tile < ntiles; tile += nctas) {
@@ -509,7 +521,7 @@ cudaError_t launch_node_pre_fwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   if (ntiles == 0) return cudaSuccess;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
   const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
-  node_pre_fwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreFwdSmem, st>>>(a, nactive); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(node_pre_fwd_kernel, node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreFwdSmem, st, a, nactive)) return e_;
   return cudaGetLastError();
 }
 cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) {
@@ -518,7 +530,7 @@ cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   if (ntiles == 0) return cudaSuccess;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.gUh == nullptr;
   const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
-  node_pre_bwd_kernel<<<node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreBwdSmem, st>>>(a, nactive); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(node_pre_bwd_kernel, node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreBwdSmem, st, a, nactive)) return e_;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st, bool zero = true) {
@@ -535,8 +547,8 @@ cudaError_t launch_node_h_fwd(const NodeHArgs& a, int sms, cudaStream_t st, bool
   if (ntiles == 0) return cudaSuccess;
   cudaError_t e = zero ? cudaMemsetAsync(a.zh1, 0, sizeof(float) * kH * (size_t)a.N, st) : cudaSuccess;
   if (e != cudaSuccess) return e;
-  node_h_z_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
-  node_h_out_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(node_h_z_kernel, node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st, a)) return e_;
+  if (cudaError_t e_ = launch_pdl(node_h_out_kernel, persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st, a)) return e_;
   return cudaGetLastError();
 }
 cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
@@ -551,8 +563,8 @@ cudaError_t launch_node_h_bwd(const NodeHArgs& a, int sms, cudaStream_t st) {
   }
   int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0) return cudaSuccess;
-  node_h_bwd1_kernel<<<persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
-  node_h_bwd2_kernel<<<node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(node_h_bwd1_kernel, persistent_grid(ntiles, 2 * sms), kThreads, kNodeHSmem, st, a)) return e_;
+  if (cudaError_t e_ = launch_pdl(node_h_bwd2_kernel, node_pre_grid(ntiles, a.C + 1, sms), kThreads, kNodeHSmem, st, a)) return e_;
   return cudaGetLastError();
 }
 

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   using SM = FwdSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
   FwdVec* v = reinterpret_cast<FwdVec*>(smem + SM::off_vec);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  pdl_wait();
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
   const uint32_t id_g1 = umma::make_idesc_tf32(128, 64), id_gh = umma::make_idesc_tf32(128, 128);
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   using SM = HeadsSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
   HeadsVec* v = reinterpret_cast<HeadsVec*>(smem + SM::off_vec);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  pdl_wait();
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
   const uint32_t id_gh = umma::make_idesc_tf32(128, 128), id_gu = idesc_tf32(128, 64, 0, 1), id_w = idesc_tf32(128, 96, 1, 1);
@@ -751,6 +755,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   using SM = TrunkSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
   TrunkVec* v = reinterpret_cast<TrunkVec*>(smem + SM::off_vec);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
@@ -774,6 +779,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  pdl_wait();
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
   const uint32_t id_k = idesc_tf32(128, 64, 0, 0), id_mn = idesc_tf32(128, 64, 0, 1);
@@ -1044,7 +1050,7 @@ cudaError_t launch_virtual_fwd_tc(const VirtArgs& a, int sms, cudaStream_t st) {
   const int ntiles = (a.N + TN - 1) / TN;
   if (ntiles == 0) return cudaSuccess;
   const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
-  vtc::virtual_fwd_tc_kernel<CG><<<grid, 128 * CG, bytes, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(vtc::virtual_fwd_tc_kernel<CG>, grid, 128 * CG, bytes, st, a)) return e_;
   return cudaGetLastError();
 }
 
@@ -1067,10 +1073,10 @@ cudaError_t launch_virtual_bwd_tc(const VirtArgs& a, int sms, cudaStream_t st) {
   const int ntiles = (a.N + TN - 1) / TN;
   if (ntiles == 0) return cudaSuccess;
   const int grid = ntiles < sms ? ntiles : sms;
-  vtc::virtual_bwd_heads_tc_kernel<CG><<<grid, 128 * CG, vtc::HeadsSmem::bytes, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(vtc::virtual_bwd_heads_tc_kernel<CG>, grid, 128 * CG, vtc::HeadsSmem::bytes, st, a)) return e_;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  vtc::virtual_bwd_trunk_tc_kernel<CG><<<grid, 128 * CG, vtc::TrunkSmem::bytes, st>>>(a); ++g_launches;
+  if (cudaError_t e_ = launch_pdl(vtc::virtual_bwd_trunk_tc_kernel<CG>, grid, 128 * CG, vtc::TrunkSmem::bytes, st, a)) return e_;
   return cudaGetLastError();
 }
 }  // namespace fegnn
