@@ -146,17 +146,35 @@ constexpr uint32_t kR3 = 256, kR2 = 336, kDXZ = 416;        // [dW3 64 | aux 8],
 //      Every CTA of the main kernel turns them into three power-of-two factors with the bounds
 //        |g3| <= 2 ext * max|gt| * max|w4| * 1.1,  |g2| <= (max|gm| + 64 |g3| max|W3|) * 1.1,  |gz1| <= 64 |g2| max|W2| * 1.1
 //      so that every stored value stays below 2^15.  Loose by design: fp16 keeps full precision over 30 binades.
-__global__ void __launch_bounds__(256) edge_bwd_stats_kernel(int N, int Nl, const float* __restrict__ x,
-                                                             const float* __restrict__ gt, const float* __restrict__ gm,
+__global__ void __launch_bounds__(256) edge_bwd_stats_kernel(int N, int Nl, const float* x, const float* gt, const float* gm,
                                                              unsigned* __restrict__ stats /*[4], zeroed by the caller*/) {
   pdl_trigger();
   pdl_wait();
   float mt = 0.f, mm = 0.f, mx = 0.f;
   const float x0 = x[0], x1 = x[1], x2 = x[2];
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t i = i0; i < (size_t)N * 3; i += stride) mt = fmaxf(mt, fabsf(gt[i]));
-  if (gm != nullptr)
-    for (size_t i = i0; i < (size_t)N * kH; i += stride) mm = fmaxf(mm, fabsf(gm[i]));
+  // 16-byte loads, 4 in flight per thread (the arrays are 16-byte aligned slices of the workspace; a misaligned caller
+  // buffer takes the scalar tail loop for everything)
+  auto amax4 = [&](const float* p, size_t n, float& m) {
+    const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    const size_t n4 = al ? n / 4 : 0;
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    size_t i = i0;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = p4[i], b = p4[i + stride], c = p4[i + 2 * stride], d = p4[i + 3 * stride];
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
+                         fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = p4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (size_t j = n4 * 4 + i0; j < n; j += stride) m = fmaxf(m, fabsf(p[j]));
+  };
+  amax4(gt, (size_t)N * 3, mt);
+  if (gm != nullptr) amax4(gm, (size_t)N * kH, mm);
   for (size_t i = i0; i < (size_t)Nl; i += stride)
     mx = fmaxf(mx, fmaxf(fabsf(x[i * 3] - x0), fmaxf(fabsf(x[i * 3 + 1] - x1), fabsf(x[i * 3 + 2] - x2))));
   for (int o = 16; o > 0; o >>= 1) {
@@ -690,8 +708,9 @@ inline cudaError_t launch_edge_bwd_tc3(const EdgeArgs& a, unsigned* stats, int s
   // the scratch words once per step (FEGNN_F_PREZEROED) may run the backward again on the same block
   cudaError_t e = zero_stats ? cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st) : cudaSuccess;
   if (e != cudaSuccess) return e;
-  int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
-  sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);
+  // at most one block per SM: the final atomicMax is one same-address atomic per block and statistic (they serialise in L2)
+  int sblocks = (int)(((size_t)a.N * kH + 256 * 4 - 1) / (256 * 4));
+  sblocks = sblocks < 1 ? 1 : (sblocks > sms ? sms : sblocks);
   bwd3::edge_bwd_stats_kernel<<<sblocks, 256, 0, st>>>(a.N, a.Nl, a.x, a.gt, a.gm, stats); ++g_launches;
   bwd3::edge_bwd_tc3_kernel<<<grid, bwd3::kThreads3, bytes, st>>>(a, stats); ++g_launches;
   return cudaGetLastError();

@@ -732,8 +732,9 @@ inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int s
   // the scratch words once per step (FEGNN_F_PREZEROED) may run the backward again on the same block
   cudaError_t e = zero_stats ? cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned), st) : cudaSuccess;
   if (e != cudaSuccess) return e;
-  int sblocks = (int)(((size_t)a.N * kH + 256 * 32 - 1) / (256 * 32));
-  sblocks = sblocks < 1 ? 1 : (sblocks > 2 * sms ? 2 * sms : sblocks);
+  // at most one block per SM: the final atomicMax is one same-address atomic per block and statistic (they serialise in L2)
+  int sblocks = (int)(((size_t)a.N * kH + 256 * 4 - 1) / (256 * 4));
+  sblocks = sblocks < 1 ? 1 : (sblocks > sms ? sms : sblocks);
   e = launch_pdl(bwd3::edge_bwd_stats_kernel, sblocks, 256, 0, st, a.N, a.Nl, a.x, a.gt, a.gm, stats);
   if (e != cudaSuccess) return e;
   e = launch_pdl(bwd4::edge_bwd_tc4_kernel<CG>, grid, 256 * CG, bytes, st, a, (const unsigned*)stats);
