@@ -203,6 +203,39 @@ __global__ void final_gx_kernel(int N, const float* __restrict__ gx, const float
 
 }  // namespace
 
+namespace {
+
+// The per-graph phases run one CTA per graph.  fegnn_model_forward / backward put them on a second stream (fork / join
+// with events, all capturable) so they overlap the node- and edge-parallel kernels instead of idling 147 SMs.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream* s = &per_dev[dev];
+  if (s->st == nullptr) {
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return s;
+}
+#define FORK(side, main)                                 \
+  do {                                                   \
+    CK(cudaEventRecord((side)->fork, (main)));           \
+    CK(cudaStreamWaitEvent((side)->st, (side)->fork, 0)); \
+  } while (0)
+#define JOIN(side, main)                                 \
+  do {                                                   \
+    CK(cudaEventRecord((side)->join, (side)->st));       \
+    CK(cudaStreamWaitEvent((main), (side)->join, 0));    \
+  } while (0)
+
+}  // namespace
+
 extern "C" {
 
 const char* fegnn_last_error(void) { return g_err; }
@@ -258,8 +291,13 @@ int fegnn_graph_prep(int32_t N, int32_t E, int32_t B, int32_t Fe, const int64_t*
   RQ(E == 0 || Fe == 0 || (edge_attr && edge_attr_sorted));
   if (workspace_bytes < graph_prep_workspace_bytes(N, E))
     return fail(FEGNN_ENOMEM, "graph_prep workspace %zu < %zu bytes", workspace_bytes, graph_prep_workspace_bytes(N, E));
+  // the counts chain (rowptr, gptr, reciprocals: 8 small launches) and the radix sort chain (7 launches) are independent:
+  // the counts run on the side stream, so the call's critical path is the longer chain, not their sum
+  SideStream* sd = E > 0 ? side_stream() : nullptr;
+  if (sd != nullptr) FORK(sd, S(stream));
   CK(graph_prep(N, E, B, Fe, edge_index, data_batch, edge_attr, perm, rowptr, row, col, batch, gptr,
-                edge_attr_sorted, dinv, inv_nb, workspace, S(stream)));
+                edge_attr_sorted, dinv, inv_nb, workspace, S(stream), sd != nullptr ? sd->st : S(stream)));
+  if (sd != nullptr) JOIN(sd, S(stream));
   return 0;
 }
 
@@ -683,35 +721,6 @@ size_t fegnn_layer_saved_accum_floats(const fegnn_dims* d) {
 }  // extern "C"
 
 namespace {
-
-// The per-graph phases run one CTA per graph.  fegnn_model_forward / backward put them on a second stream (fork / join
-// with events, all capturable) so they overlap the node- and edge-parallel kernels instead of idling 147 SMs.
-struct SideStream {
-  cudaStream_t st = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-SideStream* side_stream() {
-  static SideStream per_dev[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream* s = &per_dev[dev];
-  if (s->st == nullptr) {
-    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-  }
-  return s;
-}
-#define FORK(side, main)                                 \
-  do {                                                   \
-    CK(cudaEventRecord((side)->fork, (main)));           \
-    CK(cudaStreamWaitEvent((side)->st, (side)->fork, 0)); \
-  } while (0)
-#define JOIN(side, main)                                 \
-  do {                                                   \
-    CK(cudaEventRecord((side)->join, (side)->st));       \
-    CK(cudaStreamWaitEvent((main), (side)->join, 0));    \
-  } while (0)
 
 struct ModelWs {
   // per layer l in [0, L]: state entering layer l (index L = outputs)

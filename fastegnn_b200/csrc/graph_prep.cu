@@ -323,12 +323,12 @@ size_t graph_prep_workspace_bytes(int N, int E) {
   size_t G = ((size_t)E + kSortTile - 1) / kSortTile;
   size_t nscan = 256 * G > (size_t)N + 1 ? 256 * G : (size_t)N + 1;
   size_t sums = (nscan + kScanChunk - 1) / kScanChunk + 1;
-  return ((size_t)4 * E + 256 * G + sums + 64) * sizeof(int);
+  return ((size_t)4 * E + 256 * G + 2 * sums + 64) * sizeof(int);      // two scan scratch areas: the two chains overlap
 }
 
 cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, const int64_t* data_batch,
                        const float* edge_attr, int* perm, int* rowptr, int* row, int* col, int* batch, int* gptr,
-                       float* ea_sorted, float* dinv, float* inv_nb, void* ws, cudaStream_t st) {
+                       float* ea_sorted, float* dinv, float* inv_nb, void* ws, cudaStream_t st, cudaStream_t st_counts) {
   const int G = (E + kSortTile - 1) / kSortTile;
   int* keysA = reinterpret_cast<int*>(ws);
   int* keysB = keysA + E;
@@ -337,15 +337,20 @@ cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, c
   int* hist = valsB + E;
   int* sums = hist + (size_t)256 * G;
   cudaError_t e;
-  // counts -> rowptr, gptr, reciprocals
-  if ((e = cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(gptr, 0, sizeof(int) * ((size_t)B + 1), st)) != cudaSuccess) return e;
-  if (E > 0) { count_rows_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, edge_index, rowptr); ++g_launches; }
-  if (N > 0) { batch_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, data_batch, batch, gptr); ++g_launches; }
-  if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums, st)) != cudaSuccess) return e;
-  if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums, st)) != cudaSuccess) return e;
-  if (N > 0) { recip_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, rowptr, dinv); ++g_launches; }
-  if (B > 0) { recip_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, gptr, inv_nb); ++g_launches; }
+  {
+    // counts -> rowptr, gptr, reciprocals (stream st_counts, own scan scratch)
+    size_t nscan = 256 * (size_t)G > (size_t)N + 1 ? 256 * (size_t)G : (size_t)N + 1;
+    int* sums2 = sums + (nscan + kScanChunk - 1) / kScanChunk + 1;
+    cudaStream_t sc = st_counts;
+    if ((e = cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), sc)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(gptr, 0, sizeof(int) * ((size_t)B + 1), sc)) != cudaSuccess) return e;
+    if (E > 0) { count_rows_kernel<<<(E + 255) / 256, 256, 0, sc>>>(E, edge_index, rowptr); ++g_launches; }
+    if (N > 0) { batch_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, data_batch, batch, gptr); ++g_launches; }
+    if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums2, sc)) != cudaSuccess) return e;
+    if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums2, sc)) != cudaSuccess) return e;
+    if (N > 0) { recip_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, rowptr, dinv); ++g_launches; }
+    if (B > 0) { recip_kernel<<<(B + 255) / 256, 256, 0, sc>>>(B, gptr, inv_nb); ++g_launches; }
+  }
   if (E == 0) return cudaGetLastError();
   // radix sort (row, edge id)
   int bits = 1;
