@@ -85,11 +85,19 @@ __global__ void __launch_bounds__(128 * CG, 2) dense_bwd_tc_kernel(const __grid_
   uint8_t *Wm = smem + Smem::off_Wm, *Wk = smem + Smem::off_Wk, *TY = smem + Smem::off_TY, *TX = smem + Smem::off_TX;
 
   // ---- prologue: weight block in both layouts (MN-major for X W; K-major only for the head recompute), vectors
-  for (int i = t; i < kH * kH; i += NT) {
-    const int n = i >> 6, k = i & 63;
-    const float w = b.W[(size_t)n * b.ldw + (size_t)k * b.wks];
-    *reinterpret_cast<float*>(Wm + mn_off(n, k, kH)) = w;
-    if (b.head) *reinterpret_cast<float*>(Wk + umma::tile_off(n, k, kH)) = w;
+  {
+    float w[kH * kH / NT];                       // every load in flight before the first store: one L2 round trip
+#pragma unroll
+    for (int j = 0; j < kH * kH / NT; ++j) {
+      const int i = t + j * NT, n = i >> 6, k = i & 63;
+      w[j] = b.W[(size_t)n * b.ldw + (size_t)k * b.wks];
+    }
+#pragma unroll
+    for (int j = 0; j < kH * kH / NT; ++j) {
+      const int i = t + j * NT, n = i >> 6, k = i & 63;
+      *reinterpret_cast<float*>(Wm + mn_off(n, k, kH)) = w[j];
+      if (b.head) *reinterpret_cast<float*>(Wk + umma::tile_off(n, k, kH)) = w[j];
+    }
   }
   for (int i = t; i < kH; i += NT) {
     v->hb[i] = b.head ? b.hb[i] : 0.f;

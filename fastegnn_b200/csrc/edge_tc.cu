@@ -14,6 +14,7 @@
 
 namespace fegnn {
 
+constexpr int kTcThreads = 256;
 constexpr int kTcMaxFe = 4;   // wider edge attributes use the fp32 FMA kernel (keeps 3 CTAs/SM worth of shared memory)
 
 struct EdgeTcVec {
@@ -40,13 +41,25 @@ struct EdgeTcSmem {
   static constexpr int ctas_per_sm = SPLIT == 3 ? 1 : 3;
 };
 
+// 16-byte chunk c of row n of the reference [64][ld] matrices -> chunk slot of the swizzled tiles.  Both weights are loaded
+// before the first store (one L2 round trip for the prologue).
 template <int SPLIT>
-__device__ __forceinline__ void tc_stage_weight(uint8_t* dst, const float* __restrict__ g, int ld) {
-  // 16-byte chunk c of row n of the reference [64][ld] matrix -> chunk slot of the swizzled tile
-#pragma unroll 8
-  for (int i = threadIdx.x; i < kH * 16; i += blockDim.x) {
-    const int n = i >> 4, c = i & 15;
-    const float4 w = *reinterpret_cast<const float4*>(g + (size_t)n * ld + c * 4);
+__device__ __forceinline__ void tc_stage_weights2(uint8_t* dst0, const float* __restrict__ g0, uint8_t* dst1,
+                                                  const float* __restrict__ g1, int ld) {
+  constexpr int NJ = kH * 16 / kTcThreads;
+  float4 w0[NJ], w1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i = threadIdx.x + j * kTcThreads, n = i >> 4, c = i & 15;
+    w0[j] = *reinterpret_cast<const float4*>(g0 + (size_t)n * ld + c * 4);
+    w1[j] = *reinterpret_cast<const float4*>(g1 + (size_t)n * ld + c * 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * NJ; ++j) {
+    const int jj = j % NJ;
+    const int i = threadIdx.x + jj * kTcThreads, n = i >> 4, c = i & 15;
+    const float4 w = j < NJ ? w0[jj] : w1[jj];
+    uint8_t* dst = j < NJ ? dst0 : dst1;
     const uint32_t o = umma::tile_chunk_off(n, c, kH);
     if (SPLIT == 3) {
       const float4 hi = make_float4(umma::to_tf32(w.x), umma::to_tf32(w.y), umma::to_tf32(w.z), umma::to_tf32(w.w));
@@ -94,7 +107,6 @@ __device__ __forceinline__ void tc_issue_gemm(uint32_t tmem_d, uint64_t a_desc, 
   }
 }
 
-constexpr int kTcThreads = 256;
 
 // SiLU of the tensor-core kernels.  SPLIT == 3 (fp32-grade): z / (1 + 2^(-z log2 e)), two MUFU ops.
 // SPLIT == 1 (TF32-grade): z (0.5 + 0.5 tanh.approx(z/2)), one MUFU op; tanh.approx has ~2^-11 relative error,
@@ -120,8 +132,7 @@ __global__ void __launch_bounds__(kTcThreads, EdgeTcSmem<SPLIT>::ctas_per_sm) ed
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const bool att = a.flags & FEGNN_F_ATTENTION, use_tanh = a.flags & FEGNN_F_TANH, norm = a.flags & FEGNN_F_NORMALIZE;
 
-  tc_stage_weight<SPLIT>(smem + SM::off_W2, a.W2, kH);
-  tc_stage_weight<SPLIT>(smem + SM::off_W3, a.W3, kH);
+  tc_stage_weights2<SPLIT>(smem + SM::off_W2, a.W2, smem + SM::off_W3, a.W3, kH);
   for (int i = t; i < kH; i += kTcThreads) {
     v->wq[i] = a.w1[(size_t)i * a.ld1 + 2 * kH];
     for (int f = 0; f < a.Fe; ++f) v->Wa[f * kH + i] = a.w1[(size_t)i * a.ld1 + 2 * kH + 1 + f];

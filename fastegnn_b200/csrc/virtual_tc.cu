@@ -42,20 +42,37 @@ __device__ __forceinline__ float silu_tc(float z) {
   return z * fmaf(0.5f, th, 0.5f);
 }
 
-// stage a reference [64][ld] weight K-major SWIZZLE_128B into rows [row0, row0+64) of a tile with R rows
+// Weight staging in two phases: every global load of a thread (all weights of the kernel) is in flight before its first
+// shared-memory store -- ONE L2 round trip per prologue.  (A load-store loop per weight serialised 4 round trips per weight:
+// 16 % of the forward kernel's samples at 8 000 nodes, profiles/ncu_top_kernels_r1_final.txt.)
 template <int NT>
-__device__ __forceinline__ void stage_w_kmajor(uint8_t* dst, const float* __restrict__ g, int ld, int row0, int R) {
-  for (int i = threadIdx.x; i < kH * 16; i += NT) {
-    const int n = i >> 4, c = i & 15;
-    *reinterpret_cast<float4*>(dst + umma::tile_chunk_off(row0 + n, c, R)) = *reinterpret_cast<const float4*>(g + (size_t)n * ld + c * 4);
+struct WRegs {
+  float4 v[kH * 16 / NT];
+};
+template <int NT>
+__device__ __forceinline__ void wregs_load(WRegs<NT>& w, const float* __restrict__ g, int ld) {
+#pragma unroll
+  for (int j = 0; j < kH * 16 / NT; ++j) {
+    const int i = threadIdx.x + j * NT, n = i >> 4, c = i & 15;
+    w.v[j] = *reinterpret_cast<const float4*>(g + (size_t)n * ld + c * 4);
+  }
+}
+// a reference [64][ld] weight K-major SWIZZLE_128B into rows [row0, row0+64) of a tile with R rows
+template <int NT>
+__device__ __forceinline__ void wregs_store_kmajor(const WRegs<NT>& w, uint8_t* dst, int row0, int R) {
+#pragma unroll
+  for (int j = 0; j < kH * 16 / NT; ++j) {
+    const int i = threadIdx.x + j * NT, n = i >> 4, c = i & 15;
+    *reinterpret_cast<float4*>(dst + umma::tile_chunk_off(row0 + n, c, R)) = w.v[j];
   }
 }
 // ... and row-major BASE32B (MN-major operand) into rows [row0, row0+64) of a tile with R rows
 template <int NT>
-__device__ __forceinline__ void stage_w_mn(uint8_t* dst, const float* __restrict__ g, int ld, int row0, int R) {
-  for (int i = threadIdx.x; i < kH * 16; i += NT) {
-    const int n = i >> 4, c = i & 15;
-    *reinterpret_cast<float4*>(dst + mn_chunk_off(row0 + n, c, R)) = *reinterpret_cast<const float4*>(g + (size_t)n * ld + c * 4);
+__device__ __forceinline__ void wregs_store_mn(const WRegs<NT>& w, uint8_t* dst, int row0, int R) {
+#pragma unroll
+  for (int j = 0; j < kH * 16 / NT; ++j) {
+    const int i = threadIdx.x + j * NT, n = i >> 4, c = i & 15;
+    *reinterpret_cast<float4*>(dst + mn_chunk_off(row0 + n, c, R)) = w.v[j];
   }
 }
 
@@ -157,9 +174,15 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   const int C = a.C, TN = kTM / C;
   const bool use_tanh = a.flags & FEGNN_F_TANH, grav = a.flags & FEGNN_F_GRAVITY;
 
-  stage_w_kmajor<NT>(smem + SM::off_V2, a.V2, kH, 0, kH);
-  stage_w_kmajor<NT>(smem + SM::off_WH, a.Wxv, kH, 0, 2 * kH);
-  stage_w_kmajor<NT>(smem + SM::off_WH, a.WX, kH, kH, 2 * kH);
+  {
+    WRegs<NT> w0, w1, w2;
+    wregs_load<NT>(w0, a.V2, kH);
+    wregs_load<NT>(w1, a.Wxv, kH);
+    wregs_load<NT>(w2, a.WX, kH);
+    wregs_store_kmajor<NT>(w0, smem + SM::off_V2, 0, kH);
+    wregs_store_kmajor<NT>(w1, smem + SM::off_WH, 0, 2 * kH);
+    wregs_store_kmajor<NT>(w2, smem + SM::off_WH, kH, 2 * kH);
+  }
   for (int i = t; i < kH; i += NT) {
     v->vr[i] = a.wv1[(size_t)i * a.ldv + 2 * kH];
     v->c2[i] = a.c2[i];
@@ -451,10 +474,15 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   const int C = a.C, TN = kTM / C;
   const bool use_tanh = a.flags & FEGNN_F_TANH, grav = a.flags & FEGNN_F_GRAVITY;
 
-  stage_w_kmajor<NT>(smem + SM::off_WHk, a.Wxv, kH, 0, 2 * kH);
-  stage_w_kmajor<NT>(smem + SM::off_WHk, a.WX, kH, kH, 2 * kH);
-  stage_w_mn<NT>(smem + SM::off_WHm, a.Wxv, kH, 0, 2 * kH);
-  stage_w_mn<NT>(smem + SM::off_WHm, a.WX, kH, kH, 2 * kH);
+  {
+    WRegs<NT> w1, w2;
+    wregs_load<NT>(w1, a.Wxv, kH);
+    wregs_load<NT>(w2, a.WX, kH);
+    wregs_store_kmajor<NT>(w1, smem + SM::off_WHk, 0, 2 * kH);
+    wregs_store_kmajor<NT>(w2, smem + SM::off_WHk, kH, 2 * kH);
+    wregs_store_mn<NT>(w1, smem + SM::off_WHm, 0, 2 * kH);
+    wregs_store_mn<NT>(w2, smem + SM::off_WHm, kH, 2 * kH);
+  }
   for (int i = t; i < kH; i += NT) {
     v->bh[i] = a.bxv[i]; v->bh[kH + i] = a.bX[i];
     v->wh[i] = a.wxv[i]; v->wh[kH + i] = a.wX[i];
@@ -761,8 +789,12 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
   const int C = a.C, TN = kTM / C;
 
-  stage_w_kmajor<NT>(smem + SM::off_V2k, a.V2, kH, 0, kH);
-  stage_w_mn<NT>(smem + SM::off_V2m, a.V2, kH, 0, kH);
+  {
+    WRegs<NT> w0;
+    wregs_load<NT>(w0, a.V2, kH);
+    wregs_store_kmajor<NT>(w0, smem + SM::off_V2k, 0, kH);
+    wregs_store_mn<NT>(w0, smem + SM::off_V2m, 0, kH);
+  }
   for (int i = t; i < kH; i += NT) {
     v->vr[i] = a.wv1[(size_t)i * a.ldv + 2 * kH];
     v->c2[i] = a.c2[i];
