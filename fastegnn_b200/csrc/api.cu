@@ -74,11 +74,11 @@ int g_virt_bwd_mode = 1;
 // 2.2e-4 on equivariant_test.py's U(0,10) inputs against its atol of 1e-4.
 int g_node_fwd_mode = 0;
 // per-node dense phases of the BACKWARD pass (node_pre_backward, node_h_backward): 0 = fp32 FMA kernels, 1 = tcgen05 TF32
-// (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default): tcgen05 from kNodeTcMinN nodes on.
-// Below that the phase is a latency chain of 1-2 tiles per CTA and the fp32 kernels (more, smaller work items) are as
-// fast or faster: measured at 8 000 nodes 54 + 46 us (fp32) against 63 + 49 us (tcgen05) per layer.
+// (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default) = 1 today: up to two node tiles per SM
+// the per-tile kernel walks the weight blocks (measured at 8 000 nodes: step 1.380 ms against 1.416 ms with the fp32 kernels),
+// above that the (tile, block) kernel (-4 % step at 160 000 nodes).
 int g_node_bwd_mode = 2;
-constexpr int kNodeTcMinN = 32768;
+constexpr int kNodeTcMinN = 0;
 inline bool node_bwd_tc(int N) { return g_node_bwd_mode == 1 || (g_node_bwd_mode == 2 && N >= kNodeTcMinN); }
 
 int sm_count() {

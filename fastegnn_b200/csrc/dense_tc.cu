@@ -23,6 +23,7 @@ using bwd2::gemm_ts_mn;
 using bwd2::idesc_tf32;
 using bwd2::make_desc_mn;
 using bwd2::mn_chunk_off;
+using bwd2::mn_load_row;
 using bwd2::mn_off;
 using bwd2::mn_store_row;
 using bwd2::tmem_ld;
@@ -30,6 +31,7 @@ using bwd2::tmem_st;
 using bwd2::tmem_st_wait;
 
 constexpr int kMaxBlk = FEGNN_MAX_C + 2;
+constexpr int kRowsMaxTilesPerSm = 2;      // up to this many node tiles per SM the per-tile kernel (below) is used
 
 struct Blk {
   // X rows [N][64] (row stride ldx floats), optional per-row scale: the gradient-side operand
@@ -299,6 +301,334 @@ __global__ void __launch_bounds__(128 * CG, 2) dense_bwd_tc_kernel(const __grid_
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------- small-N form
+// The (tile, block) decomposition above pays its fixed costs per work item: at 8 000 nodes (63 tiles) every CTA stages a weight
+// block, allocates tensor memory, handles ONE tile and flushes 4 096 weight-gradient atomics -- and `gh += G_b W_b` goes through
+// global atomics once per block.  Here a CTA owns a node tile and WALKS the blocks:
+//   * the data gradients of consecutive blocks that add into the same D (node_pre_backward: gh) accumulate in ONE tensor-memory
+//     accumulator across the blocks -- one epilogue per tile instead of one red.add pass per block;
+//   * Y (= h for every node_pre block) is loaded once per tile when consecutive blocks share it;
+//   * software pipeline over the blocks: the weight block and the X / Y rows of block b + 1 are in flight (registers) while the
+//     MMAs of block b run and the weight gradient of block b - 1 is flushed; weight tiles, X tiles, Y tiles and the weight-gradient
+//     accumulators are double-buffered;
+//   * bias column sums come from a column walk over the X tile under the MMA (was 160 shuffles per thread).
+// Used below kRowsMaxTiles tiles per SM-pair (small graphs); the (tile, block) kernel stays for large N, where its weights are
+// staged once per CTA for many tiles.
+struct VecR {
+  float hb[kH], hw2[kH];
+  float cb[2][kH], cw2[kH];
+  float cb2;
+  uint64_t bar[4];                // 0 head recompute, 1 data gradient, 2 / 3 weight gradient of slot 0 / 1
+  uint32_t tmem_slot;
+};
+struct SmemR {
+  static constexpr int kW = kH * kH * 4, kT = kTM * kH * 4;
+  static constexpr int off_Wm = 0;                 // [2] MN-major weight tiles
+  static constexpr int off_Wk = 2 * kW;            // K-major copy (head recompute only)
+  static constexpr int off_TY = 3 * kW;            // [2]
+  static constexpr int off_TX = 3 * kW + 2 * kT;   // [2]
+  static constexpr int off_vec = 3 * kW + 4 * kT;
+  static constexpr size_t bytes = off_vec + sizeof(VecR) + 1024;
+};
+constexpr uint32_t kR_ACC = 0, kR_OPA = 64, kR_RW = 128;      // + 64 * slot ; 256 columns
+
+__device__ __forceinline__ void gemm_ts_mn_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t dW, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    bwd2::mma_ts(tmem_d, tmem_a + ks * 8, desc_advance(dW, ks * 1024), idesc, (ks > 0 || accumulate) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_constant__ Args a) {
+  constexpr int NT = 256, CG = 2, CPT = kH / CG, NWR = kH * kH / NT;     // 16 weight words per thread and block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
+  VecR* v = reinterpret_cast<VecR*>(smem + SmemR::off_vec);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
+  uint8_t* Wk = smem + SmemR::off_Wk;
+  auto Wm = [&](int s_) { return smem + SmemR::off_Wm + s_ * SmemR::kW; };
+  auto TY = [&](int s_) { return smem + SmemR::off_TY + s_ * SmemR::kT; };
+  auto TX = [&](int s_) { return smem + SmemR::off_TX + s_ * SmemR::kT; };
+
+  float wreg[NWR];
+  auto load_w = [&](const Blk& b) {             // every load in flight before anything is stored
+#pragma unroll
+    for (int j = 0; j < NWR; ++j) {
+      const int i = t + j * NT, n = i >> 6, k = i & 63;
+      wreg[j] = b.W[(size_t)n * b.ldw + (size_t)k * b.wks];
+    }
+  };
+  auto store_w = [&](const Blk& b, int s_) {
+#pragma unroll
+    for (int j = 0; j < NWR; ++j) {
+      const int i = t + j * NT, n = i >> 6, k = i & 63;
+      *reinterpret_cast<float*>(Wm(s_) + mn_off(n, k, kH)) = wreg[j];
+      if (b.head) *reinterpret_cast<float*>(Wk + umma::tile_off(n, k, kH)) = wreg[j];
+    }
+  };
+  // ---- prologue (weights only): block 0's weight tile, vectors, barriers, tensor memory
+  load_w(a.blk[0]);
+  for (int i = t; i < kH; i += NT) {
+    v->cb[0][i] = 0.f; v->cb[1][i] = 0.f; v->cw2[i] = 0.f;
+  }
+  if (t == 0) {
+    v->cb2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&v->bar[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<256>(&v->tmem_slot);
+  store_w(a.blk[0], 0);
+  umma::fence_smem_to_async();
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  pdl_wait();
+  const uint32_t tmem = v->tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
+  const uint32_t id_ts_k = idesc_tf32(128, 64, 0, 0), id_ts_mn = idesc_tf32(128, 64, 0, 1), id_wg = idesc_tf32(64, 64, 1, 1);
+  const uint64_t dWk = umma::make_desc(umma::smem_u32(Wk));
+  uint32_t ph_r = 0, ph_d = 0, ph_w[2] = {0, 0};
+
+  // Operand rows of a block: the row owner (= tensor-memory lane) fetches its CPT columns of X (nothing for a head block) and,
+  // when `want_y`, of Y.  (A coalesced half-warp-per-row variant through shared memory was measured slower here: it needs a
+  // second barrier and a shared-memory round trip per block, and these launches are latency-, not LSU-bound.)
+  float xr[CPT], yr[CPT];
+  auto load_rows = [&](const Blk& b, int r, bool valid, bool want_y) {
+    if (want_y) {
+      if (valid) {
+        const float4* src = reinterpret_cast<const float4*>(b.Y + (size_t)r * b.ldy + c0);
+#pragma unroll
+        for (int ch = 0; ch < CPT / 4; ++ch) {
+          const float4 q = src[ch];
+          yr[ch * 4] = q.x; yr[ch * 4 + 1] = q.y; yr[ch * 4 + 2] = q.z; yr[ch * 4 + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) yr[j] = 0.f;
+      }
+    }
+    if (!b.head) {
+      if (valid) {
+        const float4* src = reinterpret_cast<const float4*>(b.X + (size_t)r * b.ldx + c0);
+#pragma unroll
+        for (int ch = 0; ch < CPT / 4; ++ch) {
+          const float4 q = src[ch];
+          xr[ch * 4] = q.x; xr[ch * 4 + 1] = q.y; xr[ch * 4 + 2] = q.z; xr[ch * 4 + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) xr[j] = 0.f;
+      }
+    }
+  };
+  auto same_y = [&](int b) {                    // block b reads the Y tile block b - 1 left in shared memory
+    if (b == 0) return false;
+    const Blk &p = a.blk[b - 1], &q = a.blk[b];
+    return p.Y == q.Y && p.ldy == q.ldy && p.yscale == q.yscale && p.ysilu == q.ysilu;
+  };
+  auto chain = [&](int b) {                     // block b + 1 adds its data gradient to the same D as block b
+    if (b + 1 >= a.nblk) return false;
+    const Blk &p = a.blk[b], &q = a.blk[b + 1];
+    return p.dmode == 2 && q.dmode == 2 && p.D == q.D && p.ldd == q.ldd && p.dz == q.dz && p.dscale == q.dscale;
+  };
+  // weight gradient of block b (slot s_) : tensor memory -> global, bias sums
+  auto flush_w = [&](int b, int s_) {
+    const Blk& blk = a.blk[b];
+    if (blk.gW != nullptr) {
+      umma::mbar_wait(&v->bar[2 + s_], ph_w[s_]);
+      umma::fence_after();
+      ph_w[s_] ^= 1;
+      float w[CPT];
+      tmem_ld<CPT>(tlane + kR_RW + 64 * s_, w);
+      if (lane < 16) {
+        const int n = quarter * 16 + lane;
+        float* dst = blk.gW + (size_t)n * blk.ldw + (size_t)c0 * blk.wks;
+        if (blk.wks == 1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < CPT; j += 4) atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) atomicAdd(dst + (size_t)j * blk.wks, w[j]);
+        }
+      }
+      umma::fence_before();
+    }
+    if (blk.gb != nullptr && t < kH) {
+      atomicAdd(blk.gb + t, v->cb[s_][t]);
+      v->cb[s_][t] = 0.f;
+    }
+  };
+
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r = tile * kTM + row;
+    const bool valid = r < a.N;
+    int ys = 1;                                   // Y slot of the previous block (flipped before the first store)
+    load_rows(a.blk[0], r, valid, true);
+    if (tile != (int)blockIdx.x) {                // a later tile of this CTA: block 0's weights again (slot 0 is free: all flushed)
+      load_w(a.blk[0]);
+      store_w(a.blk[0], 0);
+    }
+    for (int b = 0; b < a.nblk; ++b) {
+      const Blk& blk = a.blk[b];
+      const int s_ = b & 1;
+      const bool new_y = !same_y(b);
+      // ---- Y rows -> TY[ys]
+      if (new_y) {
+        ys ^= 1;
+        const float sc = (valid && blk.yscale != nullptr) ? blk.yscale[r] : 1.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          yr[j] *= sc;
+          if (blk.ysilu) yr[j] = valid ? silu_f(yr[j]) : 0.f;
+        }
+        mn_store_row<CPT>(TY(ys), row, cg, yr);
+      }
+      const bool more = b + 1 < a.nblk;
+      if (blk.head) {
+        // z = Y W^T on the tensor core, X = gs w2 silu'(z + b)
+        if (t < kH) { v->hb[t] = blk.hb[t]; v->hw2[t] = blk.hw2[t]; }
+        if (!new_y) mn_load_row<CPT>(TY(ys), row, cg, yr);
+        tmem_st<CPT>(tlane + kR_OPA, yr);
+        tmem_st_wait();
+        umma::fence_smem_to_async();
+        umma::fence_before();
+        __syncthreads();
+        if (warp == 0) {
+          umma::fence_after();
+          if (umma::elect_one()) {
+            // into this slot's weight-gradient columns (free: block b - 2 was flushed) -- the data-gradient accumulator
+            // may hold the running sum of a chain
+            gemm_ts_kmajor(tmem + kR_RW + 64 * s_, tmem + kR_OPA, dWk, id_ts_k);
+            umma::commit(&v->bar[0]);
+          }
+          __syncwarp();
+        }
+        umma::mbar_wait(&v->bar[0], ph_r);
+        umma::fence_after();
+        ph_r ^= 1;
+        tmem_ld<CPT>(tlane + kR_RW + 64 * s_, xr);
+        const float g = valid ? blk.gs[r] : 0.f;
+        float aw[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          float av, d;
+          silu_grad_f(xr[j] + v->hb[c0 + j], av, d);
+          aw[j] = g * av;
+          xr[j] = g * v->hw2[c0 + j] * d;
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          float sum = aw[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) atomicAdd(&v->cw2[c0 + j], sum);
+        }
+        if (cg == 0) {
+          float sum = g;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) atomicAdd(&v->cb2, sum);
+        }
+        umma::fence_before();
+      } else if (valid && blk.xscale != nullptr) {
+        const float sc = blk.xscale[r];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) xr[j] *= sc;
+      }
+      // ---- X row -> A operand (tensor memory) and TX[s_]; the data gradient of block b - 1 has left the A operand
+      tmem_st<CPT>(tlane + kR_OPA, xr);
+      mn_store_row<CPT>(TX(s_), row, cg, xr);
+      tmem_st_wait();
+      // the operands of block b + 1 (weight block, X / Y rows) go in flight now and land under the MMAs / epilogue of this one
+      if (more) {
+        load_w(a.blk[b + 1]);
+        load_rows(a.blk[b + 1], r, valid, !same_y(b + 1));
+      }
+      umma::fence_smem_to_async();
+      umma::fence_before();
+      __syncthreads();
+      const bool acc_in = b > 0 && chain(b - 1);
+      if (warp == 0) {
+        umma::fence_after();
+        if (umma::elect_one()) {
+          const uint64_t dWm = make_desc_mn(umma::smem_u32(Wm(s_)), kH * 128);
+          if (blk.dmode != 0) gemm_ts_mn_acc(tmem + kR_ACC, tmem + kR_OPA, dWm, id_ts_mn, acc_in);      // D (+)= X W
+          umma::commit(&v->bar[1]);
+          if (blk.gW != nullptr) {
+            const uint64_t dTX = make_desc_mn(umma::smem_u32(TX(s_)), kTM * 128), dTY = make_desc_mn(umma::smem_u32(TY(ys)), kTM * 128);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks)                                   // dW = X^T Y over the 128 rows
+              umma::mma_tf32(tmem + kR_RW + 64 * s_, desc_advance(dTX, ks * 1024), desc_advance(dTY, ks * 1024), id_wg, ks > 0 ? 1u : 0u);
+            umma::commit(&v->bar[2 + s_]);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- under the MMAs: bias column sums of this block, flush of block b - 1
+      if (blk.gb != nullptr) {
+        const int col = t & 63, part = t >> 6;
+        float sum = 0.f;
+#pragma unroll 8
+        for (int rr = part * 32; rr < part * 32 + 32; ++rr) sum += *reinterpret_cast<const float*>(TX(s_) + mn_off(rr, col, kTM));
+        atomicAdd(&v->cb[s_][col], sum);
+      }
+      if (b > 0) flush_w(b - 1, s_ ^ 1);           // also frees TX[s_ ^ 1]
+      // ---- the data gradient: wait (the A operand and, at the end of a chain, the accumulator are reused next)
+      umma::mbar_wait(&v->bar[1], ph_d);
+      umma::fence_after();
+      ph_d ^= 1;
+      if (blk.dmode != 0 && !chain(b)) {
+        float d[CPT];
+        tmem_ld<CPT>(tlane + kR_ACC, d);
+        if (valid) {
+          if (blk.dz != nullptr) {
+            const float4* zr = reinterpret_cast<const float4*>(blk.dz + (size_t)r * kH + c0);
+#pragma unroll
+            for (int ch = 0; ch < CPT / 4; ++ch) {
+              const float4 z = zr[ch];
+              float av, e0, e1, e2, e3;
+              silu_grad_f(z.x, av, e0); silu_grad_f(z.y, av, e1); silu_grad_f(z.z, av, e2); silu_grad_f(z.w, av, e3);
+              d[ch * 4] *= e0; d[ch * 4 + 1] *= e1; d[ch * 4 + 2] *= e2; d[ch * 4 + 3] *= e3;
+            }
+          }
+          const float sc = blk.dscale != nullptr ? blk.dscale[r] : 1.f;
+          float4* dst = reinterpret_cast<float4*>(blk.D + (size_t)r * blk.ldd + c0);
+#pragma unroll
+          for (int ch = 0; ch < CPT / 4; ++ch) {
+            const float4 q = make_float4(d[ch * 4] * sc, d[ch * 4 + 1] * sc, d[ch * 4 + 2] * sc, d[ch * 4 + 3] * sc);
+            if (blk.dmode == 2) atomicAdd(dst + ch, q);
+            else dst[ch] = q;
+          }
+        }
+      }
+      if (more) store_w(a.blk[b + 1], s_ ^ 1);     // Wm[s_ ^ 1]: last read by the data gradient of block b - 1 (waited)
+      umma::fence_before();
+      if (blk.head) {
+        __syncthreads();                           // cw2 / cb2 complete
+        if (t < kH) {
+          if (blk.g_hw2 != nullptr) atomicAdd(blk.g_hw2 + t, v->cw2[t]);
+          v->cw2[t] = 0.f;
+        }
+        if (t == 0) {
+          if (blk.g_hb2 != nullptr) atomicAdd(blk.g_hb2, v->cb2);
+          v->cb2 = 0.f;
+        }
+      }
+    }
+    __syncthreads();                               // bias sums of the last block are complete
+    flush_w(a.nblk - 1, (a.nblk - 1) & 1);
+    __syncthreads();
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+
 }  // namespace dtc
 
 cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
@@ -311,6 +641,17 @@ cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
   }
   const int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0 || a.nblk == 0) return cudaSuccess;
+  if (ntiles <= dtc::kRowsMaxTilesPerSm * sms) {   // small graphs: one CTA per node tile walks the blocks
+    static DevOnce attr2;
+    if (!attr2.get()) {
+      cudaError_t e = cudaFuncSetAttribute(dtc::dense_bwd_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)dtc::SmemR::bytes);
+      if (e != cudaSuccess) return e;
+      attr2.set();
+    }
+    if (cudaError_t e_ = launch_pdl(dtc::dense_bwd_tc_rows_kernel, ntiles < sms ? ntiles : sms, 256, dtc::SmemR::bytes, st, a)) return e_;
+    return cudaGetLastError();
+  }
   int per = (2 * sms) / a.nblk;                   // CTAs per block at 2 CTAs / SM
   per = per < 1 ? 1 : (per > ntiles ? ntiles : per);
   if (cudaError_t e_ = launch_pdl(dtc::dense_bwd_tc_kernel<2>, per * a.nblk, 256, dtc::Smem::bytes, st, a)) return e_;
