@@ -293,6 +293,23 @@ struct DevOnce {
   }
 };
 
+// Column sums over the 32 lanes of a warp for 32 per-lane values: lane L returns sum over the lanes of v[L].  Each round
+// keeps the half of the columns whose index bit matches the lane's and trades the other half with the partner lane:
+// 16 + 8 + 4 + 2 + 1 = 31 shuffles (a butterfly per column costs 160).  v is clobbered.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int n = 16; n >= 1; n >>= 1) {
+    const bool hi = lane & n;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float send = hi ? v[j] : v[j + n];
+      const float keep = hi ? v[j + n] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+    }
+  }
+  return v[0];
+}
+
 // Number of kernels this library has launched (host counter; read through fegnn_launch_count()).
 inline unsigned long long g_launches = 0;
 
@@ -308,11 +325,11 @@ inline bool pdl_enabled() {
   return on;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(block, 1, 1);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr = {};

@@ -56,6 +56,9 @@ struct Blk {
 
 struct Args {
   int N, nblk;
+  unsigned same_y_mask, chain_mask;   // bit b: block b reads block b - 1's Y tile / block b + 1 adds into block b's D (host-computed)
+  int nsplit;                  // per-tile kernel: the block list is cut into nsplit ranges, one CTA per (tile, range)
+  int split[kMaxBlk + 1];      // range s = blocks [split[s], split[s + 1])
   Blk blk[kMaxBlk];
 };
 
@@ -353,6 +356,8 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
   auto TY = [&](int s_) { return smem + SmemR::off_TY + s_ * SmemR::kT; };
   auto TX = [&](int s_) { return smem + SmemR::off_TX + s_ * SmemR::kT; };
 
+  // block range of this CTA (blockIdx.y): at a few dozen tiles the SMs left over take a share of the blocks instead of idling
+  const int b0 = a.nsplit > 1 ? a.split[blockIdx.y] : 0, b1 = a.nsplit > 1 ? a.split[blockIdx.y + 1] : a.nblk;
   float wreg[NWR];
   auto load_w = [&](const Blk& b) {             // every load in flight before anything is stored
 #pragma unroll
@@ -369,8 +374,8 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
       if (b.head) *reinterpret_cast<float*>(Wk + umma::tile_off(n, k, kH)) = wreg[j];
     }
   };
-  // ---- prologue (weights only): block 0's weight tile, vectors, barriers, tensor memory
-  load_w(a.blk[0]);
+  // ---- prologue (weights only): the first block's weight tile, vectors, barriers, tensor memory
+  load_w(a.blk[b0]);
   for (int i = t; i < kH; i += NT) {
     v->cb[0][i] = 0.f; v->cb[1][i] = 0.f; v->cw2[i] = 0.f;
   }
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc<256>(&v->tmem_slot);
-  store_w(a.blk[0], 0);
+  store_w(a.blk[b0], 0);
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
@@ -425,16 +430,8 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
       }
     }
   };
-  auto same_y = [&](int b) {                    // block b reads the Y tile block b - 1 left in shared memory
-    if (b == 0) return false;
-    const Blk &p = a.blk[b - 1], &q = a.blk[b];
-    return p.Y == q.Y && p.ldy == q.ldy && p.yscale == q.yscale && p.ysilu == q.ysilu;
-  };
-  auto chain = [&](int b) {                     // block b + 1 adds its data gradient to the same D as block b
-    if (b + 1 >= a.nblk) return false;
-    const Blk &p = a.blk[b], &q = a.blk[b + 1];
-    return p.dmode == 2 && q.dmode == 2 && p.D == q.D && p.ldd == q.ldd && p.dz == q.dz && p.dscale == q.dscale;
-  };
+  auto same_y = [&](int b) { return b != b0 && ((a.same_y_mask >> b) & 1u); };      // block b reads the Y tile block b - 1 left
+  auto chain = [&](int b) { return b + 1 < b1 && ((a.chain_mask >> b) & 1u); };       // block b + 1 adds to the same D as block b
   // weight gradient of block b (slot s_) : tensor memory -> global, bias sums
   auto flush_w = [&](int b, int s_) {
     const Blk& blk = a.blk[b];
@@ -468,14 +465,14 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
     const int r = tile * kTM + row;
     const bool valid = r < a.N;
     int ys = 1;                                   // Y slot of the previous block (flipped before the first store)
-    load_rows(a.blk[0], r, valid, true);
-    if (tile != (int)blockIdx.x) {                // a later tile of this CTA: block 0's weights again (slot 0 is free: all flushed)
-      load_w(a.blk[0]);
-      store_w(a.blk[0], 0);
+    load_rows(a.blk[b0], r, valid, true);
+    if (tile != (int)blockIdx.x) {                // a later tile of this CTA: the first block's weights again (slot 0 is free: all flushed)
+      load_w(a.blk[b0]);
+      store_w(a.blk[b0], 0);
     }
-    for (int b = 0; b < a.nblk; ++b) {
+    for (int b = b0; b < b1; ++b) {
       const Blk& blk = a.blk[b];
-      const int s_ = b & 1;
+      const int s_ = (b - b0) & 1;
       const bool new_y = !same_y(b);
       // ---- Y rows -> TY[ys]
       if (new_y) {
@@ -488,7 +485,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         }
         mn_store_row<CPT>(TY(ys), row, cg, yr);
       }
-      const bool more = b + 1 < a.nblk;
+      const bool more = b + 1 < b1;
       if (blk.head) {
         // z = Y W^T on the tensor core, X = gs w2 silu'(z + b)
         if (t < kH) { v->hb[t] = blk.hb[t]; v->hw2[t] = blk.hw2[t]; }
@@ -521,12 +518,10 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
           aw[j] = g * av;
           xr[j] = g * v->hw2[c0 + j] * d;
         }
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-          float sum = aw[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) atomicAdd(&v->cw2[c0 + j], sum);
+        {
+          static_assert(CPT == 32, "one 32-column transposed reduction per warp");
+          const float tot = warp_colsum32(aw, lane);          // 31 shuffles (a butterfly per column: 160)
+          atomicAdd(&v->cw2[c0 + lane], tot);
         }
         if (cg == 0) {
           float sum = g;
@@ -552,7 +547,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
       umma::fence_smem_to_async();
       umma::fence_before();
       __syncthreads();
-      const bool acc_in = b > 0 && chain(b - 1);
+      const bool acc_in = b > b0 && chain(b - 1);
       if (warp == 0) {
         umma::fence_after();
         if (umma::elect_one()) {
@@ -577,7 +572,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         for (int rr = part * 32; rr < part * 32 + 32; ++rr) sum += *reinterpret_cast<const float*>(TX(s_) + mn_off(rr, col, kTM));
         atomicAdd(&v->cb[s_][col], sum);
       }
-      if (b > 0) flush_w(b - 1, s_ ^ 1);           // also frees TX[s_ ^ 1]
+      if (b > b0) flush_w(b - 1, s_ ^ 1);          // also frees TX[s_ ^ 1]
       // ---- the data gradient: wait (the A operand and, at the end of a chain, the accumulator are reused next)
       umma::mbar_wait(&v->bar[1], ph_d);
       umma::fence_after();
@@ -621,7 +616,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
       }
     }
     __syncthreads();                               // bias sums of the last block are complete
-    flush_w(a.nblk - 1, (a.nblk - 1) & 1);
+    flush_w(b1 - 1, (b1 - 1 - b0) & 1);
     __syncthreads();
   }
   umma::fence_before();
@@ -631,7 +626,16 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
 
 }  // namespace dtc
 
-cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
+cudaError_t launch_dense_bwd_tc(const dtc::Args& a_in, int sms, cudaStream_t st) {
+  dtc::Args a = a_in;
+  a.nsplit = 1;
+  a.same_y_mask = a.chain_mask = 0;
+  for (int b = 1; b < a.nblk; ++b) {
+    const dtc::Blk &p = a.blk[b - 1], &q = a.blk[b];
+    if (p.Y == q.Y && p.ldy == q.ldy && p.yscale == q.yscale && p.ysilu == q.ysilu) a.same_y_mask |= 1u << b;
+    if (p.dmode == 2 && q.dmode == 2 && p.D == q.D && p.ldd == q.ldd && p.dz == q.dz && p.dscale == q.dscale)
+      a.chain_mask |= 1u << (b - 1);
+  }
   static DevOnce attr;
   if (!attr.get()) {
     cudaError_t e = cudaFuncSetAttribute(dtc::dense_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -649,7 +653,26 @@ cudaError_t launch_dense_bwd_tc(const dtc::Args& a, int sms, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       attr2.set();
     }
-    if (cudaError_t e_ = launch_pdl(dtc::dense_bwd_tc_rows_kernel, ntiles < sms ? ntiles : sms, 256, dtc::SmemR::bytes, st, a)) return e_;
+    // Fewer tiles than SMs: cut the block list into ranges of about equal cost (a head block counts twice: it has the
+    // recompute round in front of its data gradient) and launch one CTA per (tile, range).  Ranges that add into the same D do
+    // so with red.add, exactly as consecutive chains of one CTA do.
+    int nsplit = ntiles < sms ? sms / ntiles : 1;
+    if (nsplit > a.nblk) nsplit = a.nblk;
+    if (const char* e = getenv("FEGNN_DENSE_SPLIT")) { const int v_ = atoi(e); if (v_ >= 1 && v_ <= a.nblk) nsplit = v_; }
+    if (nsplit > 1) {
+      int cost[dtc::kMaxBlk], total = 0;
+      for (int b = 0; b < a.nblk; ++b) { cost[b] = a.blk[b].head ? 2 : 1; total += cost[b]; }
+      int s_ = 0, acc = 0;
+      a.split[0] = 0;
+      for (int b = 0; b < a.nblk && s_ + 1 < nsplit; ++b) {
+        acc += cost[b];
+        // close range s_ after block b once it holds its share, keeping one block for every later range
+        if (acc * nsplit >= total * (s_ + 1) || a.nblk - (b + 1) == nsplit - (s_ + 1)) a.split[++s_] = b + 1;
+      }
+      while (s_ < nsplit) a.split[++s_] = a.nblk;
+      a.nsplit = nsplit;
+    }
+    if (cudaError_t e_ = launch_pdl(dtc::dense_bwd_tc_rows_kernel, dim3(ntiles < sms ? ntiles : sms, a.nsplit), dim3(256), dtc::SmemR::bytes, st, a)) return e_;
     return cudaGetLastError();
   }
   int per = (2 * sms) / a.nblk;                   // CTAs per block at 2 CTAs / SM
