@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libfegnn.so")
+LIB_PATH = os.environ.get("FEGNN_LIB") or os.path.join(HERE, "_C", "libfegnn.so")     # FEGNN_LIB: an instrumented build (tools/)
 
 H = 64
 MAX_C = 16

@@ -327,11 +327,13 @@ struct VecR {
 };
 struct SmemR {
   static constexpr int kW = kH * kH * 4, kT = kTM * kH * 4;
+  static constexpr int kFS = kH * 65 * 4;          // weight-gradient staging [64][65] (transposed through shared memory)
   static constexpr int off_Wm = 0;                 // [2] MN-major weight tiles
   static constexpr int off_Wk = 2 * kW;            // K-major copy (head recompute only)
   static constexpr int off_TY = 3 * kW;            // [2]
   static constexpr int off_TX = 3 * kW + 2 * kT;   // [2]
-  static constexpr int off_vec = 3 * kW + 4 * kT;
+  static constexpr int off_FS = 3 * kW + 4 * kT;
+  static constexpr int off_vec = off_FS + ((kFS + 15) / 16) * 16;
   static constexpr size_t bytes = off_vec + sizeof(VecR) + 1024;
 };
 constexpr uint32_t kR_ACC = 0, kR_OPA = 64, kR_RW = 128;      // + 64 * slot ; 256 columns
@@ -341,9 +343,33 @@ __device__ __forceinline__ void gemm_ts_mn_acc(uint32_t tmem_d, uint32_t tmem_a,
   for (int ks = 0; ks < 8; ++ks)
     bwd2::mma_ts(tmem_d, tmem_a + ks * 8, desc_advance(dW, ks * 1024), idesc, (ks > 0 || accumulate) ? 1u : 0u);
 }
+// 16 bytes global -> shared without a register stop; bytes = 0 writes zeros (rows past N)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(umma::smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+#ifdef FEGNN_TRACE
+#define TR(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0) tr_[(i)] = clock64(); } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
+// Data movement (measured with clock64 stamps, tools/gpu_r2_ab.sh: the row-owner form -- every thread loading / storing ITS
+// row -- made each warp-wide 16-byte access touch 32 cache lines; the LSU spent ~4 000 cycles per operand tile pair and as
+// many per weight-gradient flush, two thirds of the kernel at 8 000 nodes):
+//   * operand rows travel global -> shared with cp.async in row-chunk order (a warp-wide copy covers 2 rows x 256 contiguous
+//     bytes) straight into the swizzled MN-major tiles; the row owner then reads ITS row back from shared memory
+//     (conflict-free) for the tensor-memory A operand and rewrites it only where a scale / SiLU applies;
+//   * the weight gradient leaves tensor memory through a [64][65] staging tile and goes out with the lanes along k
+//     (128 contiguous bytes per warp-wide reduction for wks = 1);
+//   * silu'(Y) of a block whose output gate reads the same rows (dz == Y: node_h stage 1) stays in registers.
 __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_constant__ Args a) {
   constexpr int NT = 256, CG = 2, CPT = kH / CG, NWR = kH * kH / NT;     // 16 weight words per thread and block
+#ifdef FEGNN_TRACE
+  long long tr_[48];
+  for (int i = 0; i < 48; ++i) tr_[i] = 0;
+#endif
+  TR(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   pdl_trigger();
@@ -352,6 +378,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
 
   const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
   uint8_t* Wk = smem + SmemR::off_Wk;
+  float* FS = reinterpret_cast<float*>(smem + SmemR::off_FS);
   auto Wm = [&](int s_) { return smem + SmemR::off_Wm + s_ * SmemR::kW; };
   auto TY = [&](int s_) { return smem + SmemR::off_TY + s_ * SmemR::kT; };
   auto TX = [&](int s_) { return smem + SmemR::off_TX + s_ * SmemR::kT; };
@@ -391,68 +418,56 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
+  TR(1);
   pdl_wait();
+  TR(2);
   const uint32_t tmem = v->tmem_slot;
   const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
   const uint32_t id_ts_k = idesc_tf32(128, 64, 0, 0), id_ts_mn = idesc_tf32(128, 64, 0, 1), id_wg = idesc_tf32(64, 64, 1, 1);
   const uint64_t dWk = umma::make_desc(umma::smem_u32(Wk));
   uint32_t ph_r = 0, ph_d = 0, ph_w[2] = {0, 0};
 
-  // Operand rows of a block: the row owner (= tensor-memory lane) fetches its CPT columns of X (nothing for a head block) and,
-  // when `want_y`, of Y.  (A coalesced half-warp-per-row variant through shared memory was measured slower here: it needs a
-  // second barrier and a shared-memory round trip per block, and these launches are latency-, not LSU-bound.)
-  float xr[CPT], yr[CPT];
-  auto load_rows = [&](const Blk& b, int r, bool valid, bool want_y) {
-    if (want_y) {
-      if (valid) {
-        const float4* src = reinterpret_cast<const float4*>(b.Y + (size_t)r * b.ldy + c0);
+  // rows r0 .. r0 + 127 of a [N][64] operand (row stride ld) -> an MN-major tile, 16-byte chunks in (row, chunk) order
+  auto fetch_tile = [&](uint8_t* dst, const float* src, int ld, int r0) {
 #pragma unroll
-        for (int ch = 0; ch < CPT / 4; ++ch) {
-          const float4 q = src[ch];
-          yr[ch * 4] = q.x; yr[ch * 4 + 1] = q.y; yr[ch * 4 + 2] = q.z; yr[ch * 4 + 3] = q.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) yr[j] = 0.f;
-      }
-    }
-    if (!b.head) {
-      if (valid) {
-        const float4* src = reinterpret_cast<const float4*>(b.X + (size_t)r * b.ldx + c0);
-#pragma unroll
-        for (int ch = 0; ch < CPT / 4; ++ch) {
-          const float4 q = src[ch];
-          xr[ch * 4] = q.x; xr[ch * 4 + 1] = q.y; xr[ch * 4 + 2] = q.z; xr[ch * 4 + 3] = q.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) xr[j] = 0.f;
-      }
+    for (int j = 0; j < kTM * 16 / NT; ++j) {
+      const int i = t + j * NT, rr = i >> 4, c16 = i & 15;
+      const bool ok = r0 + rr < a.N;
+      cp_async16(dst + mn_chunk_off(rr, c16, kTM), src + (size_t)(ok ? r0 + rr : 0) * ld + 4 * c16, ok ? 16 : 0);
     }
   };
   auto same_y = [&](int b) { return b != b0 && ((a.same_y_mask >> b) & 1u); };      // block b reads the Y tile block b - 1 left
   auto chain = [&](int b) { return b + 1 < b1 && ((a.chain_mask >> b) & 1u); };       // block b + 1 adds to the same D as block b
-  // weight gradient of block b (slot s_) : tensor memory -> global, bias sums
-  auto flush_w = [&](int b, int s_) {
-    const Blk& blk = a.blk[b];
-    if (blk.gW != nullptr) {
+  // weight gradient of block b (slot s_): wait for its MMAs (which also frees TX[s_] and the Y tile it read)
+  auto wait_w = [&](int b, int s_) {
+    if (a.blk[b].gW != nullptr) {
       umma::mbar_wait(&v->bar[2 + s_], ph_w[s_]);
       umma::fence_after();
       ph_w[s_] ^= 1;
+    }
+  };
+  // tensor memory -> staging tile (M = 64 layout: row n in lane (n / 16) * 32 + n % 16), then, after a barrier, out with the
+  // lanes along k; bias sums
+  auto flush_w_stage = [&](int b, int s_) {
+    if (a.blk[b].gW != nullptr) {
       float w[CPT];
       tmem_ld<CPT>(tlane + kR_RW + 64 * s_, w);
       if (lane < 16) {
         const int n = quarter * 16 + lane;
-        float* dst = blk.gW + (size_t)n * blk.ldw + (size_t)c0 * blk.wks;
-        if (blk.wks == 1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < CPT; j += 4) atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) atomicAdd(dst + (size_t)j * blk.wks, w[j]);
-        }
+        for (int j = 0; j < CPT; ++j) FS[n * 65 + c0 + j] = w[j];
       }
       umma::fence_before();
+    }
+  };
+  auto flush_w_out = [&](int b, int s_) {
+    const Blk& blk = a.blk[b];
+    if (blk.gW != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kH * kH / NT; ++j) {
+        const int i = t + j * NT, n = i >> 6, k = i & 63;
+        atomicAdd(blk.gW + (size_t)n * blk.ldw + (size_t)k * blk.wks, FS[n * 65 + k]);
+      }
     }
     if (blk.gb != nullptr && t < kH) {
       atomicAdd(blk.gb + t, v->cb[s_][t]);
@@ -462,26 +477,45 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
 
   const int ntiles = (a.N + kTM - 1) / kTM;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r = tile * kTM + row;
+    const int r0 = tile * kTM, r = r0 + row;
     const bool valid = r < a.N;
-    int ys = 1;                                   // Y slot of the previous block (flipped before the first store)
-    load_rows(a.blk[b0], r, valid, true);
+    int ys = 0;                                   // Y slot of the current block
+    {
+      const Blk& f = a.blk[b0];
+      fetch_tile(TY(0), f.Y, f.ldy, r0);
+      if (!f.head) fetch_tile(TX(0), f.X, f.ldx, r0);
+    }
     if (tile != (int)blockIdx.x) {                // a later tile of this CTA: the first block's weights again (slot 0 is free: all flushed)
       load_w(a.blk[b0]);
       store_w(a.blk[b0], 0);
     }
+    float dsil[CPT];                              // silu'(Y row) of a block with dz == Y
     for (int b = b0; b < b1; ++b) {
       const Blk& blk = a.blk[b];
       const int s_ = (b - b0) & 1;
       const bool new_y = !same_y(b);
-      // ---- Y rows -> TY[ys]
-      if (new_y) {
-        ys ^= 1;
+#ifdef FEGNN_TRACE
+      const int tb_ = 3 + 9 * (b - b0);
+#endif
+      TR(tb_);
+      if (new_y && b != b0) ys ^= 1;
+      cp_async_wait();
+      __syncthreads();                            // this block's rows have landed (every thread's copies)
+      float xr[CPT], yr[CPT];
+      const bool dz_y = new_y && blk.dz != nullptr && blk.dz == blk.Y && blk.ysilu && blk.yscale == nullptr && blk.ldy == kH;
+      // ---- Y rows: scale / SiLU in place (row owner)
+      if (new_y && (blk.yscale != nullptr || blk.ysilu)) {
+        mn_load_row<CPT>(TY(ys), row, cg, yr);
         const float sc = (valid && blk.yscale != nullptr) ? blk.yscale[r] : 1.f;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
           yr[j] *= sc;
-          if (blk.ysilu) yr[j] = valid ? silu_f(yr[j]) : 0.f;
+          if (blk.ysilu) {
+            float av, d;
+            silu_grad_f(yr[j], av, d);
+            yr[j] = valid ? av : 0.f;
+            dsil[j] = d;
+          }
         }
         mn_store_row<CPT>(TY(ys), row, cg, yr);
       }
@@ -489,7 +523,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
       if (blk.head) {
         // z = Y W^T on the tensor core, X = gs w2 silu'(z + b)
         if (t < kH) { v->hb[t] = blk.hb[t]; v->hw2[t] = blk.hw2[t]; }
-        if (!new_y) mn_load_row<CPT>(TY(ys), row, cg, yr);
+        mn_load_row<CPT>(TY(ys), row, cg, yr);
         tmem_st<CPT>(tlane + kR_OPA, yr);
         tmem_st_wait();
         umma::fence_smem_to_async();
@@ -508,6 +542,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         umma::mbar_wait(&v->bar[0], ph_r);
         umma::fence_after();
         ph_r ^= 1;
+        TR(tb_ + 1);
         tmem_ld<CPT>(tlane + kR_RW + 64 * s_, xr);
         const float g = valid ? blk.gs[r] : 0.f;
         float aw[CPT];
@@ -530,23 +565,25 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
           if (lane == 0) atomicAdd(&v->cb2, sum);
         }
         umma::fence_before();
-      } else if (valid && blk.xscale != nullptr) {
-        const float sc = blk.xscale[r];
+        mn_store_row<CPT>(TX(s_), row, cg, xr);
+      } else {
+        mn_load_row<CPT>(TX(s_), row, cg, xr);
+        if (blk.xscale != nullptr) {
+          const float sc = valid ? blk.xscale[r] : 0.f;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) xr[j] *= sc;
+          for (int j = 0; j < CPT; ++j) xr[j] *= sc;
+          mn_store_row<CPT>(TX(s_), row, cg, xr);
+        }
       }
-      // ---- X row -> A operand (tensor memory) and TX[s_]; the data gradient of block b - 1 has left the A operand
+      // ---- X row -> A operand (tensor memory); the data gradient of block b - 1 has left the A operand
       tmem_st<CPT>(tlane + kR_OPA, xr);
-      mn_store_row<CPT>(TX(s_), row, cg, xr);
       tmem_st_wait();
-      // the operands of block b + 1 (weight block, X / Y rows) go in flight now and land under the MMAs / epilogue of this one
-      if (more) {
-        load_w(a.blk[b + 1]);
-        load_rows(a.blk[b + 1], r, valid, !same_y(b + 1));
-      }
+      TR(tb_ + 2);
+      if (more) load_w(a.blk[b + 1]);             // lands under the MMAs / epilogue of this block
       umma::fence_smem_to_async();
       umma::fence_before();
       __syncthreads();
+      TR(tb_ + 3);
       const bool acc_in = b > b0 && chain(b - 1);
       if (warp == 0) {
         umma::fence_after();
@@ -564,7 +601,16 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         }
         __syncwarp();
       }
-      // ---- under the MMAs: bias column sums of this block, flush of block b - 1
+      TR(tb_ + 4);
+      // ---- under the MMAs: the weight gradient of block b - 1 has finished -> its X / Y tiles are free: the rows of block
+      //      b + 1 go in flight; flush of block b - 1; bias column sums of this block
+      if (b > b0) wait_w(b - 1, s_ ^ 1);
+      if (more) {
+        const Blk& nx = a.blk[b + 1];
+        if (!same_y(b + 1)) fetch_tile(TY(ys ^ 1), nx.Y, nx.ldy, r0);
+        if (!nx.head) fetch_tile(TX(s_ ^ 1), nx.X, nx.ldx, r0);
+      }
+      if (b > b0) flush_w_stage(b - 1, s_ ^ 1);
       if (blk.gb != nullptr) {
         const int col = t & 63, part = t >> 6;
         float sum = 0.f;
@@ -572,16 +618,25 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         for (int rr = part * 32; rr < part * 32 + 32; ++rr) sum += *reinterpret_cast<const float*>(TX(s_) + mn_off(rr, col, kTM));
         atomicAdd(&v->cb[s_][col], sum);
       }
-      if (b > b0) flush_w(b - 1, s_ ^ 1);          // also frees TX[s_ ^ 1]
+      TR(tb_ + 5);
+      if (b > b0) {
+        __syncthreads();                           // staging tile complete
+        flush_w_out(b - 1, s_ ^ 1);
+      }
+      TR(tb_ + 6);
       // ---- the data gradient: wait (the A operand and, at the end of a chain, the accumulator are reused next)
       umma::mbar_wait(&v->bar[1], ph_d);
       umma::fence_after();
       ph_d ^= 1;
+      TR(tb_ + 7);
       if (blk.dmode != 0 && !chain(b)) {
         float d[CPT];
         tmem_ld<CPT>(tlane + kR_ACC, d);
         if (valid) {
-          if (blk.dz != nullptr) {
+          if (dz_y) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) d[j] *= dsil[j];
+          } else if (blk.dz != nullptr) {
             const float4* zr = reinterpret_cast<const float4*>(blk.dz + (size_t)r * kH + c0);
 #pragma unroll
             for (int ch = 0; ch < CPT / 4; ++ch) {
@@ -601,6 +656,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
           }
         }
       }
+      TR(tb_ + 8);
       if (more) store_w(a.blk[b + 1], s_ ^ 1);     // Wm[s_ ^ 1]: last read by the data gradient of block b - 1 (waited)
       umma::fence_before();
       if (blk.head) {
@@ -615,14 +671,30 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
         }
       }
     }
-    __syncthreads();                               // bias sums of the last block are complete
-    flush_w(b1 - 1, (b1 - 1 - b0) & 1);
-    __syncthreads();
+    TR(45);
+    {
+      const int bl = b1 - 1, sl = (b1 - 1 - b0) & 1;
+      wait_w(bl, sl);
+      flush_w_stage(bl, sl);
+      __syncthreads();                             // staging tile and the bias sums of the last block are complete
+      flush_w_out(bl, sl);
+      __syncthreads();
+    }
+    TR(46);
   }
   umma::fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
+  TR(47);
+#ifdef FEGNN_TRACE
+  if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0) {
+    printf("DTRACE nblk=%d b0=%d b1=%d head0=%d :", a.nblk, b0, b1, a.blk[b0].head);
+    for (int i = 1; i < 48; ++i) if (tr_[i]) printf(" %d:%lld", i, tr_[i] - tr_[0]);
+    printf("\n");
+  }
+#endif
 }
+#undef TR
 
 }  // namespace dtc
 
