@@ -293,6 +293,13 @@ struct DevOnce {
   }
 };
 
+// 16 bytes global -> shared without a register stop; bytes = 0 writes zeros (rows past the end)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+               :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Column sums over the 32 lanes of a warp for 32 per-lane values: lane L returns sum over the lanes of v[L].  Each round
 // keeps the half of the columns whose index bit matches the lane's and trades the other half with the partner lane:
 // 16 + 8 + 4 + 2 + 1 = 31 shuffles (a butterfly per column costs 160).  v is clobbered.

@@ -343,12 +343,6 @@ __device__ __forceinline__ void gemm_ts_mn_acc(uint32_t tmem_d, uint32_t tmem_a,
   for (int ks = 0; ks < 8; ++ks)
     bwd2::mma_ts(tmem_d, tmem_a + ks * 8, desc_advance(dW, ks * 1024), idesc, (ks > 0 || accumulate) ? 1u : 0u);
 }
-// 16 bytes global -> shared without a register stop; bytes = 0 writes zeros (rows past N)
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(umma::smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 #ifdef FEGNN_TRACE
 #define TR(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0) tr_[(i)] = clock64(); } while (0)
 #else

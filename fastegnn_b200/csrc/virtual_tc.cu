@@ -330,11 +330,6 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) u[j] = valid ? silu_tc(u[j] + v->c2[c0 + j]) : 0.f;
       tmem_st<CPT>(tlane + kF_OPA, u);
-      if (valid) {
-        float4* dst = reinterpret_cast<float4*>(a.u + ((size_t)tile * TN * C + row) * kH + c0);
-#pragma unroll
-        for (int ch = 0; ch < CPT / 4; ++ch) dst[ch] = make_float4(u[ch * 4], u[ch * 4 + 1], u[ch * 4 + 2], u[ch * 4 + 3]);
-      }
       mn_store_row<CPT>(T, row, cg, u);          // G1 has finished reading T (bar[0])
       tmem_st_wait();
     }
@@ -349,6 +344,17 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
         umma::commit(&v->bar[1]);
       }
       __syncwarp();
+    }
+    // u -> HBM (saved for backward / phi_h) from the T tile in (row, chunk) order: a warp-wide store covers 2 rows x 256
+    // contiguous bytes (the row owners' stores touched 32 lines each)
+    {
+      float* ubase = a.u + (size_t)tile * TN * C * kH;
+#pragma unroll
+      for (int j = 0; j < kTM * 16 / NT; ++j) {
+        const int i = t + j * NT, rr = i >> 4, c16 = i & 15;
+        if (v->skey[rr] >= 0)
+          *reinterpret_cast<float4*>(ubase + (size_t)rr * kH + 4 * c16) = *reinterpret_cast<const float4*>(T + mn_chunk_off(rr, c16, kTM));
+      }
     }
     rows_to_graph<NT>(T, v->skey, &v->acc, C, TN, single, a.Usum);                 // overlaps GH
     umma::mbar_wait(&v->bar[1], phase);
@@ -499,8 +505,10 @@ struct HeadsSmem {
   static constexpr int off_TU = 65536;                     // u [128][64] BASE32B
   static constexpr int off_AUX = off_TU + 32768;           // [128][32], adjacent: B = [TU | AUX], N = 96
   static constexpr int off_TGH = off_AUX + 16384;          // [gzxv | gzX] [128][128] BASE32B (A of the weight-gradient GEMM)
-  static constexpr int off_vec = off_TGH + 65536;
+  static constexpr int off_SG = off_TGH + 65536;           // upstream dL/du rows of the tile [128][64] BASE32B (cp.async landing zone)
+  static constexpr int off_vec = off_SG + 32768;
   static constexpr size_t bytes = off_vec + sizeof(HeadsVec) + 1024;
+  static_assert(bytes <= 232448, "heads kernel: shared memory");
 };
 constexpr uint32_t kH_ACCH = 0, kH_ACCG = 128, kH_RW = 192, kH_OPA = 288;     // 416 columns
 
@@ -554,6 +562,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   uint8_t* TU = smem + SM::off_TU;
   uint8_t* AUX = smem + SM::off_AUX;
   uint8_t* TGH = smem + SM::off_TGH;
+  uint8_t* SG = smem + SM::off_SG;
   uint32_t phase = 0;
   bool first_tile = true;
   int cur_b = -1;
@@ -569,6 +578,18 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     }
     umma::fence_before();
     __syncthreads();
+    // rows of this tile in the [N, C, 64] arrays; the upstream dL/du rows go in flight now, in (row, chunk) order, and are read
+    // back by the row owners in epilogue 2 (a row-owner load touches 32 lines per access)
+    const int nrows = min(TN, a.N - tile * TN) * C;
+    const size_t tbase = (size_t)tile * TN * C * kH;
+    if (a.gu != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kTM * 16 / NT; ++j) {
+        const int i = t + j * NT, rr = i >> 4, c16 = i & 15;
+        const bool ok = rr < nrows;
+        cp_async16(SG + mn_chunk_off(rr, c16, kTM), a.gu + tbase + (size_t)(ok ? rr : 0) * kH + 4 * c16, ok ? 16 : 0);
+      }
+    }
     bwd_geometry(a, &v->g, tile, TN, AUX);
     __syncthreads();
     const bool single = v->g.b_first == v->g.b_last;
@@ -695,6 +716,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
       }
       v->g.sgD[t * 3 + 0] = gD[0]; v->g.sgD[t * 3 + 1] = gD[1]; v->g.sgD[t * 3 + 2] = gD[2];
     }
+    cp_async_wait();                           // this thread's share of the upstream dL/du rows has landed in SG
     __syncthreads();
     if (single && warp == NW - 1) small_from_rows(v->g.sgD, &v->acc, C, TN, lane);
     if (t < TN) {
@@ -724,14 +746,11 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
       tmem_ld<CPT>(tlane + kH_ACCG, g);
       const int key = v->g.skey[row];
       if (key >= 0) {
-        const size_t ro = ((size_t)tile * TN * C + row) * kH + c0;
         if (a.gu != nullptr) {
-          const float4* src = reinterpret_cast<const float4*>(a.gu + ro);
+          float q[CPT];
+          mn_load_row<CPT>(SG, row, cg, q);
 #pragma unroll
-          for (int ch = 0; ch < CPT / 4; ++ch) {
-            const float4 q = src[ch];
-            g[ch * 4] += q.x; g[ch * 4 + 1] += q.y; g[ch * 4 + 2] += q.z; g[ch * 4 + 3] += q.w;
-          }
+          for (int j = 0; j < CPT; ++j) g[j] += q[j];
         }
         if (a.gUsum != nullptr) {
           const float4* src = reinterpret_cast<const float4*>(a.gUsum + (size_t)key * kH + c0);
@@ -741,9 +760,13 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
             g[ch * 4] += q.x; g[ch * 4 + 1] += q.y; g[ch * 4 + 2] += q.z; g[ch * 4 + 3] += q.w;
           }
         }
-        float4* dst = reinterpret_cast<float4*>(a.gu_work + ro);
+        // gu_work: the tile's rows TRANSPOSED by 16-byte chunk -- chunk c16 of row r at tile base + (c16 * nrows + r) * 16 bytes --
+        // so that the row owners' stores here and loads in the trunk kernel are contiguous across a warp.  In place over gu:
+        // every upstream row of this tile was copied to SG before the barrier above.
+        float4* dst = reinterpret_cast<float4*>(a.gu_work + tbase);
 #pragma unroll
-        for (int ch = 0; ch < CPT / 4; ++ch) dst[ch] = make_float4(g[ch * 4], g[ch * 4 + 1], g[ch * 4 + 2], g[ch * 4 + 3]);
+        for (int ch = 0; ch < CPT / 4; ++ch)
+          dst[(size_t)(cg * (CPT / 4) + ch) * nrows + row] = make_float4(g[ch * 4], g[ch * 4 + 1], g[ch * 4 + 2], g[ch * 4 + 3]);
       }
     }
     phase ^= 1;
@@ -962,10 +985,12 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
       tmem_ld<CPT>(tlane + kT_ACC0, z);
       const bool valid = v->g.skey[row] >= 0;
       if (valid) {
-        const float4* src = reinterpret_cast<const float4*>(a.gu_work + ((size_t)tile * TN * C + row) * kH + c0);
+        // total dL/du of the row, written by the heads kernel transposed by 16-byte chunk (see there)
+        const int nrows = min(TN, a.N - tile * TN) * C;
+        const float4* src = reinterpret_cast<const float4*>(a.gu_work + (size_t)tile * TN * C * kH);
 #pragma unroll
         for (int ch = 0; ch < CPT / 4; ++ch) {
-          const float4 q = src[ch];
+          const float4 q = src[(size_t)(cg * (CPT / 4) + ch) * nrows + row];
           float u_, d;
           silu_grad_tc(z[ch * 4] + v->c2[c0 + ch * 4], u_, d); z[ch * 4] = q.x * d;
           silu_grad_tc(z[ch * 4 + 1] + v->c2[c0 + ch * 4 + 1], u_, d); z[ch * 4 + 1] = q.y * d;
