@@ -285,16 +285,22 @@ class FastEGNN(nn.Module):
             raise RuntimeError(f"edge_attr has {edge_attr.size(1)} columns, model was built with edge_attr_nf="
                                f"{self._edge_attr_nf}")
         B = int(loc_mean.size(0))
-        graph = CsrGraph(edge_index, data_batch, edge_attr, B)
+        graph = CsrGraph(edge_index, data_batch, edge_attr, B, overlap=True)      # the sort runs under the first node phase
         return self._run_stack(graph, node_feat, node_loc, node_vel, loc_mean)
 
     def _run_stack(self, graph, node_feat, node_loc, node_vel, loc_mean):
         args = (node_feat.contiguous().float(), node_loc.contiguous().float(), node_vel.contiguous().float(),
                 loc_mean.contiguous().float())
-        if not torch.is_grad_enabled() or (not self.training and not self.eval_keeps_graph):
-            return _stack_inference(self, graph, *[a.detach() for a in args])
-        params = [p for _, p in self.named_parameters()]
-        return _StackFn.apply(self, graph, *args, *params)
+        try:
+            if not torch.is_grad_enabled() or (not self.training and not self.eval_keeps_graph):
+                return _stack_inference(self, graph, *[a.detach() for a in args])
+            params = [p for _, p in self.named_parameters()]
+            return _StackFn.apply(self, graph, *args, *params)
+        finally:
+            # the C call has joined the side stream of CsrGraph(overlap=True): later users of the graph (backward) need no wait
+            if getattr(graph, "_ready", None) is not None:
+                graph._ready = None
+                graph.c.ready_event = None
 
 
 def unsorted_segment_sum(data, segment_ids, num_segments):

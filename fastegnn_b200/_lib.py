@@ -30,7 +30,7 @@ class Dims(C.Structure):
 
 class Graph(C.Structure):
     _fields_ = [("row", C.c_void_p), ("col", C.c_void_p), ("batch", C.c_void_p), ("edge_attr", C.c_void_p),
-                ("dinv", C.c_void_p), ("inv_nb", C.c_void_p)]
+                ("dinv", C.c_void_p), ("inv_nb", C.c_void_p), ("ready_event", C.c_void_p)]
 
 
 # member order of fegnn_layer_params / fegnn_layer_grads -> reference state_dict suffix

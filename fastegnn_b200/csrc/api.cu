@@ -808,12 +808,22 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   CK(cudaMemsetAsync(w.xsum[0], 0, sizeof(float) * ((size_t)L * al4(B * 3) + B * 3), st));
   for (int l = 0; l < L; ++l)
     CK(cudaMemsetAsync(w.saved[l].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+  const bool rf = d->flags & FEGNN_F_RF;          // FastRF: h and S pass through every layer (models/FastRF.py:186)
+  const bool graph_pending = g->ready_event != nullptr;
+  if (graph_pending) {
+    // the CSR sort is still running on another stream: everything above and the first layer's node phase read no graph
+    // array and run under it; this stream joins the sort here
+    fegnn_dims d0 = *d;
+    d0.flags |= FEGNN_F_PREZEROED;
+    if (rf || L == 1) d0.flags |= FEGNN_F_LAST;
+    TRY(fegnn_node_pre_forward(&d0, &layers[0], w.h[0], &w.saved[0], stream));
+    CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));
+  }
   CK(launch_graph_xsum(d->N, w.x[0], g->batch, w.xsum[0], st));
   SideStream* sd = side_stream();
   RQ(sd != nullptr);
   void* side = sd->st;
   FORK(sd, st);                                   // side: graph_pre(0)
-  const bool rf = d->flags & FEGNN_F_RF;          // FastRF: h and S pass through every layer (models/FastRF.py:186)
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
     dl.flags |= FEGNN_F_PREZEROED;
@@ -823,7 +833,7 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
     fegnn_layer_saved* sv = &w.saved[l];
     const int ls = rf ? 0 : l;                    // layer whose (h, S) state this layer reads
     TRY(fegnn_graph_pre_forward(&dl, g, p, w.Z[l], w.Sx[ls], w.xsum[l], sv, side));      // side (1 CTA per graph)
-    TRY(fegnn_node_pre_forward(&dl, p, w.h[ls], sv, stream));
+    if (!(graph_pending && l == 0)) TRY(fegnn_node_pre_forward(&dl, p, w.h[ls], sv, stream));
     if (rf) TRY(fegnn_rf_vel_forward(d->N, v, p, sv->sv, stream));
     TRY(fegnn_edge_forward(&dl, g, p, w.x[l], sv, stream));
     JOIN(sd, st);                                 // virtual needs G1, M of graph_pre
@@ -877,6 +887,7 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
     broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, Sx[2]); ++g_launches;
     CK(cudaGetLastError());
   }
+  if (g->ready_event != nullptr) CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));   // CSR sort on another stream
   TRY(fegnn_graph_xsum(d->N, d->B, x[2], g->batch, xsum[2], stream));
   SideStream* sd = side_stream();
   RQ(sd != nullptr);

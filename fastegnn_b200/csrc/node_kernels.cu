@@ -100,7 +100,7 @@ constexpr size_t kNodePreFwdSmem = (kWFloats + kTileFloats + 2 * kH) * sizeof(fl
 
 // Work item = (node tile, weight block).  The grid is a multiple of the number of active blocks, so a
 // CTA always meets the same block and stages its 64x64 weight once; small N still fills the GPU
-// (N = 8000 -> 63 tiles x 6 blocks = 378 CTAs instead of 63).
+// (N = 8000 -> 63 tiles x 6 blocks = 378 CTAs instead of 63; three CTAs per SM hold them in one wave).
 __device__ __forceinline__ int node_pre_block_id(int k, bool last, bool grav, bool rf = false) {
   // k-th ACTIVE block -> block id (0 P, 1 Q, 2 Av, 3 Uh, 4 vel, 5 grav)
   if (last && k >= 3) ++k;
@@ -109,7 +109,7 @@ __device__ __forceinline__ int node_pre_block_id(int k, bool last, bool grav, bo
   return k;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) node_pre_fwd_kernel(NodePreArgs a, int nactive) {
+__global__ void __launch_bounds__(kThreads, 3) node_pre_fwd_kernel(NodePreArgs a, int nactive) {
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
   float* T0 = Ws + kWFloats;
@@ -509,8 +509,8 @@ cudaError_t launch_graph_xsum(int N, const float* x, const int* batch, float* xs
     }                                                                                                        \
   } while (0)
 
-static inline int node_pre_grid(int ntiles, int nactive, int sms) {
-  int per = (2 * sms) / nactive;            // CTAs per block id at 2 CTAs/SM
+static inline int node_pre_grid(int ntiles, int nactive, int sms, int ctas_per_sm = 2) {
+  int per = (ctas_per_sm * sms) / nactive;  // CTAs per block id
   if (per < 1) per = 1;
   if (per > ntiles) per = ntiles;
   return per * nactive;
@@ -521,7 +521,7 @@ cudaError_t launch_node_pre_fwd(const NodePreArgs& a, int sms, cudaStream_t st) 
   if (ntiles == 0) return cudaSuccess;
   const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
   const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
-  if (cudaError_t e_ = launch_pdl(node_pre_fwd_kernel, node_pre_grid(ntiles, nactive, sms), kThreads, kNodePreFwdSmem, st, a, nactive)) return e_;
+  if (cudaError_t e_ = launch_pdl(node_pre_fwd_kernel, node_pre_grid(ntiles, nactive, sms, 3), kThreads, kNodePreFwdSmem, st, a, nactive)) return e_;
   return cudaGetLastError();
 }
 cudaError_t launch_node_pre_bwd(const NodePreArgs& a, int sms, cudaStream_t st) {

@@ -36,10 +36,19 @@ using bwd2::tmem_ld;
 using bwd2::tmem_st;
 using bwd2::tmem_st_wait;
 
+// With t = z / 2: z (0.5 + 0.5 tanh t) = t + t tanh t (FMUL, MUFU, FFMA); silu_tc_hb takes HALF the bias, so that the bias
+// add and the halving are one FFMA (3 instructions per activation instead of 5).
 __device__ __forceinline__ float silu_tc(float z) {
+  const float t = 0.5f * z;
   float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
-  return z * fmaf(0.5f, th, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+  return fmaf(t, th, t);
+}
+__device__ __forceinline__ float silu_tc_hb(float z, float half_bias) {
+  const float t = fmaf(z, 0.5f, half_bias);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+  return fmaf(t, th, t);
 }
 
 // Weight staging in two phases: every global load of a thread (all weights of the kernel) is in flight before its first
@@ -216,8 +225,8 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   }
   for (int i = t; i < kH; i += NT) {
     v->vr[i] = a.wv1[(size_t)i * a.ldv + 2 * kH];
-    v->c2[i] = a.c2[i];
-    v->bh[i] = a.bxv[i]; v->bh[kH + i] = a.bX[i];
+    v->c2[i] = 0.5f * a.c2[i];                                              // halved: silu_tc_hb
+    v->bh[i] = 0.5f * a.bxv[i]; v->bh[kH + i] = 0.5f * a.bX[i];
     v->wh[i] = a.wxv[i]; v->wh[kH + i] = a.wX[i];
   }
   acc_clear<NT>(&v->acc);
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       tmem_ld<CPT>(tlane + kF_ACC0, u);
       const bool valid = v->skey[row] >= 0;
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) u[j] = valid ? silu_tc(u[j] + v->c2[c0 + j]) : 0.f;
+      for (int j = 0; j < CPT; ++j) u[j] = valid ? silu_tc_hb(u[j], v->c2[c0 + j]) : 0.f;
       tmem_st<CPT>(tlane + kF_OPA, u);
       mn_store_row<CPT>(T, row, cg, u);          // G1 has finished reading T (bar[0])
       tmem_st_wait();
@@ -366,10 +375,10 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       tmem_ld<CPT>(tlane + kF_ACCH, z);
       float px = 0.f, pX = 0.f;
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) px = fmaf(silu_tc(z[j] + v->bh[c0 + j]), v->wh[c0 + j], px);
+      for (int j = 0; j < CPT; ++j) px = fmaf(silu_tc_hb(z[j], v->bh[c0 + j]), v->wh[c0 + j], px);
       tmem_ld<CPT>(tlane + kF_ACCH + kH, z);
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) pX = fmaf(silu_tc(z[j] + v->bh[kH + c0 + j]), v->wh[kH + c0 + j], pX);
+      for (int j = 0; j < CPT; ++j) pX = fmaf(silu_tc_hb(z[j], v->bh[kH + c0 + j]), v->wh[kH + c0 + j], pX);
       v->spx[cg * kTM + row] = px;
       v->spX[cg * kTM + row] = pX;
     }

@@ -32,13 +32,27 @@ def _require_cuda(t: torch.Tensor, name: str):
             f"{name} is on {t.device}: fastegnn_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
 
 
+_PREP_STREAMS = {}
+
+
+def _prep_stream(dev) -> "torch.cuda.Stream":
+    """One side stream per device for CsrGraph(overlap=True)."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _PREP_STREAMS:
+        _PREP_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _PREP_STREAMS[key]
+
+
 class CsrGraph:
     """CSR-by-row view of one batch (output of fegnn_graph_prep), shared by all layers
     and by backward.  Replaces the per-layer int64 gathers / scatter_add of
     models/FastEGNN.py:182,210,279-294."""
 
     def __init__(self, edge_index: torch.Tensor, data_batch: torch.Tensor, edge_attr: Optional[torch.Tensor],
-                 n_graphs: int, n_local: Optional[int] = None):
+                 n_graphs: int, n_local: Optional[int] = None, overlap: bool = False):
+        """overlap=True runs the sort on a per-device side stream and leaves `ready_event` in the pointer table:
+        fegnn_model_forward joins it right before its first use of the CSR arrays (the embedding and the first layer's
+        node phase run under the sort).  Any other consumer must call wait() first."""
         _require_cuda(edge_index, "edge_index")
         dev = edge_index.device
         N = int(data_batch.numel())
@@ -64,18 +78,39 @@ class CsrGraph:
         self.inv_nb = torch.empty(n_graphs, **f32)
         nbytes = int(lib.fegnn_graph_prep_workspace_bytes(N, E))
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        self._ready = None
         with _on(dev):
+            # every buffer above was allocated under the caller's stream; with overlap the side stream first joins that
+            # stream (inputs and recycled memory are ordered), then runs the sort while the caller's stream goes on
+            main = torch.cuda.current_stream(dev)
+            st = main
+            if overlap:
+                st = _prep_stream(dev)
+                st.wait_stream(main)
             L.check(lib.fegnn_graph_prep(N, E, n_graphs, Fe, L.ptr(ei), L.ptr(db), L.ptr(ea), L.ptr(self.perm),
                                          L.ptr(self.rowptr), L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch),
                                          L.ptr(self.gptr), L.ptr(self.edge_attr), L.ptr(self.dinv), L.ptr(self.inv_nb),
-                                         L.ptr(ws), nbytes, _stream(dev)), "fegnn_graph_prep")
+                                         L.ptr(ws), nbytes, st.cuda_stream), "fegnn_graph_prep")
+            if overlap:
+                self._ready = torch.cuda.Event()
+                self._ready.record(st)
         self._ws = ws   # stream-ordered: keep alive until the kernels that use it have been enqueued
+        self._keep = (ei, db, ea)   # inputs of a sort that may still be running on the side stream
         self.rebind()
 
     def rebind(self) -> None:
         """(Re)build the fegnn_graph pointer table from the current tensors (after slicing / renumbering them)."""
+        ready = getattr(self, "_ready", None)
         self.c = L.Graph(L.ptr(self.row), L.ptr(self.col), L.ptr(self.batch), L.ptr(self.edge_attr),
-                         L.ptr(self.dinv), L.ptr(self.inv_nb))
+                         L.ptr(self.dinv), L.ptr(self.inv_nb), None if ready is None else ready.cuda_event)
+
+    def wait(self) -> None:
+        """Order the current stream behind a sort that runs on the side stream (no-op otherwise)."""
+        ready = getattr(self, "_ready", None)
+        if ready is not None:
+            torch.cuda.current_stream(self.row.device).wait_event(ready)
+            self._ready = None
+            self.c.ready_event = None
 
     @classmethod
     def from_radius(cls, node_loc: torch.Tensor, data_batch: torch.Tensor, n_graphs: int, r: float,

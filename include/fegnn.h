@@ -82,6 +82,10 @@ typedef struct fegnn_graph {
   const float* edge_attr; /* [E,Fe] edge_attr[perm]                                 */
   const float* dinv;      /* [N]  1 / max(1, deg_row)        (:294 clamp(min=1))    */
   const float* inv_nb;    /* [B]  1 / max(1, nodes in graph) (global_mean_pool)     */
+  void* ready_event;      /* optional cudaEvent_t recorded behind a fegnn_graph_prep that runs on ANOTHER stream: fegnn_model_forward
+                             waits for it right before its first use of the arrays above (the embedding and the first layer's
+                             node phase run under the sort), fegnn_model_forward_inference at its start; NULL = same stream.
+                             Every other entry point ignores it: the caller orders them (ops.CsrGraph.wait)                    */
 } fegnn_graph;
 
 /* One layer's parameters in reference layout (models/FastEGNN.py:28-99).
