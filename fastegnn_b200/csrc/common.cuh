@@ -299,6 +299,9 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes
                :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: lane L returns sum over the lanes of v[L].  Each round
 // keeps the half of the columns whose index bit matches the lane's and trades the other half with the partner lane:

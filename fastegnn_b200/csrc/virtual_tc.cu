@@ -160,24 +160,36 @@ __device__ __forceinline__ void rows_to_graph(const uint8_t* T, const int* skey,
   const int j0 = grp * per, j1 = min(TN, j0 + per);
   const uint32_t cbase = (col >> 5) * (kTM * 128) + ((col & 7) << 2);
   const int c8 = (col & 31) >> 3;
+  auto at = [&](int r) { return *reinterpret_cast<const float*>(T + cbase + r * 128 + ((c8 ^ (r & 3)) << 5)); };
+  if (single) {
+    // whole tile inside one graph (unused rows of the tile hold zeros): thread (channel, column) owns its sum -- no key reads,
+    // independent loads, a plain add.  (The keyed walk below is one dependent shared-memory chain per row, and 8 groups adding
+    // into the same shared word cost ~800 cycles per atomic: 3 400 cycles per tile at C = 3.)
+    for (int c = grp; c < C; c += GR) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int jn = 0;
+      for (; jn + 3 < TN; jn += 4) {
+        a0 += at(jn * C + c); a1 += at((jn + 1) * C + c); a2 += at((jn + 2) * C + c); a3 += at((jn + 3) * C + c);
+      }
+      for (; jn < TN; ++jn) a0 += at(jn * C + c);
+      g->big[c * kH + col] += (a0 + a1) + (a2 + a3);
+    }
+    return;
+  }
   for (int c = 0; c < C; ++c) {
     int cur = -1;
     float acc = 0.f;
     for (int jn = j0; jn < j1; ++jn) {
       const int r = jn * C + c;
       const int k = skey[r];
-      if (!single && k != cur) {
+      if (k != cur) {
         if (cur >= 0) atomicAdd(dst + (size_t)cur * kH + col, acc);
         cur = k;
         acc = 0.f;
       }
-      if (k >= 0) acc += *reinterpret_cast<const float*>(T + cbase + r * 128 + ((c8 ^ (r & 3)) << 5));
+      if (k >= 0) acc += at(r);
     }
-    if (single) {
-      if (j1 > j0) atomicAdd(&g->big[c * kH + col], acc);
-    } else if (cur >= 0) {
-      atomicAdd(dst + (size_t)cur * kH + col, acc);
-    }
+    if (cur >= 0) atomicAdd(dst + (size_t)cur * kH + col, acc);
   }
 }
 
@@ -499,6 +511,18 @@ __device__ __forceinline__ void bwd_geometry(const VirtArgs& a, BwdGeo* s, int t
   }
 }
 
+
+#ifdef FEGNN_TRACE
+#define VTR_DECL() long long tr_t[64]; int tr_l[64]; int tri_ = 0; const bool tr_on = threadIdx.x == 0 && blockIdx.x == 1; \
+  if (tr_on) { tr_t[0] = clock64(); tr_l[0] = __LINE__; tri_ = 1; }
+#define VTR() do { if (tr_on && tri_ < 64) { tr_t[tri_] = clock64(); tr_l[tri_] = __LINE__; ++tri_; } } while (0)
+#define VTR_PRINT(name) do { if (tr_on) { printf("VTRACE %s :", name); \
+  for (int i_ = 1; i_ < tri_; ++i_) printf(" L%d:%lld", tr_l[i_], tr_t[i_] - tr_t[i_ - 1]); printf("\n"); } } while (0)
+#else
+#define VTR_DECL() do { } while (0)
+#define VTR() do { } while (0)
+#define VTR_PRINT(name) do { } while (0)
+#endif
 // ---- heads kernel
 struct HeadsVec {
   float bh[2 * kH], wh[2 * kH], cwh[2 * kH];
@@ -523,6 +547,7 @@ constexpr uint32_t kH_ACCH = 0, kH_ACCG = 128, kH_RW = 192, kH_OPA = 288;     //
 
 template <int CG>
 __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtArgs a) {
+  VTR_DECL();
   constexpr int NT = 128 * CG, CPT = kH / CG, NW = NT / 32;
   using SM = HeadsSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -559,6 +584,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
+    VTR();
   umma::fence_after();
   pdl_wait();
   const uint32_t tmem = v->tmem_slot;
@@ -583,14 +609,24 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (!first_tile) {                         // the previous tile's weight-gradient GEMM still reads TU, AUX and TGH
       umma::mbar_wait(&v->bar[2], phase ^ 1);
+    VTR();
       umma::fence_after();
     }
     umma::fence_before();
     __syncthreads();
+    VTR();
     // rows of this tile in the [N, C, 64] arrays; the upstream dL/du rows go in flight now, in (row, chunk) order, and are read
     // back by the row owners in epilogue 2 (a row-owner load touches 32 lines per access)
     const int nrows = min(TN, a.N - tile * TN) * C;
     const size_t tbase = (size_t)tile * TN * C * kH;
+    // the saved u rows -> TU (first group: needed right after the geometry), the upstream rows -> SG (second group)
+#pragma unroll
+    for (int j = 0; j < kTM * 16 / NT; ++j) {
+      const int i = t + j * NT, rr = i >> 4, c16 = i & 15;
+      const bool ok = rr < nrows;
+      cp_async16(TU + mn_chunk_off(rr, c16, kTM), a.u + tbase + (size_t)(ok ? rr : 0) * kH + 4 * c16, ok ? 16 : 0);
+    }
+    cp_async_commit();
     if (a.gu != nullptr) {
 #pragma unroll
       for (int j = 0; j < kTM * 16 / NT; ++j) {
@@ -599,27 +635,17 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
         cp_async16(SG + mn_chunk_off(rr, c16, kTM), a.gu + tbase + (size_t)(ok ? rr : 0) * kH + 4 * c16, ok ? 16 : 0);
       }
     }
+    cp_async_commit();
     bwd_geometry(a, &v->g, tile, TN, AUX);
+    cp_async_wait_group<1>();                  // u rows of this thread have landed (the barrier publishes everybody's)
     __syncthreads();
+    VTR();
     const bool single = v->g.b_first == v->g.b_last;
     if (!single || v->g.b_first != cur_b) {
       const int nb = single ? v->g.b_first : -1;
       acc_flush<NT>(&v->acc, cur_b, C, nullptr, a.gZ, nullptr);
       cur_b = nb;
     }
-    // ---- u tile: saved rows -> TU (half-warp per row, coalesced)
-    {
-      const int l16 = lane & 15, hsel = lane >> 4;
-      constexpr int RPW = kTM / NW;
-#pragma unroll
-      for (int i0 = 0; i0 < RPW; i0 += 2) {
-        const int rr = warp * RPW + i0 + hsel;
-        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v->g.skey[rr] >= 0) u4 = *reinterpret_cast<const float4*>(a.u + ((size_t)tile * TN * C + rr) * kH + 4 * l16);
-        *reinterpret_cast<float4*>(TU + mn_chunk_off(rr, l16, kTM)) = u4;
-      }
-    }
-    __syncthreads();
     {
       float u[CPT];
       mn_load_row<CPT>(TU, row, cg, u);
@@ -629,6 +655,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -640,6 +667,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[0], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 1: head scalars, gz = gs w silu'(z) for both heads -> tensor memory (A of gu) and TGH (A of dW)
     {
@@ -656,6 +684,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
         v->spx[cg * kTM + row] = px;
         v->spX[cg * kTM + row] = pX;
         __syncthreads();
+    VTR();
         float sx = 0.f, sX = 0.f;
 #pragma unroll
         for (int g = 0; g < CG; ++g) { sx += v->spx[g * kTM + row]; sX += v->spX[g * kTM + row]; }
@@ -663,6 +692,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
         gsx *= (1.f - sx * sx);
         gsX *= (1.f - sX * sX);
         __syncthreads();
+    VTR();
       }
       float px = 0.f, pX = 0.f;
       tmem_ld<CPT>(tlane + kH_ACCH, z);
@@ -694,6 +724,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -727,6 +758,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     }
     cp_async_wait();                           // this thread's share of the upstream dL/du rows has landed in SG
     __syncthreads();
+    VTR();
     if (single && warp == NW - 1) small_from_rows(v->g.sgD, &v->acc, C, TN, lane);
     if (t < TN) {
       const int i = tile * TN + t;
@@ -748,6 +780,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
       }
     }
     umma::mbar_wait(&v->bar[1], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 2: total dL/du of the row -> gu_work
     {
@@ -784,6 +817,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   acc_flush<NT>(&v->acc, cur_b, C, nullptr, a.gZ, nullptr);
   // ---- flush the weight gradients
   if (!first_tile) umma::mbar_wait(&v->bar[2], phase ^ 1);
+    VTR();
   umma::fence_after();
   if constexpr (CPT == 16) {
     // the 2 x 16 per-row partial sums of a warp as ONE 32-column transposed reduction: 31 shuffles instead of 160
@@ -808,6 +842,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     }
   }
   __syncthreads();
+    VTR();
   if (!first_tile) {
     // RW: lane n = row of [dWxv ; dWX] (M = 128 layout: row m in lane m), columns 0-63 = k, column 64 = bias sum
     float w[CPT];
@@ -837,7 +872,10 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   }
   umma::fence_before();
   __syncthreads();
+    VTR();
   if (warp == 0) umma::tmem_dealloc<512>(tmem);
+  VTR();
+  VTR_PRINT("heads");
 }
 
 // ---- trunk kernel
@@ -863,6 +901,7 @@ constexpr uint32_t kT_ACC0 = 0, kT_ACC1 = 64, kT_R2 = 128, kT_DXZ = 224, kT_OPA 
 
 template <int CG>
 __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtArgs a) {
+  VTR_DECL();
   constexpr int NT = 128 * CG, CPT = kH / CG, NW = NT / 32;
   using SM = TrunkSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -894,6 +933,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
+    VTR();
   umma::fence_after();
   pdl_wait();
   const uint32_t tmem = v->tmem_slot;
@@ -918,12 +958,15 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (!first_tile) {                         // previous tile's last GEMMs still read AUX, TA, TG and TM
       umma::mbar_wait(&v->bar[2], phase ^ 1);
+    VTR();
       umma::fence_after();
     }
     umma::fence_before();
     __syncthreads();
+    VTR();
     bwd_geometry(a, &v->g, tile, TN, AUX);
     __syncthreads();
+    VTR();
     const bool single = v->g.b_first == v->g.b_last;
     if (!single || v->g.b_first != cur_b) {
       const int nb = single ? v->g.b_first : -1;
@@ -969,6 +1012,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
       }
     }
     __syncthreads();
+    VTR();
     {
       float a1[CPT];
       mn_load_row<CPT>(TA, row, cg, a1);
@@ -978,6 +1022,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -987,6 +1032,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[0], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 1: gz2 = dL/du * silu'(z2 + c2) -> tensor memory (A of ga1) and TG (A of dV2)
     {
@@ -1017,6 +1063,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -1027,6 +1074,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[1], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 2: gz1 = ga1 * silu'(z1) -> TM ; grho = gz1 . vr
     {
@@ -1058,6 +1106,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -1069,24 +1118,30 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
     phase ^= 1;
     first_tile = false;
     // ---- outputs: gG1 by key, gAv by node, and the rho term of the coordinate gradients
+    VTR();
     rows_to_graph<NT>(TM, v->g.skey, &v->acc, C, TN, single, a.gG1);
+    VTR();
     {
       constexpr int GR = NT / 64;
       const int col = t & 63, grp = t >> 6;
       const uint32_t cbase = (col >> 5) * (kTM * 128) + ((col & 7) << 2);
       const int c8 = (col & 31) >> 3;
-      for (int jn = grp; jn < TN; jn += GR) {
-        const int i = tile * TN + jn;
-        if (i < a.N) {
-          float sum = 0.f;
-          for (int c = 0; c < C; ++c) {
-            const int r = jn * C + c;
-            sum += *reinterpret_cast<const float*>(TM + cbase + r * 128 + ((c8 ^ (r & 3)) << 5));
-          }
-          a.gAv[(size_t)i * kH + col] = sum;
+      // two nodes per trip with independent sums (the single-sum walk was a dependent shared-memory chain: 2 300 cycles per tile)
+      auto at = [&](int r) { return *reinterpret_cast<const float*>(TM + cbase + r * 128 + ((c8 ^ (r & 3)) << 5)); };
+      for (int jn = grp; jn < TN; jn += 2 * GR) {
+        const int jb = jn + GR;
+        const int ia = tile * TN + jn, ib = tile * TN + jb;
+        const bool hb = jb < TN;                       // rows of nodes past N hold zeros
+        float sa = 0.f, sb = 0.f;
+        for (int c = 0; c < C; ++c) {
+          sa += at(jn * C + c);
+          if (hb) sb += at(jb * C + c);
         }
+        if (ia < a.N) a.gAv[(size_t)ia * kH + col] = sa;
+        if (hb && ib < a.N) a.gAv[(size_t)ib * kH + col] = sb;
       }
     }
+    VTR();
     if (t < kTM) {
       const int key = v->g.skey[t];
       float gD[3] = {0, 0, 0};
@@ -1106,6 +1161,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
       v->g.sgD[t * 3 + 0] = gD[0]; v->g.sgD[t * 3 + 1] = gD[1]; v->g.sgD[t * 3 + 2] = gD[2];
     }
     __syncthreads();
+    VTR();
     if (single && warp == NW - 1) small_from_rows(v->g.sgD, &v->acc, C, TN, lane);
     if (t < TN) {
       const int i = tile * TN + t;
@@ -1121,6 +1177,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   }
   acc_flush<NT>(&v->acc, cur_b, C, a.gG1, a.gZ, nullptr);
   if (!first_tile) umma::mbar_wait(&v->bar[2], phase ^ 1);
+    VTR();
   umma::fence_after();
   if (!first_tile) {
     // R2 (M = 64 layout: row n in lane (n/16)*32 + n%16): columns 0-31 aux sums (0: dc2), 32-95: dV2[n][k]
@@ -1150,7 +1207,10 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_trunk_tc_kernel(VirtA
   }
   umma::fence_before();
   __syncthreads();
+    VTR();
   if (warp == 0) umma::tmem_dealloc<512>(tmem);
+  VTR();
+  VTR_PRINT("trunk");
 }
 
 }  // namespace vtc
