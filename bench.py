@@ -1097,6 +1097,9 @@ def phase_profile(model, t, dev, data, E, N, B, C, flush):
     calls += [(f"virtual_bwd[mode={m}]", with_mode("virtual_backward", m, virt_bwd_fn)) for m in (0, 1)]
     npre_fn = dict(calls)["node_pre_fwd"]
     calls += [(f"node_pre_fwd[mode={m}]", with_mode("node_forward", m, npre_fn)) for m in (0, 1)]
+    if "node_h_fwd" in dict(calls):
+        nh_fn = dict(calls)["node_h_fwd"]
+        calls += [(f"node_h_fwd[mode={m}]", with_mode("node_forward", m, nh_fn)) for m in (0, 3)]
     edge_bwd_fn = dict(calls)["edge_bwd"]
     calls += [(f"edge_bwd[mode={m}]", with_mode("edge_backward", m, edge_bwd_fn)) for m in (0, 1, 2, 4, 5, 7, 8)]
     for name, fn in calls:

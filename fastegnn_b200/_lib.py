@@ -63,7 +63,7 @@ class LayerPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n, _ in LAYER_FIELDS]
 
 
-SAVED_FIELDS = ["P", "Q", "Av", "Uh", "sv", "sg", "M", "Zc", "G1", "msum", "tsum", "u", "zh1", "Dsum", "Usum", "scratch"]
+SAVED_FIELDS = ["P", "Q", "Av", "Uh", "sv", "sg", "M", "Zc", "G1", "msum", "tsum", "u", "zh1", "Dsum", "Usum", "scratch", "wimg"]
 
 
 class Saved(C.Structure):
@@ -118,6 +118,7 @@ SIGNATURES = {
     "fegnn_edge_forward": (C.c_int, [_PD, _PG, _PP, vp, _PS, vp]),
     "fegnn_virtual_forward": (C.c_int, [_PD, _PG, _PP, vp, vp, vp, _PS, vp, vp, vp]),
     "fegnn_node_h_forward": (C.c_int, [_PD, _PG, _PP, vp, _PS, vp, vp]),
+    "fegnn_node_h_weight_images": (C.c_int, [_PD, i32, _PP, C.POINTER(C.c_void_p), vp]),
     "fegnn_graph_post_forward": (C.c_int, [_PD, _PG, _PP, vp, vp, _PS, vp, vp, vp]),
     "fegnn_graph_post_backward": (C.c_int, [_PD, _PG, _PP, _PP, vp, _PS, vp, vp, vp, vp, vp, vp, vp]),
     "fegnn_node_h_backward": (C.c_int, [_PD, _PG, _PP, _PP, _PS, vp, vp, vp, vp, vp]),
@@ -165,11 +166,12 @@ PHASES = ("edge_forward", "edge_backward", "virtual_forward", "virtual_backward"
 
 def set_precision(name: str) -> None:
     """"fp32": every phase on the fp32 FMA kernels (tight parity).  "tf32" (default): the fused edge phase and the
-    dense real<->virtual phase run on tcgen05 TF32 tiles, forward and backward (stated tolerance).
-    "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge tiles, fp32 FMA virtual and node phases).
+    dense real<->virtual phase run on tcgen05 TF32 tiles, forward and backward (stated tolerance); phi_h of
+    the forward runs on tcgen05 3xTF32 tiles (fp32-grade).
+    "tf32x3": TF32 backward, fp32-grade forward (3xTF32 edge and phi_h tiles, fp32 FMA virtual and node_pre phases).
     "tf32_all": "tf32" plus the tcgen05 node_pre forward (h rounded to TF32: fastest, but equivariance only to ~3e-4 on
     equivariant_test.py's inputs)."""
-    table = {"fp32": (0, 0, 0, 0, 0, 0), "tf32": (1, 6, 1, 1, 0, 2), "tf32x3": (3, 6, 0, 1, 0, 2), "tf32_all": (1, 6, 1, 1, 1, 2)}
+    table = {"fp32": (0, 0, 0, 0, 0, 0), "tf32": (1, 6, 1, 1, 3, 2), "tf32x3": (3, 6, 0, 1, 3, 2), "tf32_all": (1, 6, 1, 1, 1, 2)}
     for phase, mode in zip(PHASES, table[name]):
         set_mode(phase, mode)
 

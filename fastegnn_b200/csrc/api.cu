@@ -68,11 +68,13 @@ int g_edge_bwd_mode = 6;
 // 0 = fp32 FMA kernels, 1 = tcgen05 TF32 kernels (attention=True layers always take 0)
 int g_virt_fwd_mode = 1;
 int g_virt_bwd_mode = 1;
-// per-node dense phases: 0 = fp32 FMA kernels (default), 1 = tcgen05 TF32 kernels.  Opt-in: h is the one operand of the
+// per-node dense phases of the forward: 0 = fp32 FMA kernels, 1 = tcgen05 TF32 node_pre.  Opt-in: h is the one operand of the
 // path that is neither bounded by an activation nor an invariant the next layer re-derives exactly, so rounding it to
 // TF32 turns fp32-level noise between a rotated and an unrotated run into 2^-11 |h| jumps in P / Q / Av / Uh -- measured
 // 2.2e-4 on equivariant_test.py's U(0,10) inputs against its atol of 1e-4.
-int g_node_fwd_mode = 0;
+// 3 (default) = node_pre on the fp32 FMA kernel, phi_h (fegnn_node_h_forward) on tcgen05 with the error-compensated 3xTF32
+// split (fp32-grade: node_tc.cu); mode 1 takes the same phi_h kernel.
+int g_node_fwd_mode = 3;
 // per-node dense phases of the BACKWARD pass (node_pre_backward, node_h_backward): 0 = fp32 FMA kernels, 1 = tcgen05 TF32
 // (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default) = 1 today: up to two node tiles per SM
 // the per-tile kernel walks the weight blocks (measured at 8 000 nodes: step 1.380 ms against 1.416 ms with the fp32 kernels),
@@ -256,8 +258,8 @@ int fegnn_set_mode(const char* phase, int mode) {
   }
   if (strcmp(phase, "node_forward") == 0 || strcmp(phase, "node_backward") == 0) {
     const bool fwd = phase[5] == 'f';
-    if (mode != 0 && mode != 1 && !(mode == 2 && !fwd))
-      return fail(FEGNN_EINVAL, "%s mode must be 0 or 1%s", phase, fwd ? "" : " or 2 (auto)");
+    if (mode != 0 && mode != 1 && !(mode == 2 && !fwd) && !(mode == 3 && fwd))
+      return fail(FEGNN_EINVAL, "%s mode must be 0 or 1%s", phase, fwd ? " or 3 (3xTF32 phi_h)" : " or 2 (auto)");
     (fwd ? g_node_fwd_mode : g_node_bwd_mode) = mode;
     return 0;
   }
@@ -420,7 +422,29 @@ int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_
   a.dinv = (d->flags & FEGNN_F_NODE_SUM) ? nullptr : g->dinv;     // VNEGNN's A2A stage sums the messages (models/VNEGNN.py:87)
   a.node_w0 = p->node_w0; a.node_w2 = p->node_w2; a.node_b2 = p->node_b2;
   a.zh1 = sv->zh1; a.h_new = h_new;
-  CK(launch_node_h_fwd(a, sm_count(), S(stream), !(d->flags & FEGNN_F_PREZEROED)));
+  a.wimg = sv->wimg;
+  if (g_node_fwd_mode != 0 && sv->wimg != nullptr) {
+    if (!(d->flags & FEGNN_F_WIMG_READY)) {
+      const float *w0 = p->node_w0, *w2 = p->node_w2;
+      float* img = sv->wimg;
+      CK(launch_node_h_wprep(d->C, ldn(d), 1, &w0, &w2, &img, S(stream)));
+    }
+    CK(launch_node_h_fwd_tc(a, sm_count(), S(stream)));
+  }
+  else CK(launch_node_h_fwd(a, sm_count(), S(stream), !(d->flags & FEGNN_F_PREZEROED)));
+  return 0;
+}
+
+int fegnn_node_h_weight_images(const fegnn_dims* d, int32_t nl, const fegnn_layer_params* layers, float* const* wimg,
+                               void* stream) {
+  TRY(check_dims(d));
+  RQ(nl >= 0 && nl <= 32 && (nl == 0 || (layers && wimg)));
+  const float *w0[32], *w2[32];
+  for (int l = 0; l < nl; ++l) {
+    RQ(layers[l].node_w0 && layers[l].node_w2 && wimg[l]);
+    w0[l] = layers[l].node_w0; w2[l] = layers[l].node_w2;
+  }
+  CK(launch_node_h_wprep(d->C, ldn(d), nl, w0, w2, wimg, S(stream)));
   return 0;
 }
 
@@ -695,7 +719,8 @@ size_t fegnn_layer_saved_floats(const fegnn_dims* d) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   return 3 * al4(N * kH) /*P Av Uh*/ + al4(Nl * kH) /*Q*/ + 2 * al4(N) /*sv sg*/ + al4(B * C * C) + al4(B * 3 * C) +
          al4(B * C * kH) /*M Zc G1*/ + al4(N * kH) + al4(N * 3) /*msum tsum*/ + al4(N * C * kH) /*u*/ +
-         al4(N * kH) /*zh1*/ + al4(B * 3 * C) + al4(B * C * kH) /*Dsum Usum*/ + 16 /*scratch*/;
+         al4(N * kH) /*zh1*/ + al4(B * 3 * C) + al4(B * C * kH) /*Dsum Usum*/ + 16 /*scratch*/ +
+         (C + 2) * 2 * (size_t)(kH * kH) /*wimg*/;
 }
 int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved* out) {
   TRY(check_dims(d));
@@ -711,6 +736,7 @@ int fegnn_layer_saved_bind(const fegnn_dims* d, float* block, fegnn_layer_saved*
   out->sv = take(N); out->sg = take(N);
   out->M = take(B * C * C); out->Zc = take(B * 3 * C); out->G1 = take(B * C * kH);
   out->u = take(N * C * kH);
+  out->wimg = take((C + 2) * 2 * (size_t)(kH * kH));
   return 0;
 }
 size_t fegnn_layer_saved_accum_floats(const fegnn_dims* d) {
@@ -820,6 +846,15 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
     CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));
   }
   CK(launch_graph_xsum(d->N, w.x[0], g->batch, w.xsum[0], st));
+  // phi_h on the tensor cores: the operand-tile images of every layer's weight blocks in ONE launch here, ahead of the chain
+  bool wimg_ready = false;
+  if (g_node_fwd_mode != 0 && !rf && L > 1) {
+    const float *w0[32], *w2[32];
+    float* img[32];
+    for (int l = 0; l + 1 < L; ++l) { w0[l] = layers[l].node_w0; w2[l] = layers[l].node_w2; img[l] = w.saved[l].wimg; }
+    CK(launch_node_h_wprep(d->C, ldn(d), L - 1, w0, w2, img, st));
+    wimg_ready = true;
+  }
   SideStream* sd = side_stream();
   RQ(sd != nullptr);
   void* side = sd->st;
@@ -827,6 +862,7 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
     dl.flags |= FEGNN_F_PREZEROED;
+    if (wimg_ready) dl.flags |= FEGNN_F_WIMG_READY;
     const bool last = rf || l == L - 1;
     if (last) dl.flags |= FEGNN_F_LAST;
     const fegnn_layer_params* p = &layers[l];

@@ -320,6 +320,19 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// clock64 stamps between the barriers of ONE thread of ONE CTA (instrumented build only: -DFEGNN_TRACE, tools/)
+#ifdef FEGNN_TRACE
+#define VTR_DECL() long long tr_t[64]; int tr_l[64]; int tri_ = 0; const bool tr_on = threadIdx.x == 0 && blockIdx.x == 1; \
+  if (tr_on) { tr_t[0] = clock64(); tr_l[0] = __LINE__; tri_ = 1; }
+#define VTR() do { if (tr_on && tri_ < 64) { tr_t[tri_] = clock64(); tr_l[tri_] = __LINE__; ++tri_; } } while (0)
+#define VTR_PRINT(name) do { if (tr_on) { printf("VTRACE %s :", name); \
+  for (int i_ = 1; i_ < tri_; ++i_) printf(" L%d:%lld", tr_l[i_], tr_t[i_] - tr_t[i_ - 1]); printf("\n"); } } while (0)
+#else
+#define VTR_DECL() do { } while (0)
+#define VTR() do { } while (0)
+#define VTR_PRINT(name) do { } while (0)
+#endif
+
 // Number of kernels this library has launched (host counter; read through fegnn_launch_count()).
 inline unsigned long long g_launches = 0;
 

@@ -161,6 +161,7 @@ __device__ __forceinline__ float pow2_to(float bound, int e_target) {   // large
 
 template <int CG>
 __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, const unsigned* stats) {
+  VTR_DECL();
   constexpr int NTG = 128 * CG, NT = 2 * NTG, CPT = kH / CG, NP = CPT / 2, NWG = NTG / 32, RPW = kTM / NWG;
   using SM = Smem4<CG>;
   using GV = GroupVec<CG>;
@@ -221,11 +222,13 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
   }
   if (t < 32) umma::tmem_alloc<512>(&sv->tmem_slot);
   __syncthreads();                               // mw[] zeroed, fp32 vectors staged
+    VTR();
   if (lane == 0) {
     atomicMax(&sv->mw[0], __float_as_uint(mw2));
     atomicMax(&sv->mw[1], __float_as_uint(mw3));
   }
   __syncthreads();
+    VTR();
   pdl_wait();                                    // everything above read weights only; `stats` comes from the pre-pass
   // ---- per-launch power-of-two scales (every thread, identical arithmetic).  Bounds from the pre-pass `stats`:
   //      |gs| <= dmax * sqrt3 * max|gt|  ->  sa ;  |w4| -> sb ;  g3 is stored times s3 = sa sb (<= 2^14)
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
+    VTR();
   umma::fence_after();
   const uint32_t tmem = sv->tmem_slot;
   const float s3 = sa * sb;
@@ -338,10 +342,12 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     const Geo* geo = &v->geo[cur];
     if (!first_tile) {                           // the previous tile's last GEMMs still read AUX, TM, TA, TG
       umma::mbar_wait(&v->bar[4], phase ^ 1);
+    VTR();
       umma::fence_after();
     }
     umma::fence_before();
     group_sync();
+    VTR();
     // ---- aux columns (1, q, ea0..ea3, gs sa [written in epilogue 2], 0) = chunk 0 of the row, from the geometry that was
     //      computed one tile ahead
     if (tg < kTM)
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
           make_uint4(pack2(geo->srow[tg] >= 0 ? 1.f : 0.f, geo->sq[tg]), pack2(geo->sea[tg * kTcMaxFe], geo->sea[tg * kTcMaxFe + 1]),
                      pack2(geo->sea[tg * kTcMaxFe + 2], geo->sea[tg * kTcMaxFe + 3]), 0u);
     group_sync();
+    VTR();
     // ---- assembly: t = z1 / 2 (P + Q in fp32, then packed), a1 = silu(z1) -> TA, silu'(z1) -> T3 (both fp16).  Half-warp per row, 4 columns
     //      per lane.  Rows past E carry t = 0 (a1 = 0, silu' = 1/2): their upstream gradients are zero.
     {
@@ -398,6 +405,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       }
     }
     group_sync();
+    VTR();
     // ---- row owners move a1 (A operand of G1) and silu'(z1) into tensor memory
     {
       uint32_t p[NP], pd[NP];
@@ -410,6 +418,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     umma::fence_smem_to_async();       // TA / AUX: generic-proxy writes -> visible to the tensor core
     umma::fence_before();
     group_sync();
+    VTR();
     if (wg == 0) {
       umma::fence_after();
       if (elect_one()) {
@@ -424,6 +433,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       if (tile + 2 * tstride < ntiles) load_idx_async(tile + 2 * tstride);
     }
     umma::mbar_wait(&v->bar[0], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 1: m = silu(z2 + b2) -> A operand and TM ; silu'(z2) -> D2T
     {
@@ -447,6 +457,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     umma::fence_smem_to_async();
     umma::fence_before();
     group_sync();
+    VTR();
     if (wg == 0) {
       umma::fence_after();
       if (elect_one()) {
@@ -456,6 +467,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[1], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 2: a3 = silu(z3 + b3) -> T3, s = w4 . a3 ; g3 = (gs sa) (w4 sb) silu'(z3) -> A operand and TG
     {
@@ -484,6 +496,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       v->spart[cg * kTM + row] = part;
       store_row<NP>(T3, row, cg, pa);
       group_sync();
+    VTR();
       float s = 0.f;
 #pragma unroll
       for (int g = 0; g < CG; ++g) s += v->spart[g * kTM + row];
@@ -512,6 +525,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     umma::fence_smem_to_async();
     umma::fence_before();
     group_sync();
+    VTR();
     if (wg == 0) {
       umma::fence_after();
       if (elect_one()) {
@@ -539,6 +553,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
         for (int j = 0; j < CPT; ++j) u[j] = 0.f;
       }
       umma::mbar_wait(&v->bar[2], phase);
+    VTR();
       umma::fence_after();
       float acc[CPT];
       uint32_t pd[NP];
@@ -549,12 +564,14 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
         pd[j >> 1] = h2u(__hmul2(__floats2half2_rn(fmaf(acc[j], k32, u[j]), fmaf(acc[j + 1], k32, u[j + 1])), u2h(pd[j >> 1])));
       tmem_stu<NP>(tlane + kOPA + cg * NP, pd);
       umma::mbar_wait(&v->bar[5], phase);        // the dW3 / dw4 GEMMs have finished reading TG (g3), TM (m), T3 (a3)
+    VTR();
       store_row<NP>(TG, row, cg, pd);
       tmem_st_wait();
     }
     umma::fence_smem_to_async();
     umma::fence_before();
     group_sync();
+    VTR();
     if (wg == 0) {
       umma::fence_after();
       if (elect_one()) {
@@ -565,6 +582,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[3], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 4: gz1 = (g2 W2) * silu'(z1) (times s1) -> TM ; gq = gz1 . wq
     {
@@ -593,6 +611,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
     umma::fence_smem_to_async();
     umma::fence_before();
     group_sync();
+    VTR();
     if (wg == 0) {
       umma::fence_after();
       if (elect_one()) {
@@ -630,6 +649,7 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
         }
       }
     }
+    VTR();
     if (tg < kTM && !(a.exp & 2u)) {
       const int r = geo->srow[tg], c = geo->scol[tg];
       float gqs = 0.f;
@@ -657,13 +677,16 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
         for (int k = 0; k < 3; ++k) atomicAdd(a.gx + (size_t)r * 3 + k, gd[k]);
       }
     }
+    VTR();
   }
   // ---- flush: each group waits for its last aux GEMM; then the whole CTA meets and group 0's warps read BOTH groups'
   //      weight-gradient tiles (M = 64 layout: row n of group g in lane (n / 16) * 32 + n % 16 + 16 g)
   if (!first_tile) umma::mbar_wait(&v->bar[4], phase ^ 1);
+    VTR();
   umma::fence_after();
   umma::fence_before();
   __syncthreads();
+    VTR();
   umma::fence_after();
   // a group that saw no tile left its accumulator lanes undefined: only groups with first_tile == false contribute.
   // (blockIdx.x * 2 + G < ntiles decides that for every thread of the CTA without communication.)
@@ -709,7 +732,10 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
   }
   umma::fence_before();
   __syncthreads();
+    VTR();
   if (t < 32) umma::tmem_dealloc<512>(tmem);
+  VTR();
+  VTR_PRINT("edge_bwd");
 }
 
 }  // namespace bwd4

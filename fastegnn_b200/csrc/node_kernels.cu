@@ -280,6 +280,7 @@ struct NodeHArgs {
   const float *h, *Uh, *msum, *dinv, *u;
   const float *node_w0, *node_w2, *node_b2;
   float *zh1, *h_new;
+  float* wimg;               // tensor-core forward: operand-tile images of the weight blocks (node_tc.cu)
   // backward
   const float* gh_new;
   float *gzh1, *gm, *gu;

@@ -174,6 +174,277 @@ __global__ void __launch_bounds__(256, 2) node_pre_fwd_tc_kernel(NodePreArgs a) 
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------- node_h forward
+// phi_h (models/FastEGNN.py:153-166) on the tensor cores with fp32-grade results (error-compensated 3xTF32, the same split as
+// edge_forward mode 3), so that it may be the DEFAULT of the forward pass -- single-pass TF32 on h breaks the script's
+// equivariance tolerance:
+//     zh1 = Uh + (msum / deg) W0a^T + sum_c u[:, c, :] W0u_c^T          h' = h + silu(zh1) W2^T + b2
+// The fp32 FMA form (node_kernels.cu) accumulated zh1 with one red.global.add pass per K-block (1 + C passes over [N, 64])
+// and ran at 14 TFLOP/s at 1 M nodes; a step spent 13 % of its time there.  Here a CTA owns a 128-node tile and WALKS the
+// K-blocks through a two-stage ring: the rows of block b + 1 (and its 64x64 weight block) are in flight in registers while
+// the three tcgen05.mma passes of block b run (a_hi w_hi + a_lo w_hi + a_hi w_lo; fp32 accumulator in tensor memory for the
+// whole sum -- no atomics, zh1 is written once).  silu(zh1) is split on chip into the next ring slot, so the output Linear is
+// just one more block.  Rows travel global -> registers -> swizzled K-major tiles in (row, 16-byte chunk) order (a warp-wide
+// access covers 2 rows x 256 contiguous bytes) and the accumulators leave through a staging tile the same way: Uh and h are
+// added in that phase in exact fp32.  Algorithmic bytes per node: 256 (3 + C) read + 512 written; HBM-bound from ~10^5 nodes.
+struct HVec {
+  float b2[kH];
+  uint64_t bar[2];                 // MMAs that read operand slot 0 / 1
+  uint32_t tmem_slot;
+};
+struct HSmem {
+  static constexpr int kT = kTM * kH * 4, kW = kH * kH * 4;
+  static constexpr int off_A = 0;                  // [2 slots][hi | lo] operand tiles
+  static constexpr int off_W = 4 * kT;             // [3 slots][hi | lo] weight tiles (cp.async ring)
+  static constexpr int off_vec = off_W + 6 * kW;
+  static constexpr size_t bytes = off_vec + sizeof(HVec) + 1024;
+  static_assert(bytes <= 232448, "node_h forward: shared memory");
+};
+constexpr uint32_t kNH_ACC1 = 0, kNH_ACC2 = 64;    // 128 tensor-memory columns
+constexpr int kWimgFloats = 2 * kH * kH;           // one weight block: hi | lo operand-tile images
+
+// Weight pre-pass: block b of layer l -> its operand-tile image (what the main kernel's ring slot holds, byte for byte), so the
+// main loop moves weights with cp.async only.  In the reference layout the u blocks are interleaved (flatten order k * C + c,
+// models/FastEGNN.py:157): read in place, one 64x64 block drags the whole [64, 64 C] slab through L1 -- measured at C = 8:
+// 128 KB of L2 traffic per block against 32 KB of node rows, 7 000 cycles per block.
+struct WPrepArgs {
+  int C, ldn;
+  const float* w0[32];
+  const float* w2[32];
+  float* wimg[32];
+};
+__global__ void __launch_bounds__(256) node_h_wprep_kernel(const __grid_constant__ WPrepArgs a) {
+  constexpr int NT = 256, NWR = kH * kH / NT;
+  pdl_trigger();
+  const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x, nb1 = a.C + 1;
+  const float* base = b < nb1 ? a.w0[l] : a.w2[l];
+  const int ld = b < nb1 ? a.ldn : kH, off = b == 0 ? kH : b < nb1 ? 2 * kH + (b - 1) : 0, wks = (b == 0 || b >= nb1) ? 1 : a.C;
+  float w[NWR];
+#pragma unroll
+  for (int j = 0; j < NWR / 4; ++j) {
+    const int i = t + j * NT, n = i >> 4, c = i & 15;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[4 * j + q] = base[(size_t)n * ld + off + (size_t)(4 * c + q) * wks];
+  }
+  pdl_wait();      // the images are written only after the predecessor has completed (a shared block may still be read)
+  float* img = a.wimg[l] + (size_t)b * kWimgFloats;
+#pragma unroll
+  for (int j = 0; j < NWR / 4; ++j) {
+    const int i = t + j * NT, n = i >> 4, c = i & 15;
+    const float4 x = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    const float4 hi = make_float4(umma::to_tf32(x.x), umma::to_tf32(x.y), umma::to_tf32(x.z), umma::to_tf32(x.w));
+    const uint32_t o = umma::tile_chunk_off(n, c, kH) >> 2;
+    *reinterpret_cast<float4*>(img + o) = hi;
+    *reinterpret_cast<float4*>(img + kH * kH + o) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
+  VTR_DECL();
+  constexpr int NT = 256, CPT = 32, NA = kTM * 16 / NT;
+  using SM = HSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
+  HVec* v = reinterpret_cast<HVec*>(smem + SM::off_vec);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
+  const int rr0 = t >> 4, c16 = t & 15;            // cooperative phases: rows rr0 + 16 j, chunk c16
+  const int nb1 = a.C + 1;                         // K-blocks of zh1: 0 = message mean, 1 + c = u[:, c, :]
+  auto At = [&](int s_) { return smem + SM::off_A + s_ * 2 * SM::kT; };
+  auto Wt = [&](int w_) { return smem + SM::off_W + w_ * 2 * SM::kW; };
+
+  float4 areg[NA];
+  float sc[NA];
+  // weight block b -> ring slot w_ (32 KB image, 8 x 16 bytes per thread), one cp.async group; b < 0: an empty group
+  auto fetch_w = [&](int b, int w_) {
+    if (b >= 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wimg + (size_t)b * kWimgFloats);
+#pragma unroll
+      for (int j = 0; j < 2 * SM::kW / 16 / NT; ++j) {
+        const int i = t + j * NT;
+        cp_async16(Wt(w_) + 16 * i, src + 16 * i, 16);
+      }
+    }
+    cp_async_commit();
+  };
+  auto load_rows = [&](float4 (&dst)[NA], const float* src, size_t ld, int i0) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int r = i0 + rr0 + 16 * j;
+      dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < a.N) dst[j] = *reinterpret_cast<const float4*>(src + (size_t)r * ld + 4 * c16);
+    }
+  };
+  auto load_a = [&](int b, int i0) {
+    if (b == 0) {
+      load_rows(areg, a.msum, kH, i0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const int r = i0 + rr0 + 16 * j;
+        sc[j] = (a.dinv != nullptr && r < a.N) ? a.dinv[r] : 1.f;      // nullptr: plain sums (FEGNN_F_NODE_SUM)
+      }
+    } else {
+      load_rows(areg, a.u + (size_t)(b - 1) * kH, (size_t)a.C * kH, i0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) sc[j] = 1.f;
+    }
+  };
+  auto store_split = [&](uint8_t* tile, int j, float4 x) {
+    const float4 hi = make_float4(umma::to_tf32(x.x), umma::to_tf32(x.y), umma::to_tf32(x.z), umma::to_tf32(x.w));
+    const uint32_t o = umma::tile_chunk_off(rr0 + 16 * j, c16, kTM);
+    *reinterpret_cast<float4*>(tile + o) = hi;
+    *reinterpret_cast<float4*>(tile + SM::kT + o) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+  };
+  auto store_a = [&](int s_) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j)
+      store_split(At(s_), j, make_float4(areg[j].x * sc[j], areg[j].y * sc[j], areg[j].z * sc[j], areg[j].w * sc[j]));
+  };
+
+  // ---- prologue (weights only): vectors, barriers, tensor memory
+  for (int i = t; i < kH; i += NT) v->b2[i] = a.node_b2[i];
+  if (t == 0) {
+    umma::mbar_init(&v->bar[0], 1);
+    umma::mbar_init(&v->bar[1], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<128>(&v->tmem_slot);
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  VTR();
+  pdl_wait();                                      // the weight images come from the pre-pass, the rows from the layer's phases
+  VTR();
+  const uint32_t tmem = v->tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
+  const uint32_t idesc = umma::make_idesc_tf32(128, kH);
+  // descriptors of slot 0; operand slot 1 lies 2 kT, weight slot w 2 w kW bytes further (only the 14-bit address field moves)
+  const uint64_t dA0 = umma::make_desc(umma::smem_u32(At(0))), dW0 = umma::make_desc(umma::smem_u32(Wt(0)));
+  // D (+)= A W^T in three passes: operand slot s_, weight slot w_
+  auto issue = [&](uint32_t acc, int s_, int w_, bool accumulate) {
+    if (warp == 0) {
+      umma::fence_after();
+      if (umma::elect_one()) {
+        const uint64_t dA = dA0 + (uint64_t)(s_ * ((2 * SM::kT) >> 4)), dW = dW0 + (uint64_t)(w_ * ((2 * SM::kW) >> 4));
+        umma::gemm_k64_desc(acc, dA, kTM, dW, kH, idesc, accumulate);
+        umma::gemm_k64_desc(acc, dA + (uint64_t)(SM::kT >> 4), kTM, dW, kH, idesc, true);
+        umma::gemm_k64_desc(acc, dA, kTM, dW + (uint64_t)(SM::kW >> 4), kH, idesc, true);
+        umma::commit(&v->bar[s_]);
+      }
+      __syncwarp();
+    }
+  };
+  uint32_t ph_bits = 0, pend_bits = 0;             // per operand slot: mbarrier phase, commit outstanding
+  auto wait_slot = [&](int s_) {                   // the MMAs that read operand slot s_ have completed
+    if ((pend_bits >> s_) & 1u) {
+      umma::mbar_wait(&v->bar[s_], (ph_bits >> s_) & 1u);
+      umma::fence_after();
+      ph_bits ^= 1u << s_;
+      pend_bits &= ~(1u << s_);
+    }
+  };
+
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  int g = 0, wq = 0;                               // running block count: operand slot g & 1, weight slot wq = g % 3
+  if ((int)blockIdx.x < ntiles) {
+    fetch_w(0, 0);
+    load_a(0, blockIdx.x * kTM);
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = tile * kTM;
+    const bool more = tile + (int)gridDim.x < ntiles;
+    float4 uh[NA], hr[NA];
+    for (int b = 0; b < nb1; ++b, ++g) {
+      const int s_ = g & 1, wn = wq == 2 ? 0 : wq + 1;
+      wait_slot(s_);                               // block g - 2 is done: operand slot s_ and weight slot (g + 1) % 3 are free
+      VTR();
+      fetch_w(b + 1, wn);                          // next block's weights (b + 1 == nb1: the output Linear) travel a full block ahead
+      store_a(s_);
+      cp_async_wait_group<1>();                    // this block's weights have landed
+      umma::fence_smem_to_async();
+      umma::fence_before();
+      __syncthreads();
+      VTR();
+      if (b + 1 < nb1) load_a(b + 1, i0);          // next block's rows travel under this block's MMAs
+      else load_rows(uh, a.Uh, kH, i0);
+      issue(tmem + kNH_ACC1, s_, wq, b > 0);
+      pend_bits |= 1u << s_;
+      wq = wn;
+    }
+    // ---- output Linear = one more block whose operand is made on chip
+    const int s2 = g & 1, so = s2 ^ 1, wn = wq == 2 ? 0 : wq + 1;
+    wait_slot(s2);
+    fetch_w(more ? 0 : -1, wn);                    // first block of the next tile
+    VTR();
+    wait_slot(so);                                 // zh1 - Uh is complete in tensor memory; both operand slots are free
+    load_rows(hr, a.h, kH, i0);
+    if (more) load_a(0, (tile + gridDim.x) * kTM);
+    VTR();
+    uint8_t* ST = At(so);                          // staging tile (row owners -> (row, chunk) order)
+    {
+      float z[CPT];
+      tmem_ld<CPT>(tlane + kNH_ACC1, z);
+#pragma unroll
+      for (int ch = 0; ch < CPT / 4; ++ch)
+        *reinterpret_cast<float4*>(ST + umma::tile_chunk_off(row, cg * (CPT / 4) + ch, kTM)) =
+            make_float4(z[4 * ch], z[4 * ch + 1], z[4 * ch + 2], z[4 * ch + 3]);
+    }
+    umma::fence_before();
+    __syncthreads();
+    VTR();
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int rr = rr0 + 16 * j;
+      float4 z = *reinterpret_cast<const float4*>(ST + umma::tile_chunk_off(rr, c16, kTM));
+      z.x += uh[j].x; z.y += uh[j].y; z.z += uh[j].z; z.w += uh[j].w;
+      if (i0 + rr < a.N) *reinterpret_cast<float4*>(a.zh1 + (size_t)(i0 + rr) * kH + 4 * c16) = z;
+      store_split(At(s2), j, make_float4(silu_f(z.x), silu_f(z.y), silu_f(z.z), silu_f(z.w)));
+    }
+    cp_async_wait_group<1>();                      // the output Linear's weights have landed
+    umma::fence_smem_to_async();
+    umma::fence_before();
+    __syncthreads();
+    VTR();
+    issue(tmem + kNH_ACC2, s2, wq, false);
+    pend_bits |= 1u << s2;
+    wait_slot(s2);
+    VTR();
+    {
+      float o[CPT];
+      tmem_ld<CPT>(tlane + kNH_ACC2, o);
+#pragma unroll
+      for (int ch = 0; ch < CPT / 4; ++ch) {
+        const float4 bb = *reinterpret_cast<const float4*>(v->b2 + c0 + 4 * ch);
+        *reinterpret_cast<float4*>(ST + umma::tile_chunk_off(row, cg * (CPT / 4) + ch, kTM)) =
+            make_float4(o[4 * ch] + bb.x, o[4 * ch + 1] + bb.y, o[4 * ch + 2] + bb.z, o[4 * ch + 3] + bb.w);
+      }
+    }
+    umma::fence_before();
+    __syncthreads();
+    VTR();
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int rr = rr0 + 16 * j;
+      if (i0 + rr < a.N) {
+        const float4 o = *reinterpret_cast<const float4*>(ST + umma::tile_chunk_off(rr, c16, kTM));
+        *reinterpret_cast<float4*>(a.h_new + (size_t)(i0 + rr) * kH + 4 * c16) =
+            make_float4(hr[j].x + o.x, hr[j].y + o.y, hr[j].z + o.z, hr[j].w + o.w);
+      }
+    }
+    ++g;
+    wq = wn;
+    __syncthreads();                               // ST (= the slot the next block is stored to) has been read
+    VTR();
+  }
+  cp_async_wait();
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<128>(tmem);
+  VTR_PRINT("node_h_fwd");
+}
+
 }  // namespace ntc
 
 cudaError_t launch_node_pre_fwd_tc(const NodePreArgs& a, int sms, cudaStream_t st) {
@@ -188,6 +459,31 @@ cudaError_t launch_node_pre_fwd_tc(const NodePreArgs& a, int sms, cudaStream_t s
   if (ntiles == 0) return cudaSuccess;
   int per = ntiles < sms ? ntiles : sms;          // CTAs per group; 2 groups -> up to 2 CTAs / SM
   ntc::node_pre_fwd_tc_kernel<<<2 * per, 256, ntc::PreSmem::bytes, st>>>(a); ++g_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_node_h_wprep(int C, int ldn, int nl, const float* const* w0, const float* const* w2, float* const* wimg,
+                                cudaStream_t st) {
+  if (nl <= 0) return cudaSuccess;
+  ntc::WPrepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.ldn = ldn;
+  for (int l = 0; l < nl; ++l) { a.w0[l] = w0[l]; a.w2[l] = w2[l]; a.wimg[l] = wimg[l]; }
+  if (cudaError_t e_ = launch_pdl(ntc::node_h_wprep_kernel, dim3(C + 2, nl), 256, 0, st, a)) return e_;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_node_h_fwd_tc(const NodeHArgs& a, int sms, cudaStream_t st) {
+  static DevOnce attr;
+  if (!attr.get()) {
+    cudaError_t e = cudaFuncSetAttribute(ntc::node_h_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ntc::HSmem::bytes);
+    if (e != cudaSuccess) return e;
+    attr.set();
+  }
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if (ntiles == 0) return cudaSuccess;
+  if (cudaError_t e_ = launch_pdl(ntc::node_h_fwd_tc_kernel, ntiles < sms ? ntiles : sms, 256, ntc::HSmem::bytes, st, a)) return e_;
   return cudaGetLastError();
 }
 

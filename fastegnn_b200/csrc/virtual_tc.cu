@@ -215,6 +215,7 @@ constexpr uint32_t kF_ACC0 = 0, kF_ACCH = 64, kF_OPA = 192;    // 256 columns
 
 template <int CG>
 __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a) {
+  VTR_DECL();
   constexpr int NT = 128 * CG, CPT = kH / CG, NW = NT / 32;
   using SM = FwdSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   umma::fence_smem_to_async();
   umma::fence_before();
   __syncthreads();
+    VTR();
   umma::fence_after();
   pdl_wait();
   const uint32_t tmem = v->tmem_slot;
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     umma::fence_before();
     __syncthreads();
+    VTR();
     // ---- geometry: one thread per (node, channel) row
     if (t < kTM) {
       const int jn = t / C, c = t - jn * C;
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       v->srho[t] = rho;
     }
     __syncthreads();
+    VTR();
     const bool single = v->b_first == v->b_last;
     if (!single || v->b_first != cur_b) {
       const int nb = single ? v->b_first : -1;
@@ -333,6 +337,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
     umma::fence_smem_to_async();
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       __syncwarp();
     }
     umma::mbar_wait(&v->bar[0], phase);
+    VTR();
     umma::fence_after();
     // ---- epilogue 1: u = silu(z2 + c2) -> HBM (saved for backward / phi_h), tensor memory (A of GH), T (Usum walk)
     {
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
     }
     umma::fence_before();
     __syncthreads();
+    VTR();
     if (warp == 0) {
       umma::fence_after();
       if (umma::elect_one()) {
@@ -379,6 +386,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
     }
     rows_to_graph<NT>(T, v->skey, &v->acc, C, TN, single, a.Usum);                 // overlaps GH
     umma::mbar_wait(&v->bar[1], phase);
+    VTR();
     umma::fence_after();
     phase ^= 1;
     // ---- epilogue 2: the two coordinate heads  s = w . silu(z + b)
@@ -395,6 +403,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       v->spX[cg * kTM + row] = pX;
     }
     __syncthreads();
+    VTR();
     if (t < kTM) {
       float sxv = 0.f, sX = 0.f;
 #pragma unroll
@@ -414,6 +423,7 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
       v->sval[t * 3 + 0] = val[0]; v->sval[t * 3 + 1] = val[1]; v->sval[t * 3 + 2] = val[2];
     }
     __syncthreads();
+    VTR();
     if (single && warp == NW - 1) small_from_rows(v->sval, &v->acc, C, TN, lane);
     if (warp * 32 < TN) {                 // x' (models/FastEGNN.py:133-142) and its per-graph sum
       const int i = tile * TN + t;
@@ -448,7 +458,10 @@ __global__ void __launch_bounds__(128 * CG, 2) virtual_fwd_tc_kernel(VirtArgs a)
   acc_flush<NT>(&v->acc, cur_b, C, a.Usum, a.Dsum, a.xsum_new);
   umma::fence_before();
   __syncthreads();
+    VTR();
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
+  VTR();
+  VTR_PRINT("vfwd");
 }
 
 
@@ -512,17 +525,6 @@ __device__ __forceinline__ void bwd_geometry(const VirtArgs& a, BwdGeo* s, int t
 }
 
 
-#ifdef FEGNN_TRACE
-#define VTR_DECL() long long tr_t[64]; int tr_l[64]; int tri_ = 0; const bool tr_on = threadIdx.x == 0 && blockIdx.x == 1; \
-  if (tr_on) { tr_t[0] = clock64(); tr_l[0] = __LINE__; tri_ = 1; }
-#define VTR() do { if (tr_on && tri_ < 64) { tr_t[tri_] = clock64(); tr_l[tri_] = __LINE__; ++tri_; } } while (0)
-#define VTR_PRINT(name) do { if (tr_on) { printf("VTRACE %s :", name); \
-  for (int i_ = 1; i_ < tri_; ++i_) printf(" L%d:%lld", tr_l[i_], tr_t[i_] - tr_t[i_ - 1]); printf("\n"); } } while (0)
-#else
-#define VTR_DECL() do { } while (0)
-#define VTR() do { } while (0)
-#define VTR_PRINT(name) do { } while (0)
-#endif
 // ---- heads kernel
 struct HeadsVec {
   float bh[2 * kH], wh[2 * kH], cwh[2 * kH];

@@ -61,6 +61,8 @@ extern "C" {
                                  Usum | scratch of the saved block -- contiguous from .msum, fegnn_layer_saved_accum_floats() words --
                                  xsum_new, gG1, gx, gP, gQ): the phase skips its own fills.  fegnn_model_forward / _backward set it
                                  and issue the fills once per step, off the kernel chain.                                         */
+#define FEGNN_F_WIMG_READY 512u /* fegnn_node_h_forward: the weight-block images in saved.wimg are current (written by
+                                  fegnn_node_h_weight_images for this layer's parameters): skip the in-call pre-pass */
 
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
@@ -131,6 +133,8 @@ typedef struct fegnn_layer_saved {   /* the accumulators msum, tsum, zh1, Dsum, 
   float *zh1;               /* [N,H] phi_h pre-activation                                 */
   float *Dsum, *Usum;       /* [B,3,C] [B,C,H] per-graph partial sums (all-reduced when partitioned) */
   float *scratch;           /* [16] words of per-layer kernel scratch (edge backward mode 5: the bound pre-pass)  */
+  float *wimg;              /* [(C+2), 2, 64*64] phi_h weight blocks as tcgen05 operand-tile images (3xTF32 hi | lo),
+                               rewritten by every fegnn_node_h_forward on the tensor cores (node_forward mode 1 / 3) */
 } fegnn_layer_saved;
 
 const char* fegnn_last_error(void);
@@ -145,9 +149,10 @@ unsigned long long fegnn_launch_count(void);
  * same operands with packed-fp16 epilogue arithmetic (SiLU on fp16 pairs), 256 / 512 threads per tile, 6 = auto (default):
  * 7 wherever the tensor-core form applies, else 4 / 0.  Layers with attention=True or Fe > 4 always take mode 0 in
  * the backward (Fe > 4 also in the forward).  "virtual_forward" / "virtual_backward": 0 = fp32 FMA kernels, 1 = tcgen05
- * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels (default), 1 = tcgen05
- * TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's atol 1e-4 on
- * its U(0,10) inputs).  "node_backward": 0 = fp32 FMA kernels, 1 = tcgen05 TF32, 2 = auto (default; = 1 today)
+ * TF32 kernels (default; attention=True layers always take 0).  "node_forward": 0 = fp32 FMA kernels, 3 (default) = fegnn_node_h_forward
+ * on tcgen05 error-compensated 3xTF32 tiles (fp32-grade) with fegnn_node_pre_forward on the fp32 FMA kernel, 1 = that plus
+ * single-pass tcgen05 TF32 for fegnn_node_pre_forward (opt-in: rounding the unbounded h to TF32 costs equivariant_test.py's
+ * atol 1e-4 on its U(0,10) inputs).  "node_backward": 0 = fp32 FMA kernels, 1 = tcgen05 TF32, 2 = auto (default; = 1 today)
  * for fegnn_node_pre_backward and fegnn_node_h_backward (gradients do not enter the forward equivariance).  Process-wide. */
 int fegnn_set_mode(const char* phase, int mode);
 int fegnn_get_mode(const char* phase);
@@ -222,6 +227,11 @@ int fegnn_virtual_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
 /* phi_h (:153-166) */
 int fegnn_node_h_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* h,
                          fegnn_layer_saved* sv, float* h_new, void* stream);
+/* Operand-tile images (3xTF32 hi | lo, K-major SWIZZLE_128B) of the phi_h weight blocks of nl layers, one launch: layer l
+ * reads node_w0 / node_w2 of layers[l] and writes wimg[l] ([(C+2), 2, 64*64] floats, e.g. saved.wimg).  Weights only: a
+ * caller may run it once per step next to the kernel chain and pass FEGNN_F_WIMG_READY to fegnn_node_h_forward. */
+int fegnn_node_h_weight_images(const fegnn_dims* d, int32_t nl, const fegnn_layer_params* layers, float* const* wimg,
+                               void* stream);
 /* Z' and S' (:146-150,:168-177) */
 int fegnn_graph_post_forward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_layer_params* p, const float* Z,
                              const float* S, const fegnn_layer_saved* sv, float* Z_new, float* S_new, void* stream);

@@ -459,6 +459,51 @@ def test_virtual_backward_modes(name, mode, layer):
     assert not bad, bad
 
 
+NODE_H_FWD_TOL = {0: TOL, 3: 1.2e-5}   # fp32 FMA kernels ; tcgen05 error-compensated 3xTF32 (fp32-grade; 2x the worst observed, 5.9e-6 at K = 576)
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "flags_c2", "small_graphs"])
+def test_node_h_forward_modes(name, mode):
+    """fegnn_node_h_forward alone (phi_h, models/FastEGNN.py:153-166): the fp32 FMA kernels against the tcgen05 3xTF32 kernel
+    (node_tc.cu, "node_forward" mode 3 = default), both against staged.node_h_fwd from exact Uh, msum, u."""
+    s = _setup(name)
+    L, lib = s["L"], s["L"].lib
+    cfg, sm, dev, graph = s["cfg"], s["sm"], s["dev"], s["graph"]
+    st = torch.cuda.current_stream().cuda_stream
+    l = 0
+    Cc, N, B, H = cfg.virtual_channels, graph.N, graph.B, 64
+    dims = s["make_dims"](N, N, graph.E, B, Cc, graph.Fe, s["flags"], cfg.gravity)
+    ptrs = s["layer_ptrs"](s["gparams"], f"gcl_{l}")
+    sv = s["SavedBlock"](dims, dev)
+    sv.buf.zero_()
+    S_ = sm.saved[l]
+    h = _g(S_["h"], dev)
+    sv.view("msum", (N, H)).copy_(_g(S_["e"]["msum"], dev))
+    sv.view("u", (N, Cc, H)).copy_(_g(S_["vf"]["u"], dev))
+    sv.view("Uh", (N, H)).copy_(_g(S_["npre"]["Uh"], dev))
+    h_new = torch.full((N, H), float("nan"), device=dev, dtype=torch.float32)
+    old = L.get_mode("node_forward")
+    try:
+        L.set_mode("node_forward", mode)
+        L.check(lib.fegnn_node_h_forward(C.byref(dims), C.byref(graph.c), C.byref(ptrs), L.ptr(h), C.byref(sv.c),
+                                         L.ptr(h_new), st))
+        torch.cuda.synchronize()
+    finally:
+        L.set_mode("node_forward", old)
+    tol = NODE_H_FWD_TOL[mode]
+    errs = []
+    _chk(errs, "node_h.zh1", sv.view("zh1", (N, H)), S_["nh"]["zh1"], tol)
+    _chk(errs, "node_h.h_new", h_new, S_["nh"]["h_new"], tol)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/node_h_fwd_mode{mode}_{name}.txt", "w") as fh:
+        for n_, e, t in errs:
+            fh.write(f"{'FAIL' if not e <= t else 'ok  '} {n_}: {e:.3e} (tol {t:.0e})\n")
+    bad = [(n_, f"{e:.3e}") for n_, e, t in errs if not e <= t]
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", ["c3", "c3_gravity_heavy", "c8", "small_graphs"])
 @pytest.mark.parametrize("layer", [0, 1])
