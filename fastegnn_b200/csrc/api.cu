@@ -75,6 +75,7 @@ int g_virt_bwd_mode = 1;
 // 3 (default) = node_pre on the fp32 FMA kernel, phi_h (fegnn_node_h_forward) on tcgen05 with the error-compensated 3xTF32
 // split (fp32-grade: node_tc.cu); mode 1 takes the same phi_h kernel.
 int g_node_fwd_mode = 3;
+const bool g_node_pre_tc3 = getenv("FEGNN_NODE_PRE_TC3") == nullptr || atoi(getenv("FEGNN_NODE_PRE_TC3")) != 0;   // experiment switch
 // per-node dense phases of the BACKWARD pass (node_pre_backward, node_h_backward): 0 = fp32 FMA kernels, 1 = tcgen05 TF32
 // (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default) = 1 today: up to two node tiles per SM
 // the per-tile kernel walks the weight blocks (measured at 8 000 nodes: step 1.380 ms against 1.416 ms with the fp32 kernels),
@@ -375,6 +376,7 @@ int fegnn_node_pre_forward(const fegnn_dims* d, const fegnn_layer_params* p, con
   NodePreArgs a = node_pre_args(d, p, h);
   a.P = sv->P; a.Q = sv->Q; a.Av = sv->Av; a.Uh = sv->Uh; a.sv = sv->sv; a.sg = sv->sg;
   if (g_node_fwd_mode == 1 && !(d->flags & FEGNN_F_RF)) CK(launch_node_pre_fwd_tc(a, sm_count(), S(stream)));
+  else if (g_node_fwd_mode == 3 && g_node_pre_tc3) CK(launch_node_pre_fwd_tc3(a, sm_count(), S(stream)));
   else CK(launch_node_pre_fwd(a, sm_count(), S(stream)));
   return 0;
 }

@@ -445,6 +445,208 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
   VTR_PRINT("node_h_fwd");
 }
 
+
+// ------------------------------------------------------------------------------------------------- node_pre forward, 3xTF32
+// The h-side halves of every first Linear (models/FastEGNN.py:104,115,139,142,162) with fp32-grade results: one CTA per
+// 128-node tile loads h ONCE (split hi | lo into the operand tile) and walks the 3-6 active weight blocks (P, Q, Av, Uh,
+// phi_v head, phi_g head); block k's three tcgen05.mma passes run into accumulator k & 1 while block k - 1 leaves through a
+// staging tile in (row, chunk) order and block k + 1's weights are split into the next slot of a three-slot ring.  The fp32
+// FMA kernel is a (tile, block) decomposition that reads h once per block and runs at a quarter of the FFMA peak.
+struct P3Vec {
+  float bias[2][kH], w2[2][kH];    // of block k in buffer k & 1: first-layer bias ; head output weights
+  float sp[kTM];                   // head: partial dot of the second column group
+  uint64_t bar[2];                 // MMAs into accumulator 0 / 1
+  uint32_t tmem_slot;
+};
+struct P3Smem {
+  static constexpr int kT = kTM * kH * 4, kW = kH * kH * 4;
+  static constexpr int off_A = 0;                  // h tile, hi | lo
+  static constexpr int off_W = 2 * kT;             // [3 slots][hi | lo]
+  static constexpr int off_ST = off_W + 6 * kW;    // staging tile
+  static constexpr int off_vec = off_ST + kT;
+  static constexpr size_t bytes = off_vec + sizeof(P3Vec) + 1024;
+  static_assert(bytes <= 232448, "node_pre forward (3xTF32): shared memory");
+};
+
+__global__ void __launch_bounds__(256, 1) node_pre_fwd_tc3_kernel(NodePreArgs a, int nactive) {
+  constexpr int NT = 256, CPT = 32, NA = kTM * 16 / NT, NWR = kH * kH / NT;
+  using SM = P3Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  pdl_trigger();
+  P3Vec* v = reinterpret_cast<P3Vec*>(smem + SM::off_vec);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int quarter = warp & 3, cg = warp >> 2, row = quarter * 32 + lane, c0 = cg * CPT;
+  const int rr0 = t >> 4, c16 = t & 15;
+  const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST, rf = a.flags & FEGNN_F_RF;
+  uint8_t* At = smem + SM::off_A;
+  uint8_t* ST = smem + SM::off_ST;
+  auto Wt = [&](int w_) { return smem + SM::off_W + w_ * 2 * SM::kW; };
+  auto blk_of = [&](int k) { return node_pre_block_id(k, last, grav, rf); };     // 0 P, 1 Q, 2 Av, 3 Uh, 4 phi_v, 5 phi_g
+  // block range of this CTA: with few tiles (gridDim.y = 2) two CTAs share a tile, each takes half of the blocks
+  const int kb = (int)blockIdx.y * nactive / (int)gridDim.y, ke = ((int)blockIdx.y + 1) * nactive / (int)gridDim.y;
+
+  float wreg[NWR];
+  float4 hreg[NA];
+  auto load_w = [&](int k) {                       // weights of the k-th active block: 4 x 16 contiguous bytes per thread
+    const int b = blk_of(k);
+    const float* src = b <= 1 ? a.edge_w0 : b == 2 ? a.edgev_w0 : b == 3 ? a.node_w0 : b == 4 ? a.vel_w0 : a.grav_w0;
+    const int ld = b <= 1 ? a.ld1 : b == 2 ? a.ldv : b == 3 ? a.ldn : kH, off = b == 1 ? kH : 0;
+    if (((ld | off) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < NWR / 4; ++j) {
+        const int i = t + j * NT, n = i >> 4, c = i & 15;
+        const float4 w = *reinterpret_cast<const float4*>(src + (size_t)n * ld + off + 4 * c);
+        wreg[4 * j] = w.x; wreg[4 * j + 1] = w.y; wreg[4 * j + 2] = w.z; wreg[4 * j + 3] = w.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NWR / 4; ++j) {
+        const int i = t + j * NT, n = i >> 4, c = i & 15;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wreg[4 * j + q] = src[(size_t)n * ld + off + 4 * c + q];
+      }
+    }
+  };
+  auto store_w = [&](int w_) {
+#pragma unroll
+    for (int j = 0; j < NWR / 4; ++j) {
+      const int i = t + j * NT, n = i >> 4, c = i & 15;
+      const float4 w = make_float4(wreg[4 * j], wreg[4 * j + 1], wreg[4 * j + 2], wreg[4 * j + 3]);
+      const float4 hi = make_float4(umma::to_tf32(w.x), umma::to_tf32(w.y), umma::to_tf32(w.z), umma::to_tf32(w.w));
+      const uint32_t o = umma::tile_chunk_off(n, c, kH);
+      *reinterpret_cast<float4*>(Wt(w_) + o) = hi;
+      *reinterpret_cast<float4*>(Wt(w_) + SM::kW + o) = make_float4(w.x - hi.x, w.y - hi.y, w.z - hi.z, w.w - hi.w);
+    }
+  };
+  auto load_h = [&](int i0) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int r = i0 + rr0 + 16 * j;
+      hreg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < a.N) hreg[j] = *reinterpret_cast<const float4*>(a.h + (size_t)r * kH + 4 * c16);
+    }
+  };
+  auto store_h = [&]() {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const float4 x = hreg[j];
+      const float4 hi = make_float4(umma::to_tf32(x.x), umma::to_tf32(x.y), umma::to_tf32(x.z), umma::to_tf32(x.w));
+      const uint32_t o = umma::tile_chunk_off(rr0 + 16 * j, c16, kTM);
+      *reinterpret_cast<float4*>(At + o) = hi;
+      *reinterpret_cast<float4*>(At + SM::kT + o) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    }
+  };
+
+  // ---- prologue (weights only)
+  load_w(kb);
+  if (t == 0) {
+    umma::mbar_init(&v->bar[0], 1);
+    umma::mbar_init(&v->bar[1], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<128>(&v->tmem_slot);
+  store_w(0);
+  load_w(kb + 1 < ke ? kb + 1 : kb);
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  pdl_wait();
+  const uint32_t tmem = v->tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16) + c0;
+  const uint32_t idesc = umma::make_idesc_tf32(128, kH);
+  const uint64_t dA = umma::make_desc(umma::smem_u32(At)), dW0 = umma::make_desc(umma::smem_u32(Wt(0)));
+  auto issue = [&](int acc_, int w_) {
+    if (warp == 0) {
+      umma::fence_after();
+      if (umma::elect_one()) {
+        const uint32_t acc = tmem + 64 * acc_;
+        const uint64_t dW = dW0 + (uint64_t)(w_ * ((2 * SM::kW) >> 4));
+        umma::gemm_k64_desc(acc, dA, kTM, dW, kH, idesc, false);
+        umma::gemm_k64_desc(acc, dA + (uint64_t)(SM::kT >> 4), kTM, dW, kH, idesc, true);
+        umma::gemm_k64_desc(acc, dA, kTM, dW + (uint64_t)(SM::kW >> 4), kH, idesc, true);
+        umma::commit(&v->bar[acc_]);
+      }
+      __syncwarp();
+    }
+  };
+  uint32_t ph_bits = 0;
+  // block k (accumulator k & 1) -> global memory: + bias, through the staging tile, rows in (row, chunk) order ; heads: the
+  // output dot product of the row
+  auto epilogue = [&](int k, int i0) {
+    const int b = blk_of(k), acc_ = (k - kb) & 1;
+    umma::mbar_wait(&v->bar[acc_], (ph_bits >> acc_) & 1u);
+    umma::fence_after();
+    ph_bits ^= 1u << acc_;
+    float z[CPT];
+    tmem_ld<CPT>(tlane + 64 * acc_, z);
+    if (b < 4) {
+#pragma unroll
+      for (int ch = 0; ch < CPT / 4; ++ch) {
+        const float4 bb = *reinterpret_cast<const float4*>(v->bias[acc_] + c0 + 4 * ch);
+        *reinterpret_cast<float4*>(ST + umma::tile_chunk_off(row, cg * (CPT / 4) + ch, kTM)) =
+            make_float4(z[4 * ch] + bb.x, z[4 * ch + 1] + bb.y, z[4 * ch + 2] + bb.z, z[4 * ch + 3] + bb.w);
+      }
+      umma::fence_before();
+      __syncthreads();
+      float* out = b == 0 ? a.P : b == 1 ? a.Q : b == 2 ? a.Av : a.Uh;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const int rr = rr0 + 16 * j;
+        if (i0 + rr < a.N)
+          *reinterpret_cast<float4*>(out + (size_t)(i0 + rr) * kH + 4 * c16) =
+              *reinterpret_cast<const float4*>(ST + umma::tile_chunk_off(rr, c16, kTM));
+      }
+    } else {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) s = fmaf(silu_f(z[j] + v->bias[acc_][c0 + j]), v->w2[acc_][c0 + j], s);
+      if (cg == 1) v->sp[row] = s;
+      umma::fence_before();
+      __syncthreads();
+      if (cg == 0 && i0 + row < a.N) (b == 4 ? a.sv : a.sg)[i0 + row] = s + v->sp[row] + (b == 4 ? a.vel_b2[0] : a.grav_b2[0]);
+    }
+  };
+  // bias / head vectors of block k -> buffer k & 1 (written at the top of iteration k, read by epilogue(k) an iteration later)
+  auto stage_vecs = [&](int k) {
+    const int b = blk_of(k);
+    if (t < kH) {
+      const float* bias = b == 0 ? a.edge_b0 : b == 2 ? a.edgev_b0 : b == 3 ? a.node_b0 : b == 4 ? a.vel_b0 : b == 5 ? a.grav_b0 : nullptr;
+      const float* w2 = b == 4 ? a.vel_w2 : b == 5 ? a.grav_w2 : nullptr;
+      v->bias[(k - kb) & 1][t] = bias != nullptr ? bias[t] : 0.f;
+      v->w2[(k - kb) & 1][t] = w2 != nullptr ? w2[t] : 0.f;
+    }
+  };
+
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if ((int)blockIdx.x < ntiles) load_h(blockIdx.x * kTM);
+  int wq = 0;                                      // weight ring slot of the block at hand (runs on across tiles)
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = tile * kTM;
+    store_h();                                     // the previous tile's last block has completed (its epilogue waited)
+    if (tile + (int)gridDim.x < ntiles) load_h((tile + gridDim.x) * kTM);      // next tile's rows travel under this tile's blocks
+    for (int k = kb; k < ke; ++k) {
+      // at this point: W(k) sits in slot wq (stored an iteration ago), the registers hold the weights of the block after it
+      stage_vecs(k);
+      umma::fence_smem_to_async();
+      umma::fence_before();
+      __syncthreads();                             // W(k) [and h] visible ; staging tile and accumulator of block k - 2 consumed
+      issue((k - kb) & 1, wq);
+      const int wn = wq == 2 ? 0 : wq + 1;
+      const int k1 = k + 1 < ke ? k + 1 : kb, k2 = k1 + 1 < ke ? k1 + 1 : kb;      // past the last block: the next tile's
+      store_w(wn);                                 // slot of block k - 2, which has completed (epilogue(k - 2) waited for it)
+      load_w(k2);
+      wq = wn;
+      if (k > kb) epilogue(k - 1, i0);
+    }
+    __syncthreads();                               // the staging tile of the block before the last has been written out
+    epilogue(ke - 1, i0);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<128>(tmem);
+}
+
 }  // namespace ntc
 
 cudaError_t launch_node_pre_fwd_tc(const NodePreArgs& a, int sms, cudaStream_t st) {
@@ -459,6 +661,25 @@ cudaError_t launch_node_pre_fwd_tc(const NodePreArgs& a, int sms, cudaStream_t s
   if (ntiles == 0) return cudaSuccess;
   int per = ntiles < sms ? ntiles : sms;          // CTAs per group; 2 groups -> up to 2 CTAs / SM
   ntc::node_pre_fwd_tc_kernel<<<2 * per, 256, ntc::PreSmem::bytes, st>>>(a); ++g_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_node_pre_fwd_tc3(const NodePreArgs& a, int sms, cudaStream_t st) {
+  static DevOnce attr;
+  if (!attr.get()) {
+    cudaError_t e = cudaFuncSetAttribute(ntc::node_pre_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ntc::P3Smem::bytes);
+    if (e != cudaSuccess) return e;
+    attr.set();
+  }
+  const int ntiles = (a.N + kTM - 1) / kTM;
+  if (ntiles == 0) return cudaSuccess;
+  const bool grav = a.flags & FEGNN_F_GRAVITY, last = a.flags & FEGNN_F_LAST;
+  const int nactive = 4 + (grav ? 2 : 1) - (last ? 1 : 0) - ((a.flags & FEGNN_F_RF) ? 1 : 0);
+  const int nsplit = 2 * ntiles <= sms ? 2 : 1;   // few tiles: two CTAs per tile, half of the blocks each
+  if (cudaError_t e_ = launch_pdl(ntc::node_pre_fwd_tc3_kernel, dim3(ntiles < sms ? ntiles : sms, nsplit), 256, ntc::P3Smem::bytes,
+                                  st, a, nactive))
+    return e_;
   return cudaGetLastError();
 }
 
