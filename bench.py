@@ -263,7 +263,9 @@ def time_cpu(step, warmup, steps):
 
 # ----------------------------------------------------------------------------- the timed step
 DTYPE_DEFAULT = ("tf32: tcgen05 TF32 operand tiles with fp32 accumulation and tanh.approx SiLU in the edge and virtual "
-                 "phases, fp32 FMA everywhere else (the reference is strict fp32; the fp32-kernel figure is in `fp32_mode`)")
+                 "phases (fp16 operands with power-of-two scales in the edge backward), TF32 tiles in the node-side backward, "
+                 "error-compensated 3xTF32 tiles (fp32-grade) in the node-side forward, fp32 FMA in the per-graph phases "
+                 "(the reference is strict fp32; the fp32-kernel figure is in `fp32_mode`)")
 
 
 def make_cloud_device(n: int, mean_deg: float, C: int, seed: int, gravity, dev, r: float = 0.035, vel_std: float = 0.01):
@@ -1024,6 +1026,11 @@ def edge_bwd_at_scale(model, dev, flush, peak_tf, probes, peaks, name="water3d_b
         t_model = max(flop / (probes["tcgen05_f16_tflops"] * 1e12), 3 * H * E / (probes["mufu_tanh_gops"] * 1e9),
                       algo_bytes / (peaks.get("hbm_gbs", 6650.0) * 1e9))
         out["frac_of_model"] = t_model / t_s
+    try:                           # dram bytes of one ncu --set full capture of this launch (profiles/ncu_traffic_r2.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+        out["traffic"] = tr.get(f"edge_bwd[mode=7]@E={E}")
+    except Exception:
+        out["traffic"] = None
     del sv, graph, t
     torch.cuda.empty_cache()
     return out
