@@ -9,6 +9,9 @@
 // Sort: least-significant-digit radix sort, 8-bit digits, ceil(bits(N-1)/8) passes.
 // Each pass = per-tile histogram -> exclusive scan (digit-major) -> stable scatter, where a
 // tile is 4096 consecutive elements and the in-tile stable rank comes from warp match masks.
+// Small edge lists (up to kFusedMaxTiles tiles of 1024: Water-3D has 178) take a shorter chain: tiles of 1024 so that
+// every SM has one, the scan folded into the scatter kernel (each CTA sums the tile histograms below it: 2 launches
+// per pass instead of 3) and the CSR emission (perm, row, col, sorted edge_attr) folded into the last scatter.
 #include "common.cuh"
 
 namespace fegnn {
@@ -17,6 +20,9 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;                             // rounds per warp
 constexpr int kSortTile = kSortThreads * kSortItems;       // 4096
 constexpr int kScanChunk = 4096;                           // 256 threads x 16
+constexpr int kFusedItems = 4;                             // small edge lists: tiles of 1024 ...
+constexpr int kFusedTile = kSortThreads * kFusedItems;
+constexpr int kFusedMaxTiles = 512;                        // ... up to this many (E <= 524 288)
 
 // ---------------------------------------------------------------- exclusive scan (int32)
 __global__ void __launch_bounds__(256) scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ sums) {
@@ -218,6 +224,69 @@ __global__ void recip_kernel(int n, const int* __restrict__ ptr, float* __restri
   }
 }
 
+// ---------------------------------------------------------------- small graphs: the counts chain in two launches
+// (1) degree counts and the int32 batch vector + per-graph node counts in one grid; (2) both exclusive scans (rowptr, gptr)
+// with their clamped reciprocals (unsorted_segment_mean's count.clamp(min=1), models/FastEGNN.py:294 / global_mean_pool) in
+// one two-block launch.  Replaces count_rows, batch, scan, scan, recip, recip (6 launches of a few microseconds each on the
+// critical path of the first edge kernel).
+__global__ void count_rows_batch_kernel(int E, int N, const int64_t* __restrict__ row64, const int64_t* __restrict__ b64,
+                                        int* __restrict__ deg, int* __restrict__ batch, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) atomicAdd(deg + (int)row64[i], 1);
+  if (i < (N + 31) / 32 * 32) {                  // whole warps: the match below is warp-wide
+    const int b = i < N ? (int)b64[i] : -1;
+    if (i < N) batch[i] = b;
+    // a warp usually holds one graph id -> one atomic per group of equal ids, not per node
+    const unsigned same = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(cnt + b, __popc(same));
+  }
+}
+__global__ void __launch_bounds__(1024) scan2_recip_kernel(int* __restrict__ p0, int n0, float* __restrict__ r0,
+                                                            int* __restrict__ p1, int n1, float* __restrict__ r1) {
+  __shared__ int buf[kSmemScan];
+  __shared__ int wsum[32];
+  int* io = blockIdx.x == 0 ? p0 : p1;
+  const int n = blockIdx.x == 0 ? n0 : n1;
+  float* rc = blockIdx.x == 0 ? r0 : r1;
+  for (int i = threadIdx.x; i < n; i += 1024) buf[i] = io[i];
+  __syncthreads();
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int tsum = 0;
+  for (int i = lo; i < hi; ++i) tsum += buf[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = tsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = wsum[lane], ti = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    wsum[lane] = ti - t;
+  }
+  __syncthreads();
+  int run = wsum[w] + inc - tsum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = buf[i];
+    buf[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    io[i] = buf[i];
+    if (i + 1 < n) {
+      const int c = buf[i + 1] - buf[i];
+      rc[i] = 1.f / (float)(c < 1 ? 1 : c);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- radix passes
 // keys come from the int64 row vector in the first pass (vals implicit = index)
 template <bool FIRST>
@@ -297,6 +366,131 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(int E, int 
   }
 }
 
+// ---------------------------------------------------------------- small edge lists: 2 launches per pass
+// histogram of tile b in hist[b * 256 + digit] (tile-major: the scatter kernel's column sums are coalesced)
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_hist_fused_kernel(int E, int shift, const int64_t* __restrict__ row64,
+                                                                        const int* __restrict__ keys, int* __restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kFusedTile;
+#pragma unroll
+  for (int r = 0; r < kFusedItems; ++r) {
+    const int idx = base + r * kSortThreads + threadIdx.x;
+    if (idx < E) {
+      const int k = FIRST ? (int)row64[idx] : keys[idx];
+      atomicAdd(&h[(k >> shift) & 255], 1);
+    }
+  }
+  __syncthreads();
+  hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+struct CsrOut {            // last pass: the CSR arrays instead of (key, value) pairs
+  const int64_t* col64;
+  const float* ea;
+  int *perm, *row, *col;
+  float* ea_sorted;
+  int Fe;
+};
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_fused_kernel(int E, int shift, const int64_t* __restrict__ row64,
+                                                                           const int* __restrict__ keys,
+                                                                           const int* __restrict__ vals, int G,
+                                                                           const int* __restrict__ hist,
+                                                                           int* __restrict__ keys_out, int* __restrict__ vals_out,
+                                                                           CsrOut o) {
+  __shared__ int wcount[8][256];    // per-warp digit counts, later running offsets
+  __shared__ int goff[256];
+  __shared__ int wtot[8];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < 8 * 256; i += kSortThreads) (&wcount[0][0])[i] = 0;
+  const int wbase = blockIdx.x * kFusedTile + w * (kFusedItems * 32);
+  int k[kFusedItems];
+#pragma unroll
+  for (int r = 0; r < kFusedItems; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    k[r] = idx < E ? (FIRST ? (int)row64[idx] : keys[idx]) : -1;
+  }
+  // the scan, inline: digit `tid` starts at (all smaller digits of every tile) + (this digit in the tiles below).  The column
+  // sums over the G tile histograms are split four ways (64 threads x int4 per histogram row, rows b = q mod 4) with 16 loads
+  // in flight per thread: the plain one-digit-per-thread walk was G dependent-latency batches, 8 us at Water-3D.
+  {
+    __shared__ int part[2][4][256];
+    const int q = tid >> 6, c4 = tid & 63;
+    int4 tot4 = make_int4(0, 0, 0, 0), bel4 = make_int4(0, 0, 0, 0);
+    const int4* h4 = reinterpret_cast<const int4*>(hist);
+#pragma unroll 16
+    for (int b = q; b < G; b += 4) {
+      const int4 c = h4[b * 64 + c4];
+      tot4.x += c.x; tot4.y += c.y; tot4.z += c.z; tot4.w += c.w;
+      if (b < (int)blockIdx.x) { bel4.x += c.x; bel4.y += c.y; bel4.z += c.z; bel4.w += c.w; }
+    }
+    *reinterpret_cast<int4*>(&part[0][q][4 * c4]) = tot4;
+    *reinterpret_cast<int4*>(&part[1][q][4 * c4]) = bel4;
+    __syncthreads();
+    const int tot = part[0][0][tid] + part[0][1][tid] + part[0][2][tid] + part[0][3][tid];
+    const int below = part[1][0][tid] + part[1][1][tid] + part[1][2][tid] + part[1][3][tid];
+    int inc = tot;
+#pragma unroll
+    for (int o_ = 1; o_ < 32; o_ <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o_);
+      if (lane >= o_) inc += u;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    int wpre = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) wpre += ww < w ? wtot[ww] : 0;
+    goff[tid] = wpre + inc - tot + below;
+  }
+  // phase 1: per-warp digit counts
+#pragma unroll
+  for (int r = 0; r < kFusedItems; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    if (idx < E) atomicAdd(&wcount[w][(k[r] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  // phase 2: exclusive prefix over warps per digit (thread tid owns digit tid)
+  {
+    int run = 0;
+    for (int ww = 0; ww < 8; ++ww) {
+      const int c = wcount[ww][tid];
+      wcount[ww][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase 3: in-order stable ranking, 32 elements per round
+#pragma unroll
+  for (int r = 0; r < kFusedItems; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    const bool valid = idx < E;
+    const int d = valid ? ((k[r] >> shift) & 255) : 256 + lane;   // invalid lanes never match
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    int pos = 0;
+    if (valid) pos = goff[d] + wcount[w][d] + rank;
+    __syncwarp();
+    if (valid && rank == 0) wcount[w][d] += __popc(m);
+    __syncwarp();
+    if (valid) {
+      const int v = FIRST ? idx : vals[idx];
+      if (LAST) {
+        o.perm[pos] = v;
+        o.row[pos] = k[r];
+        o.col[pos] = (int)o.col64[v];
+        for (int f = 0; f < o.Fe; ++f) o.ea_sorted[(size_t)pos * o.Fe + f] = o.ea[(size_t)v * o.Fe + f];
+      } else {
+        keys_out[pos] = k[r];
+        vals_out[pos] = v;
+      }
+    }
+  }
+}
+
 __global__ void iota_copy_kernel(int E, const int64_t* __restrict__ row64, int* __restrict__ keys, int* __restrict__ vals) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < E) {
@@ -321,6 +515,8 @@ __global__ void finalize_kernel(int E, int Fe, const int* __restrict__ keys, con
 
 size_t graph_prep_workspace_bytes(int N, int E) {
   size_t G = ((size_t)E + kSortTile - 1) / kSortTile;
+  const size_t Gf = ((size_t)E + kFusedTile - 1) / kFusedTile;
+  if (Gf <= (size_t)kFusedMaxTiles) G = Gf;                 // the short chain's tile histograms
   size_t nscan = 256 * G > (size_t)N + 1 ? 256 * G : (size_t)N + 1;
   size_t sums = (nscan + kScanChunk - 1) / kScanChunk + 1;
   return ((size_t)4 * E + 256 * G + 2 * sums + 64) * sizeof(int);      // two scan scratch areas: the two chains overlap
@@ -330,26 +526,35 @@ cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, c
                        const float* edge_attr, int* perm, int* rowptr, int* row, int* col, int* batch, int* gptr,
                        float* ea_sorted, float* dinv, float* inv_nb, void* ws, cudaStream_t st, cudaStream_t st_counts) {
   const int G = (E + kSortTile - 1) / kSortTile;
+  const int Gf = (E + kFusedTile - 1) / kFusedTile;
+  static const bool fused_ok = getenv("FEGNN_SORT_FUSED") == nullptr || atoi(getenv("FEGNN_SORT_FUSED")) != 0;   // experiment switch
+  const int Gh = Gf <= kFusedMaxTiles ? Gf : G;             // tiles whose histograms the workspace holds (as sized above)
   int* keysA = reinterpret_cast<int*>(ws);
   int* keysB = keysA + E;
   int* valsA = keysB + E;
   int* valsB = valsA + E;
   int* hist = valsB + E;
-  int* sums = hist + (size_t)256 * G;
+  int* sums = hist + (size_t)256 * Gh;
   cudaError_t e;
   {
     // counts -> rowptr, gptr, reciprocals (stream st_counts, own scan scratch)
-    size_t nscan = 256 * (size_t)G > (size_t)N + 1 ? 256 * (size_t)G : (size_t)N + 1;
+    size_t nscan = 256 * (size_t)Gh > (size_t)N + 1 ? 256 * (size_t)Gh : (size_t)N + 1;
     int* sums2 = sums + (nscan + kScanChunk - 1) / kScanChunk + 1;
     cudaStream_t sc = st_counts;
     if ((e = cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), sc)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(gptr, 0, sizeof(int) * ((size_t)B + 1), sc)) != cudaSuccess) return e;
-    if (E > 0) { count_rows_kernel<<<(E + 255) / 256, 256, 0, sc>>>(E, edge_index, rowptr); ++g_launches; }
-    if (N > 0) { batch_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, data_batch, batch, gptr); ++g_launches; }
-    if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums2, sc)) != cudaSuccess) return e;
-    if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums2, sc)) != cudaSuccess) return e;
-    if (N > 0) { recip_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, rowptr, dinv); ++g_launches; }
-    if (B > 0) { recip_kernel<<<(B + 255) / 256, 256, 0, sc>>>(B, gptr, inv_nb); ++g_launches; }
+    if (fused_ok && N > 0 && B > 0 && N + 1 <= kSmemScan && B + 1 <= kSmemScan) {
+      const int n = E > N ? E : N;
+      count_rows_batch_kernel<<<(n + 255) / 256, 256, 0, sc>>>(E, N, edge_index, data_batch, rowptr, batch, gptr); ++g_launches;
+      scan2_recip_kernel<<<2, 1024, 0, sc>>>(rowptr, N + 1, dinv, gptr, B + 1, inv_nb); ++g_launches;
+    } else {
+      if (E > 0) { count_rows_kernel<<<(E + 255) / 256, 256, 0, sc>>>(E, edge_index, rowptr); ++g_launches; }
+      if (N > 0) { batch_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, data_batch, batch, gptr); ++g_launches; }
+      if ((e = exclusive_scan(rowptr, N + 1, rowptr, nullptr, sums2, sc)) != cudaSuccess) return e;
+      if ((e = exclusive_scan(gptr, B + 1, gptr, nullptr, sums2, sc)) != cudaSuccess) return e;
+      if (N > 0) { recip_kernel<<<(N + 255) / 256, 256, 0, sc>>>(N, rowptr, dinv); ++g_launches; }
+      if (B > 0) { recip_kernel<<<(B + 255) / 256, 256, 0, sc>>>(B, gptr, inv_nb); ++g_launches; }
+    }
   }
   if (E == 0) return cudaGetLastError();
   // radix sort (row, edge id)
@@ -360,6 +565,31 @@ cudaError_t graph_prep(int N, int E, int B, int Fe, const int64_t* edge_index, c
   const int* vin = nullptr;
   int* kout = keysA;
   int* vout = valsA;
+  if (Gf <= kFusedMaxTiles && fused_ok) {
+    // short chain: per pass one histogram launch and one scatter launch that scans for itself; the last one emits the CSR
+    const CsrOut o{edge_index + E, edge_attr, perm, row, col, ea_sorted, Fe};
+    for (int p = 0; p < passes; ++p) {
+      const int shift = 8 * p;
+      const bool first = p == 0, lastp = p == passes - 1;
+      if (first) radix_hist_fused_kernel<true><<<Gf, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, hist);
+      else radix_hist_fused_kernel<false><<<Gf, kSortThreads, 0, st>>>(E, shift, nullptr, kin, hist);
+      ++g_launches;
+      if (first && lastp)
+        radix_scatter_fused_kernel<true, true><<<Gf, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, nullptr, Gf, hist, kout, vout, o);
+      else if (first)
+        radix_scatter_fused_kernel<true, false><<<Gf, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, nullptr, Gf, hist, kout, vout, o);
+      else if (lastp)
+        radix_scatter_fused_kernel<false, true><<<Gf, kSortThreads, 0, st>>>(E, shift, nullptr, kin, vin, Gf, hist, kout, vout, o);
+      else
+        radix_scatter_fused_kernel<false, false><<<Gf, kSortThreads, 0, st>>>(E, shift, nullptr, kin, vin, Gf, hist, kout, vout, o);
+      ++g_launches;
+      kin = kout;
+      vin = vout;
+      kout = (kout == keysA) ? keysB : keysA;
+      vout = (vout == valsA) ? valsB : valsA;
+    }
+    return cudaGetLastError();
+  }
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
     if (p == 0) radix_hist_kernel<true><<<G, kSortThreads, 0, st>>>(E, shift, edge_index, nullptr, G, hist);
