@@ -923,7 +923,10 @@ def rollout_profile(model, t, dev, E, flush, steps=20):
     out = {}
     was_training = model.training
     try:
-        for name, keep in (("forward_only", False), ("training_forward", True)):
+        order = (("forward_only", False), ("training_forward", True))
+        if os.environ.get("FEGNN_ROLLOUT_ORDER") == "rev":
+            order = order[::-1]
+        for name, keep in order:
             model.eval()
             model.eval_keeps_graph = keep
             side = torch.cuda.Stream()

@@ -212,7 +212,7 @@ namespace {
 // with events, all capturable) so they overlap the node- and edge-parallel kernels instead of idling 147 SMs.
 struct SideStream {
   cudaStream_t st = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr;
 };
 SideStream* side_stream() {
   static SideStream per_dev[64];
@@ -223,6 +223,7 @@ SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s->aux, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return s;
 }
@@ -890,10 +891,19 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
 // utils/train.py:24-27,191-192: validation and test run the model with backprop=False.  Nothing is kept for a backward:
 // the layers ping-pong between two state sets and share ONE block of per-layer intermediates, so the workspace is
 // 2 states + 1 block instead of (L + 1) states + L blocks (3.4 GB instead of 13.4 GB at 1 M nodes, C = 8, L = 4).
+// Small graphs get TWO blocks (layer l uses block l & 1): with one, the per-graph kernels of layer l + 1 (side stream) must not
+// start before layer l's node phase has read u / msum, and the next main-stream kernels not before graph_post(l) has read
+// Dsum / Usum -- a join + fork per layer that puts 12 us of one-CTA kernels on the chain (4 layers at Water-3D: 0.374 ms against
+// 0.327 for the training forward).  With two, the stack has the training forward's fork / join structure.  Large graphs keep
+// one block: there the serialisation is noise and the block is gigabytes.
+constexpr int kInferTwoBlocksMaxN = 65536;
+static inline size_t infer_blocks(const fegnn_dims* d) { return d->N <= kInferTwoBlocksMaxN ? 2 : 1; }
+
 size_t fegnn_model_inference_workspace_floats(const fegnn_dims* d) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
   const size_t per_state = al4(N * kH) + al4(Nl * 3) + al4(B * 3 * C) + al4(B * C * kH) + al4(B * 3);
-  return 3 * per_state + fegnn_layer_saved_floats(d);      // two ping-pong states + the (h, S) of the embedding (FastRF)
+  // two ping-pong states + the (h, S) of the embedding (FastRF) + the shared block(s) of per-layer intermediates
+  return 3 * per_state + infer_blocks(d) * fegnn_layer_saved_floats(d);
 }
 
 int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
@@ -914,9 +924,11 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
   for (int i = 0; i < 3; ++i) {
     h[i] = take(N * kH); x[i] = take(Nl * 3); Z[i] = take(B * 3 * C); Sx[i] = take(B * C * kH); xsum[i] = take(B * 3);
   }
-  fegnn_layer_saved sv_;
-  fegnn_layer_saved_bind(d, p, &sv_);
-  fegnn_layer_saved* sv = &sv_;
+  const bool two = infer_blocks(d) == 2;
+  fegnn_layer_saved sv_[2];
+  fegnn_layer_saved_bind(d, p, &sv_[0]);
+  if (two) fegnn_layer_saved_bind(d, p + fegnn_layer_saved_floats(d), &sv_[1]);
+  else sv_[1] = sv_[0];
   // slot 2 keeps the embedding state (h0, S0): FastRF reads it in every layer; slots 0 / 1 ping-pong
   TRY(fegnn_embed_forward(d->N, Fin, node_feat, embed_w, embed_b, h[2], stream));
   CK(cudaMemcpyAsync(x[2], x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
@@ -925,35 +937,79 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
     broadcast_vnf_kernel<<<(unsigned)((B * C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, vnf, Sx[2]); ++g_launches;
     CK(cudaGetLastError());
   }
-  if (g->ready_event != nullptr) CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));   // CSR sort on another stream
+  const bool rf = d->flags & FEGNN_F_RF;
+  const bool graph_pending = g->ready_event != nullptr;
+  if (graph_pending) {
+    // the CSR sort is still running on another stream: everything above, the first block's fill and the first layer's node
+    // phase read no graph array and run under it; this stream joins the sort here
+    fegnn_dims d0 = *d;
+    d0.flags |= FEGNN_F_PREZEROED;
+    if (rf || L == 1) d0.flags |= FEGNN_F_LAST;
+    CK(cudaMemsetAsync(sv_[0].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+    if (two) CK(cudaMemsetAsync(sv_[1].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+    TRY(fegnn_node_pre_forward(&d0, &layers[0], h[2], &sv_[0], stream));
+    CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));
+  }
   TRY(fegnn_graph_xsum(d->N, d->B, x[2], g->batch, xsum[2], stream));
   SideStream* sd = side_stream();
   RQ(sd != nullptr);
   void* side = sd->st;
   FORK(sd, st);
-  const bool rf = d->flags & FEGNN_F_RF;
+  // phi_h weight images off the chain (two blocks): layer 0's here, layer l + 1's on the side stream next to graph_post(l)
+  // (the image buffer of block (l + 1) & 1 was last read by phi_h of layer l - 1, ahead of the fork)
+  const bool img_ahead = two && g_node_fwd_mode != 0 && !rf && L > 1;
+  auto weight_images = [&](int l, cudaStream_t s_) -> cudaError_t {
+    const float *w0 = layers[l].node_w0, *w2 = layers[l].node_w2;
+    float* img = sv_[l & 1].wimg;
+    return launch_node_h_wprep(d->C, ldn(d), 1, &w0, &w2, &img, s_);
+  };
+  if (img_ahead) CK(weight_images(0, st));
   int cur = 2;                                    // state entering the layer
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
     const bool last = rf || l == L - 1;
     if (last) dl.flags |= FEGNN_F_LAST;
+    dl.flags |= FEGNN_F_PREZEROED;                // one fill of the block's accumulators here instead of one per phase ...
+    if (img_ahead) dl.flags |= FEGNN_F_WIMG_READY;
     const fegnn_layer_params* pl = &layers[l];
     const int nxt = cur == 2 ? 0 : (cur ^ 1);
     const int hs = rf ? 2 : cur;                  // layer whose (h, S) this layer reads
+    fegnn_layer_saved* sv = &sv_[l & 1];
+    // two blocks: blocks 0 / 1 are filled ahead of the chain, block l & 1 for layer l >= 2 on the side stream during layer
+    // l - 1 (below) -- a memset node between two kernels of the chain would cut their programmatic overlap
+    if (two) {
+      if (!graph_pending && l < 2) CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+      if (l >= 2) CK(cudaStreamWaitEvent(st, sd->aux, 0));
+    } else if (!(graph_pending && l == 0)) {
+      CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+    }
+    // ... and the per-graph coordinate sums of the state this layer produces on the side stream (last read by the per-graph
+    // kernels of the layer that consumed that state, earlier on the same stream; joined in front of virtual_forward)
+    CK(cudaMemsetAsync(xsum[nxt], 0, sizeof(float) * 3 * B, S(side)));
     TRY(fegnn_graph_pre_forward(&dl, g, pl, Z[cur], Sx[hs], xsum[cur], sv, side));
-    TRY(fegnn_node_pre_forward(&dl, pl, h[hs], sv, stream));
+    if (!(graph_pending && l == 0)) TRY(fegnn_node_pre_forward(&dl, pl, h[hs], sv, stream));
     if (rf) TRY(fegnn_rf_vel_forward(d->N, v, pl, sv->sv, stream));
     TRY(fegnn_edge_forward(&dl, g, pl, x[cur], sv, stream));
     JOIN(sd, st);
     TRY(fegnn_virtual_forward(&dl, g, pl, x[cur], v, Z[cur], sv, x[nxt], xsum[nxt], stream));
     FORK(sd, st);
+    if (two && l >= 1 && l + 1 < L) {
+      // the other block's accumulators for layer l + 1: last read by layer l - 1 (node phase on this stream ahead of the
+      // fork, per-graph kernels earlier on the side stream)
+      CK(cudaMemsetAsync(sv_[(l + 1) & 1].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), S(side)));
+      CK(cudaEventRecord(sd->aux, S(side)));
+    }
     if (!last) TRY(fegnn_node_h_forward(&dl, g, pl, h[cur], sv, h[nxt], stream));
     TRY(fegnn_graph_post_forward(&dl, g, pl, Z[cur], Sx[hs], sv, Z[nxt], Sx[nxt], side));
+    if (img_ahead && l + 2 < L) CK(weight_images(l + 1, S(side)));
     // the shared block is rewritten by the next layer: its per-graph kernels (side) must not start before this layer's
     // node_h (main) has read u / msum, and its main-stream kernels not before this layer's graph_post (side) has read
-    // Dsum / Usum
-    JOIN(sd, st);
-    FORK(sd, st);
+    // Dsum / Usum.  (Two blocks: block l & 1 is next written by layer l + 2, whose kernels are ordered behind both by the
+    // join in front of virtual_forward(l + 1).)
+    if (!two) {
+      JOIN(sd, st);
+      FORK(sd, st);
+    }
     cur = nxt;
   }
   JOIN(sd, st);

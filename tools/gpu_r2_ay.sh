@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 1700 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | cut -c1-400
+B="python bench.py --no-cpu-baseline --no-gpu-eager-bar --no-per-config --no-fp32-line --no-phases"
+for i in 1 2; do
+timeout 600 $B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print('step', round(d['ms_per_step'],4), round(d['e2e']['ms_per_step'],4), 'rollout', d['rollout'])"
+done
