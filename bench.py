@@ -391,7 +391,7 @@ class StepBench:
             self.pipe = PipelinedStep(lambda t: self.train_step(t, t["idx"]), host, self.dev)
             self.pipe_host = host
             self.pipe.prefetch(host)
-        return self.pipe.run(self.pipe_host).item()
+        return self.pipe.run_and_read(self.pipe_host)
 
     def e2e(self):
         if self.g is not None:

@@ -408,11 +408,26 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_fused_kernel(int E
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int i = tid; i < 8 * 256; i += kSortThreads) (&wcount[0][0])[i] = 0;
   const int wbase = blockIdx.x * kFusedTile + w * (kFusedItems * 32);
-  int k[kFusedItems];
+  // every global load of the thread goes out first: keys, values and -- last pass -- the gathers of the CSR emission
+  // (col64[v], edge_attr[v]); they travel under the column sums and the ranking instead of two dependent round trips per round
+  int k[kFusedItems], vv[kFusedItems];
 #pragma unroll
   for (int r = 0; r < kFusedItems; ++r) {
     const int idx = wbase + r * 32 + lane;
     k[r] = idx < E ? (FIRST ? (int)row64[idx] : keys[idx]) : -1;
+    vv[r] = idx < E ? (FIRST ? idx : vals[idx]) : 0;
+  }
+  constexpr int kEaRegs = 4;                       // edge_attr columns carried in registers (wider: gathered at the store)
+  int cc[kFusedItems];
+  float ee[kFusedItems][kEaRegs];
+  if (LAST) {
+#pragma unroll
+    for (int r = 0; r < kFusedItems; ++r) {
+      const int idx = wbase + r * 32 + lane;
+      cc[r] = idx < E ? (int)o.col64[vv[r]] : 0;
+#pragma unroll
+      for (int f = 0; f < kEaRegs; ++f) ee[r][f] = (idx < E && f < o.Fe) ? o.ea[(size_t)vv[r] * o.Fe + f] : 0.f;
+    }
   }
   // the scan, inline: digit `tid` starts at (all smaller digits of every tile) + (this digit in the tiles below).  The column
   // sums over the G tile histograms are split four ways (64 threads x int4 per histogram row, rows b = q mod 4) with 16 loads
@@ -477,12 +492,15 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_fused_kernel(int E
     if (valid && rank == 0) wcount[w][d] += __popc(m);
     __syncwarp();
     if (valid) {
-      const int v = FIRST ? idx : vals[idx];
+      const int v = vv[r];
       if (LAST) {
         o.perm[pos] = v;
         o.row[pos] = k[r];
-        o.col[pos] = (int)o.col64[v];
-        for (int f = 0; f < o.Fe; ++f) o.ea_sorted[(size_t)pos * o.Fe + f] = o.ea[(size_t)v * o.Fe + f];
+        o.col[pos] = cc[r];
+#pragma unroll
+        for (int f = 0; f < kEaRegs; ++f)
+          if (f < o.Fe) o.ea_sorted[(size_t)pos * o.Fe + f] = ee[r][f];
+        for (int f = kEaRegs; f < o.Fe; ++f) o.ea_sorted[(size_t)pos * o.Fe + f] = o.ea[(size_t)v * o.Fe + f];
       } else {
         keys_out[pos] = k[r];
         vals_out[pos] = v;

@@ -514,3 +514,40 @@ def test_driver_smoke_entry_point():
     """__graft_entry__.smoke() -- what the driver runs on the GPU box before the bench -- must hold in both modes."""
     import __graft_entry__ as entry
     entry.smoke()
+
+
+def test_pipelined_step_reads_the_loss_through_the_graph():
+    """fastegnn_b200.PipelinedStep (the step glue of utils/train.py:30-53,168-173): double-buffered inputs copied from pinned
+    host memory under the previous step, the step as a captured graph, the loss returned through a copy node into pinned host
+    memory.  Two different batches alternate; every loss must equal the eager loss of the same batch."""
+    from fastegnn_b200 import PipelinedStep
+    cfg, params, inp = make_graph_case(seed=71, sizes=[80, 60], deg=6, C=3, L=3, gravity=[0, -1, 0])
+    dev = torch.device("cuda:0")
+    m = build_gpu_model(cfg, params, dev)
+    m.train()
+    keys = ["node_feat", "node_loc", "node_vel", "edge_index", "data_batch", "loc_mean", "edge_attr"]
+    host_a = {k: inp[k].clone().pin_memory() for k in keys}
+    host_b = {k: v.clone().pin_memory() for k, v in host_a.items()}
+    host_b["node_loc"] = (host_a["node_loc"] * 1.1).pin_memory()
+    host_b["loc_mean"] = (host_a["loc_mean"] * 1.1).pin_memory()
+
+    def step(t):
+        x, Z = m(node_feat=t["node_feat"], node_loc=t["node_loc"], node_vel=t["node_vel"], edge_index=t["edge_index"],
+                 data_batch=t["data_batch"], loc_mean=t["loc_mean"], edge_attr=t["edge_attr"])
+        return (x * x).mean() + (Z * Z).mean()
+
+    with precision("fp32"):
+        want = []
+        for h in (host_a, host_b):
+            with torch.no_grad():
+                want.append(float(step({k: v.to(dev) for k, v in h.items()})))
+        pipe = PipelinedStep(step, host_a, dev)
+        pipe.prefetch(host_a)
+        got = []
+        seq = [host_b, host_a, host_b, host_a]           # batch loaded under step k = the batch of step k + 1
+        for nxt in seq:
+            got.append(pipe.run_and_read(nxt))
+    assert pipe.why is None, pipe.why
+    exp = [want[0], want[1], want[0], want[1]]
+    for g_, w_ in zip(got, exp):
+        assert abs(g_ - w_) <= 1e-5 * abs(w_), (got, exp)

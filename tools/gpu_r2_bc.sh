@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+timeout 900 python -m pytest tests -m gpu -q -x -k "pipelin or Pipelin or runtime or adam or train" 2>&1 | tail -2 | cut -c1-300
+B="python bench.py --no-cpu-baseline --no-gpu-eager-bar --no-per-config --no-fp32-line --no-phases"
+for i in 1 2 3; do
+timeout 600 $B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print('step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['ms_per_step'],4), 'serial', round(d['e2e']['ms_per_step_serial_copy'],4))"
+done
