@@ -9,8 +9,7 @@
 // Sort: least-significant-digit radix sort, 8-bit digits, ceil(bits(N-1)/8) passes.
 // Each pass = per-tile histogram -> exclusive scan (digit-major) -> stable scatter, where a
 // tile is 4096 consecutive elements and the in-tile stable rank comes from warp match masks.
-// Small edge lists (up to kFusedMaxTiles tiles of 1024: Water-3D has 178) take a shorter chain: tiles of 1024 so that
-// every SM has one, the scan folded into the scatter kernel (each CTA sums the tile histograms below it: 2 launches
+// Small edge lists (up to kFusedMaxTiles tiles of 2048: Water-3D has 89) take a shorter chain: smaller tiles, the scan folded into the scatter kernel (each CTA sums the tile histograms below it: 2 launches
 // per pass instead of 3) and the CSR emission (perm, row, col, sorted edge_attr) folded into the last scatter.
 #include "common.cuh"
 
@@ -20,9 +19,10 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;                             // rounds per warp
 constexpr int kSortTile = kSortThreads * kSortItems;       // 4096
 constexpr int kScanChunk = 4096;                           // 256 threads x 16
-constexpr int kFusedItems = 4;                             // small edge lists: tiles of 1024 ...
+constexpr int kFusedItems = 8;                             // small edge lists: tiles of 2048 ...
 constexpr int kFusedTile = kSortThreads * kFusedItems;
-constexpr int kFusedMaxTiles = 512;                        // ... up to this many (E <= 524 288)
+constexpr int kFusedMaxTiles = 128;                        // ... up to this many (E <= 262 144): every CTA of the scatter kernel
+                                                           // reads all tile histograms (G^2 KB of L2 traffic: 8 MB at G = 89)
 
 // ---------------------------------------------------------------- exclusive scan (int32)
 __global__ void __launch_bounds__(256) scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ sums) {
@@ -437,11 +437,26 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_fused_kernel(int E
     const int q = tid >> 6, c4 = tid & 63;
     int4 tot4 = make_int4(0, 0, 0, 0), bel4 = make_int4(0, 0, 0, 0);
     const int4* h4 = reinterpret_cast<const int4*>(hist);
-#pragma unroll 16
-    for (int b = q; b < G; b += 4) {
-      const int4 c = h4[b * 64 + c4];
-      tot4.x += c.x; tot4.y += c.y; tot4.z += c.z; tot4.w += c.w;
-      if (b < (int)blockIdx.x) { bel4.x += c.x; bel4.y += c.y; bel4.z += c.z; bel4.w += c.w; }
+    // Every CTA reads the same G histogram rows: walked in the same order they all hit the same few L2 lines at the same
+    // time (65 % of the kernel's samples sat on the first add behind these loads).  Each CTA starts at its own row instead.
+    constexpr int kBatch = 16;                     // loads issued back to back before the first add
+    const int n4 = (G + 3) / 4, rot = (int)((blockIdx.x * 11u) % (unsigned)n4);
+    for (int j0 = 0; j0 < n4; j0 += kBatch) {
+      int4 c[kBatch];
+      int bb[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        int jj = j0 + j + rot;
+        jj -= jj >= n4 ? n4 : 0;
+        bb[j] = j0 + j < n4 ? q + 4 * jj : G;
+        c[j] = bb[j] < G ? __ldcg(h4 + bb[j] * 64 + c4) : make_int4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int m = bb[j] < (int)blockIdx.x ? -1 : 0;
+        tot4.x += c[j].x; tot4.y += c[j].y; tot4.z += c[j].z; tot4.w += c[j].w;
+        bel4.x += c[j].x & m; bel4.y += c[j].y & m; bel4.z += c[j].z & m; bel4.w += c[j].w & m;
+      }
     }
     *reinterpret_cast<int4*>(&part[0][q][4 * c4]) = tot4;
     *reinterpret_cast<int4*>(&part[1][q][4 * c4]) = bel4;
