@@ -77,9 +77,9 @@ int g_virt_bwd_mode = 1;
 int g_node_fwd_mode = 3;
 const bool g_node_pre_tc3 = getenv("FEGNN_NODE_PRE_TC3") == nullptr || atoi(getenv("FEGNN_NODE_PRE_TC3")) != 0;   // experiment switch
 // per-node dense phases of the BACKWARD pass (node_pre_backward, node_h_backward): 0 = fp32 FMA kernels, 1 = tcgen05 TF32
-// (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default) = 1 today: up to two node tiles per SM
-// the per-tile kernel walks the weight blocks (measured at 8 000 nodes: step 1.380 ms against 1.416 ms with the fp32 kernels),
-// above that the (tile, block) kernel (-4 % step at 160 000 nodes).
+// (dense_tc.cu; gradients do not enter the forward equivariance), 2 = auto (default) = 1 today: the per-tile kernel that
+// walks the weight blocks, at every size (measured at 8 000 nodes: step 1.380 ms against 1.416 ms with the fp32 kernels; at
+// 160 000 nodes 11.95 ms against 12.89 ms with the (tile, block) kernel, which stays selectable by environment).
 int g_node_bwd_mode = 2;
 constexpr int kNodeTcMinN = 0;
 inline bool node_bwd_tc(int N) { return g_node_bwd_mode == 1 || (g_node_bwd_mode == 2 && N >= kNodeTcMinN); }

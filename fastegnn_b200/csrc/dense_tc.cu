@@ -31,7 +31,11 @@ using bwd2::tmem_st;
 using bwd2::tmem_st_wait;
 
 constexpr int kMaxBlk = FEGNN_MAX_C + 2;
-constexpr int kRowsMaxTilesPerSm = 2;      // up to this many node tiles per SM the per-tile kernel (below) is used
+// Up to this many node tiles per SM the per-tile kernel (below) is used: every size.  It was written for small graphs, but
+// measured on the B200 it also wins where the (tile, block) kernel was the default (no red.add pass over [N, 64] per block):
+// 12.89 -> 11.95 ms per step at 160 000 nodes / 3.6 M edges, 122.8 -> 120.1 ms at 1 M nodes / C = 8.  The (tile, block) kernel
+// stays selectable (FEGNN_DENSE_ROWS_MAX_TILES_PER_SM=2).
+constexpr int kRowsMaxTilesPerSm = 1 << 20;
 
 struct Blk {
   // X rows [N][64] (row stride ldx floats), optional per-row scale: the gradient-side operand
@@ -711,7 +715,9 @@ cudaError_t launch_dense_bwd_tc(const dtc::Args& a_in, int sms, cudaStream_t st)
   }
   const int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0 || a.nblk == 0) return cudaSuccess;
-  if (ntiles <= dtc::kRowsMaxTilesPerSm * sms) {   // small graphs: one CTA per node tile walks the blocks
+  static const int rows_max = getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM") ? atoi(getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM"))
+                                                                         : dtc::kRowsMaxTilesPerSm;      // experiment switch
+  if ((long long)ntiles <= (long long)rows_max * sms) {   // small graphs: one CTA per node tile walks the blocks
     static DevOnce attr2;
     if (!attr2.get()) {
       cudaError_t e = cudaFuncSetAttribute(dtc::dense_bwd_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
