@@ -327,6 +327,11 @@ class StepBench:
         svv, srv = mmd_scales
 
         def allreduce_grads():
+            flat = opt.flat_grad() if hasattr(opt, "flat_grad") else None
+            if flat is not None:                 # the gradients ARE one flat buffer: all-reduce it in place
+                dist.all_reduce(flat)
+                flat.div_(world)
+                return
             grads = [p.grad for p in params if p.grad is not None]
             flat = torch._utils._flatten_dense_tensors(grads)
             dist.all_reduce(flat)

@@ -55,6 +55,25 @@ class FusedAdam(torch.optim.Optimizer):
                 view.copy_(p)
                 p.data = view                    # the module keeps its Parameter objects; storage is now the flat buffer
 
+    def flat_grad(self):
+        """The ONE buffer behind every parameter's .grad when the gradients are views of a flat buffer laid out like the
+        parameters (what the stack's backward hands to autograd), else None.  A data-parallel caller all-reduces this tensor
+        in place -- one collective, no flatten / unflatten copies around it (they were 3 of the step's kernels)."""
+        ps = [p for g in self.param_groups for p in g["params"]]
+        if self._flat_grad_ptr(ps) is None:
+            return None
+        base = None
+        for p in ps:
+            g = p.grad
+            if g is None:
+                continue
+            b = g._base if g._base is not None else g
+            if base is None:
+                base = b
+            elif b.data_ptr() != base.data_ptr():
+                return None
+        return base if base is not None and base.is_contiguous() and base.numel() >= self._n else None
+
     def _flat_grad_ptr(self, ps):
         """Device pointer of a flat gradient buffer laid out like the parameters, or None."""
         base = None

@@ -625,6 +625,10 @@ class PartitionedFastEGNN:
     def allreduce_gradients(self) -> None:
         """Sum the weight gradients over ranks (one collective on a flat buffer)."""
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        bases = {(g._base if g._base is not None else g).data_ptr() for g in grads}
+        if len(bases) == 1 and grads[0]._base is not None and grads[0]._base.is_contiguous():
+            dist.all_reduce(grads[0]._base, group=self.comm.group)      # the gradients are views of one flat buffer
+            return
         flat = torch._utils._flatten_dense_tensors(grads)
         dist.all_reduce(flat, group=self.comm.group)
         torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
