@@ -243,7 +243,7 @@ SideStream* side_stream() {
 extern "C" {
 
 const char* fegnn_last_error(void) { return g_err; }
-int fegnn_version(void) { return 100; }
+int fegnn_version(void) { return 101; }      // 101: fegnn_layer_saved.wimg, fegnn_node_h_weight_images, FEGNN_F_WIMG_READY
 unsigned long long fegnn_launch_count(void) { return g_launches; }
 int fegnn_set_mode(const char* phase, int mode) {
   if (phase == nullptr) return fail(FEGNN_EINVAL, "phase is null");

@@ -138,7 +138,7 @@ typedef struct fegnn_layer_saved {   /* the accumulators msum, tsum, zh1, Dsum, 
 } fegnn_layer_saved;
 
 const char* fegnn_last_error(void);
-int fegnn_version(void);
+int fegnn_version(void);   /* 101 (100: before fegnn_layer_saved.wimg / fegnn_node_h_weight_images / FEGNN_F_WIMG_READY) */
 /* kernels launched by this library so far in this process (host-side counter; bench.py reports it) */
 unsigned long long fegnn_launch_count(void);
 /* Arithmetic mode of a phase.  "edge_forward": 0 = fp32 FMA kernel, 1 = tcgen05 single-pass TF32 tiles (default),
