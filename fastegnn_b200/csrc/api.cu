@@ -509,6 +509,7 @@ int fegnn_node_h_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn
       if (k == 0) {
         q.Y = sv->msum; q.ldy = kH; q.yscale = a.dinv; q.W = p->node_w0 + kH; q.wks = 1;
         q.D = gm; q.ldd = kH; q.dscale = a.dinv; q.gW = gr->node_w0 ? gr->node_w0 + kH : nullptr;
+        q.dmax = sv->scratch != nullptr ? reinterpret_cast<unsigned*>(sv->scratch) + 1 : nullptr;   // max|gm| (FEGNN_F_STATS_READY)
       } else {
         const int c = k - 1;
         q.Y = sv->u + (size_t)c * kH; q.ldy = d->C * kH; q.W = p->node_w0 + 2 * kH + c; q.wks = d->C;
@@ -544,6 +545,7 @@ int fegnn_virtual_backward(const fegnn_dims* d, const fegnn_graph* g, const fegn
   if (g_virt_bwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION) && gu != nullptr) {
     a.gu_work = const_cast<float*>(gu);
     a.u = sv->u;                                       // the heads are recomputed from the saved u
+    a.stats = reinterpret_cast<unsigned*>(sv->scratch);   // max|gt|, max|x - x_0| for the edge backward (FEGNN_F_STATS_READY)
     CK(launch_virtual_bwd_tc<4>(a, sm_count(), S(stream)));
   } else {
     CK(launch_virtual_bwd(a, sm_count(), S(stream)));
@@ -567,8 +569,9 @@ int fegnn_edge_backward(const fegnn_dims* d, const fegnn_graph* g, const fegnn_l
   int mode = g_edge_bwd_mode;
   if (mode == 6) mode = (tc_ok && sv->scratch != nullptr) ? 7 : 4;      // auto: the packed-fp16 kernel wherever it applies
   if ((mode == 7 || mode == 8) && (!tc_ok || sv->scratch == nullptr)) mode = 4;
-  if (mode == 7) CK(launch_edge_bwd_tc4<2>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
-  else if (mode == 8) CK(launch_edge_bwd_tc4<4>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
+  const bool pre = !(d->flags & FEGNN_F_STATS_READY);      // the bound pre-pass (its statistics came with the layer's other phases)
+  if (mode == 7) CK(launch_edge_bwd_tc4<2>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero && pre, pre));
+  else if (mode == 8) CK(launch_edge_bwd_tc4<4>(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero && pre, pre));
   else if (mode == 5 && tc_ok && sv->scratch != nullptr)
     CK(launch_edge_bwd_tc3(a, reinterpret_cast<unsigned*>(sv->scratch), sm_count(), S(stream), zero));
   else if (mode == 2 && tc_ok) CK(launch_edge_bwd_tc2<2>(a, sm_count(), S(stream)));
@@ -1060,6 +1063,12 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     fegnn_layer_grads* gr = &grads[l];
     const fegnn_layer_saved* sv = &w.saved[l];
     const int ls = rf ? 0 : l;
+    // the edge backward's bound statistics come out of this layer's virtual backward (max|gt|, max|x - x_0|) and node_h
+    // backward (max|gm|; the last layer has no gm) when those run on their tensor-core kernels: no pre-pass kernel on the chain
+    static const bool stats_fused = getenv("FEGNN_STATS_FUSED") == nullptr || atoi(getenv("FEGNN_STATS_FUSED")) != 0;   // experiment switch
+    if (stats_fused && !rf && g_virt_bwd_mode == 1 && !(d->flags & FEGNN_F_ATTENTION) && sv->scratch != nullptr &&
+        (last || (node_bwd_tc(d->N) && dense_bwd_uses_rows(d->N, sm_count()))))
+      dl.flags |= FEGNN_F_STATS_READY;
     // FastRF: S is one tensor read by every layer, so dL/dS of the layers above passes through (gS = gS_new)
     TRY(fegnn_graph_post_backward(&dl, g, p, gr, w.Sx[ls], sv, gZ_new, gS_new, s.gZ[cur], s.gS[cur], s.gDsum, s.gUsum,
                                   side));                                                   // side, under node_h_bwd

@@ -50,6 +50,7 @@ struct Blk {
   float* D;
   const float* dz;
   const float* dscale;
+  unsigned* dmax; // per-tile kernel: atomicMax of the bit patterns of |D| (bound statistic of a consumer), or nullptr
   float* gW;     // += X^T Y   (same ldw / wks addressing)
   float* gb;     // += column sums of X (or nullptr)
   // head block (phi_v / phi_g): X = gs[row] * hw2 * silu'(Y W^T + hb) ; g_hw2 += sum gs silu(z) ; g_hb2 += sum gs
@@ -424,6 +425,8 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
   const uint32_t id_ts_k = idesc_tf32(128, 64, 0, 0), id_ts_mn = idesc_tf32(128, 64, 0, 1), id_wg = idesc_tf32(64, 64, 1, 1);
   const uint64_t dWk = umma::make_desc(umma::smem_u32(Wk));
   uint32_t ph_r = 0, ph_d = 0, ph_w[2] = {0, 0};
+  float dmx = 0.f;                 // running max |D| of the block that carries a dmax pointer
+  unsigned* dmx_ptr = nullptr;
 
   // rows r0 .. r0 + 127 of a [N][64] operand (row stride ld) -> an MN-major tile, 16-byte chunks in (row, chunk) order
   auto fetch_tile = [&](uint8_t* dst, const float* src, int ld, int r0) {
@@ -646,6 +649,10 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
           }
           const float sc = blk.dscale != nullptr ? blk.dscale[r] : 1.f;
           float4* dst = reinterpret_cast<float4*>(blk.D + (size_t)r * blk.ldd + c0);
+          if (blk.dmax != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) dmx = fmaxf(dmx, fabsf(d[j] * sc));
+          }
 #pragma unroll
           for (int ch = 0; ch < CPT / 4; ++ch) {
             const float4 q = make_float4(d[ch * 4] * sc, d[ch * 4 + 1] * sc, d[ch * 4 + 2] * sc, d[ch * 4 + 3] * sc);
@@ -654,6 +661,7 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
           }
         }
       }
+      if (blk.dmax != nullptr) dmx_ptr = blk.dmax;
       TR(tb_ + 8);
       if (more) store_w(a.blk[b + 1], s_ ^ 1);     // Wm[s_ ^ 1]: last read by the data gradient of block b - 1 (waited)
       umma::fence_before();
@@ -680,6 +688,11 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
     }
     TR(46);
   }
+  if (dmx_ptr != nullptr) {                       // uniform over the CTA (the block list is)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmx = fmaxf(dmx, __shfl_xor_sync(0xffffffffu, dmx, o));
+    if (lane == 0) atomicMax(dmx_ptr, __float_as_uint(dmx));
+  }
   umma::fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
@@ -695,6 +708,17 @@ __global__ void __launch_bounds__(256, 1) dense_bwd_tc_rows_kernel(const __grid_
 #undef TR
 
 }  // namespace dtc
+
+static inline int dense_rows_max_tiles_per_sm() {
+  static const int v = getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM") ? atoi(getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM"))
+                                                                    : dtc::kRowsMaxTilesPerSm;      // experiment switch
+  return v;
+}
+// true when launch_dense_bwd_tc takes the per-tile kernel (the one that honours Blk::dmax)
+inline bool dense_bwd_uses_rows(int N, int sms) {
+  const int ntiles = (N + kTM - 1) / kTM;
+  return (long long)ntiles <= (long long)dense_rows_max_tiles_per_sm() * sms;
+}
 
 cudaError_t launch_dense_bwd_tc(const dtc::Args& a_in, int sms, cudaStream_t st) {
   dtc::Args a = a_in;
@@ -715,9 +739,7 @@ cudaError_t launch_dense_bwd_tc(const dtc::Args& a_in, int sms, cudaStream_t st)
   }
   const int ntiles = (a.N + kTM - 1) / kTM;
   if (ntiles == 0 || a.nblk == 0) return cudaSuccess;
-  static const int rows_max = getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM") ? atoi(getenv("FEGNN_DENSE_ROWS_MAX_TILES_PER_SM"))
-                                                                         : dtc::kRowsMaxTilesPerSm;      // experiment switch
-  if ((long long)ntiles <= (long long)rows_max * sms) {   // small graphs: one CTA per node tile walks the blocks
+  if (dense_bwd_uses_rows(a.N, sms)) {   // small graphs: one CTA per node tile walks the blocks
     static DevOnce attr2;
     if (!attr2.get()) {
       cudaError_t e = cudaFuncSetAttribute(dtc::dense_bwd_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -742,7 +742,8 @@ __global__ void __launch_bounds__(256 * CG, 1) edge_bwd_tc4_kernel(EdgeArgs a, c
 
 // stats: 4 unsigned of caller scratch (device)
 template <int CG>
-inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st, bool zero_stats = true) {
+inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int sms, cudaStream_t st, bool zero_stats = true,
+                                       bool run_stats = true) {
   static DevOnce attr;
   const size_t bytes = bwd4::Smem4<CG>::bytes;
   if (!attr.get()) {
@@ -761,8 +762,10 @@ inline cudaError_t launch_edge_bwd_tc4(const EdgeArgs& a, unsigned* stats, int s
   // at most one block per SM: the final atomicMax is one same-address atomic per block and statistic (they serialise in L2)
   int sblocks = (int)(((size_t)a.N * kH + 256 * 4 - 1) / (256 * 4));
   sblocks = sblocks < 1 ? 1 : (sblocks > sms ? sms : sblocks);
-  e = launch_pdl(bwd3::edge_bwd_stats_kernel, sblocks, 256, 0, st, a.N, a.Nl, a.x, a.gt, a.gm, stats);
-  if (e != cudaSuccess) return e;
+  if (run_stats) {
+    e = launch_pdl(bwd3::edge_bwd_stats_kernel, sblocks, 256, 0, st, a.N, a.Nl, a.x, a.gt, a.gm, stats);
+    if (e != cudaSuccess) return e;
+  }
   e = launch_pdl(bwd4::edge_bwd_tc4_kernel<CG>, grid, 256 * CG, bytes, st, a, (const unsigned*)stats);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();

@@ -22,6 +22,7 @@ struct VirtArgs {
   // backward inputs
   const float *gx_new, *gxsum_next, *gDsum, *gUsum, *gu;
   float* gu_work;              // tensor-core backward: [N,C,H] scratch (total dL/du between its two kernels)
+  unsigned* stats;             // tensor-core backward: bound statistics of the edge backward (max|gt| in [0], max|x - x_0| in [2]) or nullptr
   // backward outputs
   float *gAv, *gG1, *gx, *gZ, *gsv, *gsg, *gt;
   float *g_wv1, *g_V2, *g_c2, *g_Wxv, *g_bxv, *g_wxv, *g_WX, *g_bX, *g_wX, *g_wav, *g_bav;

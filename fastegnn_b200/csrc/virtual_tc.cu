@@ -604,6 +604,7 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
   bool first_tile = true;
   int cur_b = -1;
   float pwx[CPT], pwX[CPT];        // per-row partial sums of dwxv / dwX over this thread's tiles
+  float st_gt = 0.f, st_x = 0.f;   // bound statistics of the edge backward over this thread's nodes: max|gt|, max|x - x_0|
 #pragma unroll
   for (int j = 0; j < CPT; ++j) { pwx[j] = 0.f; pwX[j] = 0.f; }
 
@@ -774,6 +775,10 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
           for (int c = 0; c < C; ++c) sum += v->g.sgD[(t * C + c) * 3 + k];
           a.gx[(size_t)i * 3 + k] = g - sum;          // the trunk kernel subtracts the rho term
           a.gt[(size_t)i * 3 + k] = g * di;
+          if (a.stats != nullptr) {
+            st_gt = fmaxf(st_gt, fabsf(g * di));
+            st_x = fmaxf(st_x, fabsf(a.x[(size_t)i * 3 + k] - a.x[k]));
+          }
           gsv = fmaf(g, a.v[(size_t)i * 3 + k], gsv);
           gsg = fmaf(g, a.grav[k], gsg);
         }
@@ -817,6 +822,18 @@ __global__ void __launch_bounds__(128 * CG, 1) virtual_bwd_heads_tc_kernel(VirtA
     first_tile = false;
   }
   acc_flush<NT>(&v->acc, cur_b, C, nullptr, a.gZ, nullptr);
+  // ---- bound statistics of the edge backward (what its pre-pass kernel would compute from gt and x): one atomic pair per CTA
+  if (a.stats != nullptr && warp < 4) {            // the threads t < TN <= 128 that wrote gt
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      st_gt = fmaxf(st_gt, __shfl_xor_sync(0xffffffffu, st_gt, o));
+      st_x = fmaxf(st_x, __shfl_xor_sync(0xffffffffu, st_x, o));
+    }
+    if (lane == 0) {                               // non-negative floats order like their bit patterns
+      atomicMax(a.stats + 0, __float_as_uint(st_gt));
+      atomicMax(a.stats + 2, __float_as_uint(st_x));
+    }
+  }
   // ---- flush the weight gradients
   if (!first_tile) umma::mbar_wait(&v->bar[2], phase ^ 1);
     VTR();

@@ -63,6 +63,9 @@ extern "C" {
                                  and issue the fills once per step, off the kernel chain.                                         */
 #define FEGNN_F_WIMG_READY 512u /* fegnn_node_h_forward: the weight-block images in saved.wimg are current (written by
                                   fegnn_node_h_weight_images for this layer's parameters): skip the in-call pre-pass */
+#define FEGNN_F_STATS_READY 1024u /* fegnn_edge_backward (tensor-core modes 7 / 8): saved.scratch[0..2] already hold the bound
+                                    statistics (max|gt|, max|gm|, max|x - x_0|) -- written by fegnn_virtual_backward and
+                                    fegnn_node_h_backward of the same layer on their tensor-core kernels: skip the pre-pass */
 
 typedef struct fegnn_dims {
   int32_t N;        /* owned real nodes                                             */
