@@ -841,6 +841,16 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
   for (int l = 0; l < L; ++l)
     CK(cudaMemsetAsync(w.saved[l].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
   const bool rf = d->flags & FEGNN_F_RF;          // FastRF: h and S pass through every layer (models/FastRF.py:186)
+  // phi_h on the tensor cores: the operand-tile images of every layer's weight blocks in ONE launch here -- weights only, so it
+  // runs ahead of the chain and (graph_pending) under the CSR sort
+  bool wimg_ready = false;
+  if (g_node_fwd_mode != 0 && !rf && L > 1) {
+    const float *w0[32], *w2[32];
+    float* img[32];
+    for (int l = 0; l + 1 < L; ++l) { w0[l] = layers[l].node_w0; w2[l] = layers[l].node_w2; img[l] = w.saved[l].wimg; }
+    CK(launch_node_h_wprep(d->C, ldn(d), L - 1, w0, w2, img, st));
+    wimg_ready = true;
+  }
   const bool graph_pending = g->ready_event != nullptr;
   if (graph_pending) {
     // the CSR sort is still running on another stream: everything above and the first layer's node phase read no graph
@@ -852,15 +862,6 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
     CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));
   }
   CK(launch_graph_xsum(d->N, w.x[0], g->batch, w.xsum[0], st));
-  // phi_h on the tensor cores: the operand-tile images of every layer's weight blocks in ONE launch here, ahead of the chain
-  bool wimg_ready = false;
-  if (g_node_fwd_mode != 0 && !rf && L > 1) {
-    const float *w0[32], *w2[32];
-    float* img[32];
-    for (int l = 0; l + 1 < L; ++l) { w0[l] = layers[l].node_w0; w2[l] = layers[l].node_w2; img[l] = w.saved[l].wimg; }
-    CK(launch_node_h_wprep(d->C, ldn(d), L - 1, w0, w2, img, st));
-    wimg_ready = true;
-  }
   SideStream* sd = side_stream();
   RQ(sd != nullptr);
   void* side = sd->st;
@@ -1090,17 +1091,20 @@ int fegnn_model_backward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegn
     gx_new = s.gx[cur]; gZ_new = s.gZ[cur]; gS_new = s.gS[cur]; gxsum_next = s.gxsum[cur];
     cur ^= 1;
   }
-  JOIN(sd, st);
+  // tail: the input-coordinate gradient, dL/d loc_mean and dL/d virtual_node_feat (short kernels on the per-graph results) run
+  // on the side stream next to the embedding backward instead of in front of and behind it
+  FORK(sd, st);                                   // gx of layer 0 is complete on the main stream (edge, virtual backward)
   if (N > 0) {
-    final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, st>>>(d->N, gx_new, gxsum_next, g->batch, g_x0); ++g_launches;
+    final_gx_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, S(side)>>>(d->N, gx_new, gxsum_next, g->batch, g_x0); ++g_launches;
     CK(cudaGetLastError());
   }
-  CK(cudaMemcpyAsync(g_loc_mean, gZ_new, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, st));
-  TRY(fegnn_embed_backward(d->N, Fin, node_feat, embed_w, s.gh, g_embed_w, g_embed_b, g_node_feat, stream));
+  CK(cudaMemcpyAsync(g_loc_mean, gZ_new, sizeof(float) * 3 * C * B, cudaMemcpyDeviceToDevice, S(side)));
   if (B > 0) {
-    reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, st>>>(d->B, d->C, gS_new, g_vnf); ++g_launches;
+    reduce_gS_kernel<<<(unsigned)((C * kH + 255) / 256), 256, 0, S(side)>>>(d->B, d->C, gS_new, g_vnf); ++g_launches;
     CK(cudaGetLastError());
   }
+  TRY(fegnn_embed_backward(d->N, Fin, node_feat, embed_w, s.gh, g_embed_w, g_embed_b, g_node_feat, stream));
+  JOIN(sd, st);
   return 0;
 }
 
