@@ -296,7 +296,7 @@ class StepBench:
     def __init__(self, data, hp, dev, world=1, rank=0, model_name="fastegnn", graph=None, runner_factory=None,
                  use_cuda_graph=True, n_global=None, idx_all=None, mmd_scales=(1.0, 1.0), seed=0):
         import torch.distributed as dist
-        from fastegnn_b200 import FastEGNN, FusedAdam, _lib, mmd_loss
+        from fastegnn_b200 import FastEGNN, FusedAdam, _lib, mmd_loss, mse_mmd_loss
         self._lib, self.dev, self.world, self.hp = _lib, dev, world, hp
         C = data["C"]
         torch.manual_seed(seed)
@@ -352,7 +352,8 @@ class StepBench:
                 x, Z = model(node_feat=t["node_feat"], node_loc=t["loc_0"], node_vel=t["vel_0"],
                              edge_index=graph if prebuilt else t["edge_index"], data_batch=t["batch"],
                              loc_mean=t["loc_mean"], edge_attr=None if prebuilt else t["edge_attr"])
-                loss = torch.nn.functional.mse_loss(x, t["loc_t"]) + hp["weight"] * mmd_loss(x, Z, idx, hp["sigma"])
+                # utils/train.py:104-163: MSE + weight * MMD -- one launch per direction (mse_mmd_loss), not ten torch kernels
+                loss, _mse = mse_mmd_loss(x, t["loc_t"], Z, idx, hp["sigma"], hp["weight"])
                 loss.backward()
                 if world > 1:
                     allreduce_grads()

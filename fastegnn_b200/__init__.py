@@ -5,6 +5,7 @@ Public surface (mirrors models/FastEGNN.py of GLAD-RUC/FastEGNN):
     FastRF                         the radial-field sibling (models/FastRF.py) on the same kernels
     VNEGNN                         the virtual-node EGNN sibling (models/VNEGNN.py): A2A / A2V / V2A stages on the same kernels
     mmd_loss                       the MMD regulariser of utils/train.py:111-165 as one op
+    mse_mmd_loss                   the step's whole loss (MSE + weight * MMD, utils/train.py:104-163) as one op
     CsrGraph                       the once-per-batch CSR graph prep; CsrGraph.from_radius builds the graph on the device
     FusedAdam                      torch.optim.Adam's step (utils/train.py:168-170) as one launch over flat buffers
     PipelinedStep                  a training step as a CUDA graph with double-buffered inputs (H2D of batch k+1 under step k)
@@ -14,8 +15,8 @@ from . import _lib  # noqa: F401  (fails loudly when the shared library has not 
 from .FastEGNN import E_GCL_vel, FastEGNN, unsorted_segment_mean, unsorted_segment_sum  # noqa: F401
 from .FastRF import FastRF  # noqa: F401
 from .VNEGNN import VNEGNN  # noqa: F401
-from .ops import CsrGraph, mmd_loss  # noqa: F401
+from .ops import CsrGraph, mmd_loss, mse_mmd_loss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .runtime import PipelinedStep  # noqa: F401
 
-__all__ = ["FastEGNN", "FastRF", "VNEGNN", "E_GCL_vel", "mmd_loss", "CsrGraph", "FusedAdam", "PipelinedStep", "unsorted_segment_sum", "unsorted_segment_mean"]
+__all__ = ["FastEGNN", "FastRF", "VNEGNN", "E_GCL_vel", "mmd_loss", "mse_mmd_loss", "CsrGraph", "FusedAdam", "PipelinedStep", "unsorted_segment_sum", "unsorted_segment_mean"]

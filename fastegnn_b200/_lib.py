@@ -148,6 +148,8 @@ SIGNATURES = {
     "fegnn_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float, vp]),
     "fegnn_mmd_forward": (C.c_int, [i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
     "fegnn_mmd_backward": (C.c_int, [i32, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+    "fegnn_mse_mmd_forward": (C.c_int, [i32, i32, i32, i32] + [C.c_float] * 5 + [vp] * 7),
+    "fegnn_mse_mmd_backward": (C.c_int, [i32, i32, i32, i32] + [C.c_float] * 5 + [vp] * 9),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1159,4 +1159,24 @@ int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma,
   return 0;
 }
 
+int fegnn_mse_mmd_forward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float weight, float scale_vv,
+                          float scale_rv, float inv_count, const float* x, const float* target, const float* Z,
+                          const int32_t* sample_idx, float* out_total, float* out_mse, void* stream) {
+  RQ(N >= 0 && B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 0 && sigma > 0.f && out_total && out_mse && (B == 0 || Z));
+  RQ((N == 0 || (x && target)) && (B == 0 || ns == 0 || (x && sample_idx)));
+  CK(launch_mse_mmd_fwd(N, B, C, ns, sigma, weight, scale_vv, scale_rv, inv_count, x, target, Z, sample_idx, out_total,
+                        out_mse, S(stream)));
+  return 0;
+}
+int fegnn_mse_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float weight, float scale_vv,
+                           float scale_rv, float inv_count, const float* x, const float* target, const float* Z,
+                           const int32_t* sample_idx, const float* g_total, const float* g_mse, float* gx, float* gZ,
+                           void* stream) {
+  RQ(N >= 0 && B >= 0 && C >= 1 && C <= FEGNN_MAX_C && ns >= 0 && sigma > 0.f && gx && (B == 0 || (Z && gZ)));
+  RQ((N == 0 || (x && target)) && (B == 0 || ns == 0 || (x && sample_idx)));
+  CK(launch_mse_mmd_bwd(N, B, C, ns, sigma, weight, scale_vv, scale_rv, inv_count, x, target, Z, sample_idx, g_total, g_mse,
+                        gx, gZ, S(stream)));
+  return 0;
+}
+
 }  // extern "C"

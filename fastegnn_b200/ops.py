@@ -264,6 +264,55 @@ def mmd_loss(node_loc: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx:
     return _MmdFn.apply(node_loc, virtual_node_loc, sample_idx.contiguous(), sigma, scale_vv, scale_rv)
 
 
+class _MseMmdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, Z, sample_idx, sigma, weight, scale_vv, scale_rv, inv_count):
+        _require_cuda(x, "node_loc")
+        x, target, Z = x.contiguous(), target.contiguous().float(), Z.contiguous()
+        B, _, C_ = Z.shape
+        total = torch.empty((), device=x.device, dtype=torch.float32)
+        mse = torch.empty((), device=x.device, dtype=torch.float32)
+        with _on(x.device):
+            L.check(lib.fegnn_mse_mmd_forward(x.size(0), B, C_, sample_idx.size(1), float(sigma), float(weight),
+                                              float(scale_vv), float(scale_rv), float(inv_count), L.ptr(x), L.ptr(target),
+                                              L.ptr(Z), L.ptr(sample_idx), L.ptr(total), L.ptr(mse), _stream(x.device)),
+                    "fegnn_mse_mmd_forward")
+        ctx.save_for_backward(x, target, Z, sample_idx)
+        ctx.cfg = (float(sigma), float(weight), float(scale_vv), float(scale_rv), float(inv_count))
+        ctx.set_materialize_grads(False)         # an unused output arrives as None in backward, not as a zero-fill kernel
+        return total, mse
+
+    @staticmethod
+    def backward(ctx, g_total, g_mse):
+        x, target, Z, idx = ctx.saved_tensors
+        B, _, C_ = Z.shape
+        sigma, weight, svv, srv, inv_count = ctx.cfg
+        gx = torch.empty_like(x)
+        gZ = torch.empty_like(Z)
+        gt = None if g_total is None else g_total.reshape(1).contiguous().float()
+        gm = None if g_mse is None else g_mse.reshape(1).contiguous().float()
+        with _on(x.device):
+            L.check(lib.fegnn_mse_mmd_backward(x.size(0), B, C_, idx.size(1), sigma, weight, svv, srv, inv_count, L.ptr(x),
+                                               L.ptr(target), L.ptr(Z), L.ptr(idx), L.ptr(gt), L.ptr(gm), L.ptr(gx), L.ptr(gZ),
+                                               _stream(x.device)), "fegnn_mse_mmd_backward")
+        return gx, None, gZ, None, None, None, None, None, None
+
+
+def mse_mmd_loss(node_loc: torch.Tensor, target: torch.Tensor, virtual_node_loc: torch.Tensor, sample_idx: torch.Tensor,
+                 sigma: float, weight: float, scale_vv: float = 1.0, scale_rv: float = 1.0, inv_count: float = None):
+    """The training step's loss of utils/train.py:104-163 in one launch per direction:
+    `total = mse_loss(node_loc, target) + weight * mmd_loss(node_loc, virtual_node_loc, sample_idx, sigma)`.
+    Returns (total, mse): `total` is what the loop back-propagates (:166), `mse` what it logs (:107).  No gradient flows to
+    `target`.  inv_count defaults to 1 / node_loc.numel() (torch's mean reduction)."""
+    if sample_idx.dtype != torch.int32:
+        sample_idx = sample_idx.to(torch.int32)
+    if inv_count is None:
+        inv_count = 1.0 / max(1, node_loc.numel())
+    total, mse = _MseMmdFn.apply(node_loc, target, virtual_node_loc, sample_idx.contiguous(), sigma, weight, scale_vv,
+                                 scale_rv, inv_count)
+    return total, mse
+
+
 # ----------------------------------------------------------------------------- unsorted_segment_sum / _mean
 class _SegmentFn(torch.autograd.Function):
     @staticmethod

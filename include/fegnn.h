@@ -375,6 +375,19 @@ int fegnn_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma,
                        const float* x, const float* Z, const int32_t* sample_idx, const float* gloss /*[1]*/,
                        float* gx /*[N,3] zeroed here*/, float* gZ /*[B,3,C] =*/, void* stream);
 
+/* The step's loss (utils/train.py:104,163): total = MSE + weight * MMD in one kernel per direction.
+ *   MSE = inv_count * sum (x - target)^2  (inv_count = 1 / (3 N) is torch's mean; a partitioned caller passes 1 / (3 N_global)),
+ *   MMD as above.  out_total[0], out_mse[0] (the MSE term alone, what the reference logs at :107) are zeroed here.
+ * Backward: g_total / g_mse = dL/d(total), dL/d(mse) (device scalars, either may be NULL);
+ *   gx [N,3] (zeroed here) = (g_total + g_mse) * 2 inv_count (x - target) + g_total * weight * dMMD/dx ; gZ [B,3,C] =. */
+int fegnn_mse_mmd_forward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float weight, float scale_vv,
+                          float scale_rv, float inv_count, const float* x, const float* target, const float* Z,
+                          const int32_t* sample_idx, float* out_total, float* out_mse, void* stream);
+int fegnn_mse_mmd_backward(int32_t N, int32_t B, int32_t C, int32_t ns, float sigma, float weight, float scale_vv,
+                           float scale_rv, float inv_count, const float* x, const float* target, const float* Z,
+                           const int32_t* sample_idx, const float* g_total, const float* g_mse, float* gx, float* gZ,
+                           void* stream);
+
 /* ------------------------------------------------------------------ roofline probes (measurement only)
  * One launch of a micro-benchmark for the pipe a kernel of the path is bound by: kind 0 = tcgen05.mma kind::tf32
  * (cta_group::1, M128 N256 K8, shared-memory operands), 1 = tcgen05.mma kind::f16 (K16), 2 = fp32 FMA, 3 = MUFU

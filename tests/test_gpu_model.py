@@ -551,3 +551,39 @@ def test_pipelined_step_reads_the_loss_through_the_graph():
     exp = [want[0], want[1], want[0], want[1]]
     for g_, w_ in zip(got, exp):
         assert abs(g_ - w_) <= 1e-5 * abs(w_), (got, exp)
+
+
+def test_mse_mmd_loss_matches_the_torch_composition():
+    """fastegnn_b200.mse_mmd_loss (the step's loss of utils/train.py:104-163 in one launch per direction) against
+    mse_loss + weight * mmd_loss, values and gradients, with gradients flowing into both returned terms."""
+    from fastegnn_b200 import mmd_loss, mse_mmd_loss
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    sizes = [37, 64, 21]
+    N, B, Cc, ns = sum(sizes), len(sizes), 3, 9
+    x = torch.randn(N, 3, generator=gen).to(dev).requires_grad_(True)
+    tgt = torch.randn(N, 3, generator=gen).to(dev)
+    Z = torch.randn(B, 3, Cc, generator=gen).to(dev).requires_grad_(True)
+    offs = np.concatenate([[0], np.cumsum(sizes)])[:-1]
+    idx = torch.stack([torch.randperm(n, generator=gen)[:ns] + int(o) for n, o in zip(sizes, offs)]).to(torch.int32).to(dev)
+    sigma, weight = 1.5, 0.01
+    ref_mse = torch.nn.functional.mse_loss(x, tgt)
+    ref_tot = ref_mse + weight * mmd_loss(x, Z, idx, sigma)
+    (ref_tot + 0.25 * ref_mse).backward()
+    gx_ref, gZ_ref = x.grad.clone(), Z.grad.clone()
+    x.grad = None
+    Z.grad = None
+    tot, mse = mse_mmd_loss(x, tgt, Z, idx, sigma, weight)
+    (tot + 0.25 * mse).backward()
+    assert abs(float(tot) - float(ref_tot)) <= 2e-6 * abs(float(ref_tot))
+    assert abs(float(mse) - float(ref_mse)) <= 2e-6 * abs(float(ref_mse))
+    assert rel_err(x.grad.cpu(), gx_ref.cpu()) < 2e-6 and rel_err(Z.grad.cpu(), gZ_ref.cpu()) < 2e-6
+    # the usual call: only the total is back-propagated
+    x.grad = None
+    Z.grad = None
+    mse_mmd_loss(x, tgt, Z, idx, sigma, weight)[0].backward()
+    g2 = x.grad.clone()
+    x.grad = None
+    Z.grad = None
+    (torch.nn.functional.mse_loss(x, tgt) + weight * mmd_loss(x, Z, idx, sigma)).backward()
+    assert rel_err(g2.cpu(), x.grad.cpu()) < 2e-6
