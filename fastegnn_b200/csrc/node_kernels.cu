@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(int N, int Fin, int
 #pragma unroll
   for (int f = 0; f < 16; ++f) aw[f] = 0.f;
   float ab = 0.f;
-#pragma unroll 4
+#pragma unroll 16                                // a chunk of 64 nodes = 16 rows per thread: every load in flight at once
   for (int i = i0 + grp; i < i1; i += 4) {
     float g = gh[(size_t)i * kH + n];
     ab += g;
