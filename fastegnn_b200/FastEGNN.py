@@ -161,7 +161,7 @@ class _StackFn(torch.autograd.Function):
 
 def _stack_inference(mod: "FastEGNN", graph: CsrGraph, node_feat, x0, v, loc_mean):
     """FastEGNN.forward without autograd: fegnn_model_forward_inference (two ping-pong states + one shared block of
-    per-layer intermediates -- two alternating blocks up to 65 536 nodes; nothing is kept for a backward)."""
+    per-layer intermediates -- a ring of four blocks up to 65 536 nodes; nothing is kept for a backward)."""
     dev = x0.device
     N, B, Cc, Lyr = graph.N, graph.B, mod.virtual_channels, mod.n_layers
     dims = make_dims(N, N, graph.E, B, Cc, graph.Fe, mod._flag_word, mod._gravity)

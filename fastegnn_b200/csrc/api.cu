@@ -895,13 +895,15 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
 // utils/train.py:24-27,191-192: validation and test run the model with backprop=False.  Nothing is kept for a backward:
 // the layers ping-pong between two state sets and share ONE block of per-layer intermediates, so the workspace is
 // 2 states + 1 block instead of (L + 1) states + L blocks (3.4 GB instead of 13.4 GB at 1 M nodes, C = 8, L = 4).
-// Small graphs get TWO blocks (layer l uses block l & 1): with one, the per-graph kernels of layer l + 1 (side stream) must not
-// start before layer l's node phase has read u / msum, and the next main-stream kernels not before graph_post(l) has read
-// Dsum / Usum -- a join + fork per layer that puts 12 us of one-CTA kernels on the chain (4 layers at Water-3D: 0.374 ms against
-// 0.327 for the training forward).  With two, the stack has the training forward's fork / join structure.  Large graphs keep
-// one block: there the serialisation is noise and the block is gigabytes.
-constexpr int kInferTwoBlocksMaxN = 65536;
-static inline size_t infer_blocks(const fegnn_dims* d) { return d->N <= kInferTwoBlocksMaxN ? 2 : 1; }
+// Small graphs get a RING of kInferBlocks blocks (layer l uses block l % kInferBlocks; a stack of up to that many layers has a
+// block per layer): with ONE block the per-graph kernels of layer l + 1 (side stream) must not start before layer l's node
+// phase has read u / msum, and the next main-stream kernels not before graph_post(l) has read Dsum / Usum -- a join + fork
+// per layer that puts 12 us of one-CTA kernels on the chain -- and every layer needs its accumulator fill and its phi_h
+// weight images inside the chain.  With the ring the stack has the training forward's structure: fills and weight images
+// ahead of the first kernel, one fork / join pair per layer.  Large graphs keep one block: there all of this is noise and the
+// block is gigabytes.
+constexpr int kInferRingMaxN = 65536, kInferBlocks = 4;      // 4 = n_layers of every reference main
+static inline size_t infer_blocks(const fegnn_dims* d) { return d->N <= kInferRingMaxN ? kInferBlocks : 1; }
 
 size_t fegnn_model_inference_workspace_floats(const fegnn_dims* d) {
   const size_t N = d->N, Nl = d->Nl, B = d->B, C = d->C;
@@ -928,11 +930,14 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
   for (int i = 0; i < 3; ++i) {
     h[i] = take(N * kH); x[i] = take(Nl * 3); Z[i] = take(B * 3 * C); Sx[i] = take(B * C * kH); xsum[i] = take(B * 3);
   }
-  const bool two = infer_blocks(d) == 2;
-  fegnn_layer_saved sv_[2];
-  fegnn_layer_saved_bind(d, p, &sv_[0]);
-  if (two) fegnn_layer_saved_bind(d, p + fegnn_layer_saved_floats(d), &sv_[1]);
-  else sv_[1] = sv_[0];
+  const int nb = (int)infer_blocks(d);            // ring of blocks (1: large graphs)
+  const bool two = nb > 1;
+  fegnn_layer_saved sv_[kInferBlocks];
+  for (int i = 0; i < kInferBlocks; ++i) {
+    if (i < nb) fegnn_layer_saved_bind(d, p + (size_t)i * fegnn_layer_saved_floats(d), &sv_[i]);
+    else sv_[i] = sv_[0];
+  }
+  const int ntop = nb < L ? nb : L;               // blocks filled (and layers whose weight images are written) ahead of the chain
   // slot 2 keeps the embedding state (h0, S0): FastRF reads it in every layer; slots 0 / 1 ping-pong
   TRY(fegnn_embed_forward(d->N, Fin, node_feat, embed_w, embed_b, h[2], stream));
   CK(cudaMemcpyAsync(x[2], x0, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, st));
@@ -942,15 +947,26 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
     CK(cudaGetLastError());
   }
   const bool rf = d->flags & FEGNN_F_RF;
+  for (int i = 0; i < ntop; ++i)
+    CK(cudaMemsetAsync(sv_[i].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
+  // phi_h weight images off the chain (ring): the first ntop layers' here in one launch, layer l + 1 >= ntop's on the side
+  // stream next to graph_post(l) (the image buffer of that block was last read by phi_h of layer l + 1 - nb, ahead of the fork)
+  const bool img_ahead = two && g_node_fwd_mode != 0 && !rf && L > 1;
+  auto weight_images = [&](int l0, int nl, cudaStream_t s_) -> cudaError_t {
+    const float *w0[32], *w2[32];
+    float* img[32];
+    for (int l = 0; l < nl; ++l) { w0[l] = layers[l0 + l].node_w0; w2[l] = layers[l0 + l].node_w2; img[l] = sv_[(l0 + l) % nb].wimg; }
+    return launch_node_h_wprep(d->C, ldn(d), nl, w0, w2, img, s_);
+  };
+  const int nimg_top = ntop < L - 1 ? ntop : L - 1;      // the last layer has no phi_h
+  if (img_ahead && nimg_top > 0) CK(weight_images(0, nimg_top, st));
   const bool graph_pending = g->ready_event != nullptr;
   if (graph_pending) {
-    // the CSR sort is still running on another stream: everything above, the first block's fill and the first layer's node
-    // phase read no graph array and run under it; this stream joins the sort here
+    // the CSR sort is still running on another stream: everything above and the first layer's node phase read no graph
+    // array and run under it; this stream joins the sort here
     fegnn_dims d0 = *d;
     d0.flags |= FEGNN_F_PREZEROED;
     if (rf || L == 1) d0.flags |= FEGNN_F_LAST;
-    CK(cudaMemsetAsync(sv_[0].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
-    if (two) CK(cudaMemsetAsync(sv_[1].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
     TRY(fegnn_node_pre_forward(&d0, &layers[0], h[2], &sv_[0], stream));
     CK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(g->ready_event), 0));
   }
@@ -959,15 +975,6 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
   RQ(sd != nullptr);
   void* side = sd->st;
   FORK(sd, st);
-  // phi_h weight images off the chain (two blocks): layer 0's here, layer l + 1's on the side stream next to graph_post(l)
-  // (the image buffer of block (l + 1) & 1 was last read by phi_h of layer l - 1, ahead of the fork)
-  const bool img_ahead = two && g_node_fwd_mode != 0 && !rf && L > 1;
-  auto weight_images = [&](int l, cudaStream_t s_) -> cudaError_t {
-    const float *w0 = layers[l].node_w0, *w2 = layers[l].node_w2;
-    float* img = sv_[l & 1].wimg;
-    return launch_node_h_wprep(d->C, ldn(d), 1, &w0, &w2, &img, s_);
-  };
-  if (img_ahead) CK(weight_images(0, st));
   int cur = 2;                                    // state entering the layer
   for (int l = 0; l < L; ++l) {
     fegnn_dims dl = *d;
@@ -978,13 +985,12 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
     const fegnn_layer_params* pl = &layers[l];
     const int nxt = cur == 2 ? 0 : (cur ^ 1);
     const int hs = rf ? 2 : cur;                  // layer whose (h, S) this layer reads
-    fegnn_layer_saved* sv = &sv_[l & 1];
-    // two blocks: blocks 0 / 1 are filled ahead of the chain, block l & 1 for layer l >= 2 on the side stream during layer
+    fegnn_layer_saved* sv = &sv_[l % nb];
+    // ring: the first ntop blocks are filled ahead of the chain, the block of a layer l >= nb on the side stream during layer
     // l - 1 (below) -- a memset node between two kernels of the chain would cut their programmatic overlap
     if (two) {
-      if (!graph_pending && l < 2) CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
-      if (l >= 2) CK(cudaStreamWaitEvent(st, sd->aux, 0));
-    } else if (!(graph_pending && l == 0)) {
+      if (l >= nb) CK(cudaStreamWaitEvent(st, sd->aux, 0));
+    } else if (l > 0) {
       CK(cudaMemsetAsync(sv->msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), st));
     }
     // ... and the per-graph coordinate sums of the state this layer produces on the side stream (last read by the per-graph
@@ -997,19 +1003,19 @@ int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, c
     JOIN(sd, st);
     TRY(fegnn_virtual_forward(&dl, g, pl, x[cur], v, Z[cur], sv, x[nxt], xsum[nxt], stream));
     FORK(sd, st);
-    if (two && l >= 1 && l + 1 < L) {
-      // the other block's accumulators for layer l + 1: last read by layer l - 1 (node phase on this stream ahead of the
-      // fork, per-graph kernels earlier on the side stream)
-      CK(cudaMemsetAsync(sv_[(l + 1) & 1].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), S(side)));
+    if (two && l + 1 >= nb && l + 1 < L) {
+      // the accumulators of the ring block that layer l + 1 reuses: last read by layer l + 1 - nb (node phase on this stream
+      // ahead of the fork, per-graph kernels earlier on the side stream)
+      CK(cudaMemsetAsync(sv_[(l + 1) % nb].msum, 0, sizeof(float) * fegnn_layer_saved_accum_floats(d), S(side)));
       CK(cudaEventRecord(sd->aux, S(side)));
     }
     if (!last) TRY(fegnn_node_h_forward(&dl, g, pl, h[cur], sv, h[nxt], stream));
     TRY(fegnn_graph_post_forward(&dl, g, pl, Z[cur], Sx[hs], sv, Z[nxt], Sx[nxt], side));
-    if (img_ahead && l + 2 < L) CK(weight_images(l + 1, S(side)));
+    if (img_ahead && l + 2 < L && l + 1 >= nimg_top) CK(weight_images(l + 1, 1, S(side)));
     // the shared block is rewritten by the next layer: its per-graph kernels (side) must not start before this layer's
     // node_h (main) has read u / msum, and its main-stream kernels not before this layer's graph_post (side) has read
-    // Dsum / Usum.  (Two blocks: block l & 1 is next written by layer l + 2, whose kernels are ordered behind both by the
-    // join in front of virtual_forward(l + 1).)
+    // Dsum / Usum.  (Ring: block l % nb is next written by layer l + nb, whose kernels are ordered behind both by the
+    // joins in front of the virtual_forward calls in between.)
     if (!two) {
       JOIN(sd, st);
       FORK(sd, st);

@@ -346,7 +346,8 @@ int fegnn_model_forward(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn
 /* Forward-only stack for evaluation / rollout (utils/train.py:24-27,191-192: backprop=False): same arguments and results
  * as fegnn_model_forward, but nothing is kept for a backward -- the layers ping-pong between two state sets and share ONE
  * block of per-layer intermediates (workspace = 3 states + 1 block instead of (L + 1) states + L blocks); up to 65 536 nodes
- * TWO blocks (layer l uses block l & 1), which removes a stream join + fork per layer from the kernel chain. */
+ * a ring of FOUR blocks (layer l uses block l % 4), which takes the per-layer join + fork, the accumulator fills and the
+ * phi_h weight images out of the kernel chain. */
 size_t fegnn_model_inference_workspace_floats(const fegnn_dims* d);
 int fegnn_model_forward_inference(const fegnn_dims* d, int32_t L, int32_t Fin, const fegnn_graph* g,
                                   const fegnn_layer_params* layers_host, const float* embed_w, const float* embed_b,
