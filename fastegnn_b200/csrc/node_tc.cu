@@ -255,8 +255,11 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
   auto At = [&](int s_) { return smem + SM::off_A + s_ * 2 * SM::kT; };
   auto Wt = [&](int w_) { return smem + SM::off_W + w_ * 2 * SM::kW; };
 
-  float4 areg[NA];
-  float sc[NA];
+  // TWO register sets of operand rows: the blocks of a tile alternate between them (block b of every tile in set b & 1), so
+  // the rows of blocks b + 1 and b + 2 are both in flight while block b is split and multiplied -- one 32 KB block in
+  // flight per SM was what bounded the kernel at 1 M nodes (2.2 TB/s of row traffic)
+  float4 areg0[NA], areg1[NA];
+  float sc0[NA], sc1[NA];
   // weight block b -> ring slot w_ (32 KB image, 8 x 16 bytes per thread), one cp.async group; b < 0: an empty group
   auto fetch_w = [&](int b, int w_) {
     if (b >= 0) {
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
       if (r < a.N) dst[j] = *reinterpret_cast<const float4*>(src + (size_t)r * ld + 4 * c16);
     }
   };
-  auto load_a = [&](int b, int i0) {
+  auto load_a = [&](int b, int i0, float4 (&areg)[NA], float (&sc)[NA]) {
     if (b == 0) {
       load_rows(areg, a.msum, kH, i0);
 #pragma unroll
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
     *reinterpret_cast<float4*>(tile + o) = hi;
     *reinterpret_cast<float4*>(tile + SM::kT + o) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
   };
-  auto store_a = [&](int s_) {
+  auto store_a = [&](int s_, const float4 (&areg)[NA], const float (&sc)[NA]) {
 #pragma unroll
     for (int j = 0; j < NA; ++j)
       store_split(At(s_), j, make_float4(areg[j].x * sc[j], areg[j].y * sc[j], areg[j].z * sc[j], areg[j].w * sc[j]));
@@ -350,28 +353,40 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
   int g = 0, wq = 0;                               // running block count: operand slot g & 1, weight slot wq = g % 3
   if ((int)blockIdx.x < ntiles) {
     fetch_w(0, 0);
-    load_a(0, blockIdx.x * kTM);
+    load_a(0, blockIdx.x * kTM, areg0, sc0);
+    load_a(1, blockIdx.x * kTM, areg1, sc1);       // nb1 = C + 1 >= 2
   }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int i0 = tile * kTM;
     const bool more = tile + (int)gridDim.x < ntiles;
     float4 uh[NA], hr[NA];
-    for (int b = 0; b < nb1; ++b, ++g) {
+    // block b of the tile out of register set `par` = b & 1 (a compile-time constant at both call sites below)
+    auto block_iter = [&](int b, int par, float4 (&areg)[NA], float (&sc)[NA]) {
       const int s_ = g & 1, wn = wq == 2 ? 0 : wq + 1;
       wait_slot(s_);                               // block g - 2 is done: operand slot s_ and weight slot (g + 1) % 3 are free
       VTR();
       fetch_w(b + 1, wn);                          // next block's weights (b + 1 == nb1: the output Linear) travel a full block ahead
-      store_a(s_);
+      store_a(s_, areg, sc);
       cp_async_wait_group<1>();                    // this block's weights have landed
       umma::fence_smem_to_async();
       umma::fence_before();
       __syncthreads();
       VTR();
-      if (b + 1 < nb1) load_a(b + 1, i0);          // next block's rows travel under this block's MMAs
-      else load_rows(uh, a.Uh, kH, i0);
+      // the freed register set takes the block two ahead: of this tile, else the block of the NEXT tile with this parity
+      if (b + 2 < nb1) load_a(b + 2, i0, areg, sc);
+      else if (more) load_a(par, (tile + gridDim.x) * kTM, areg, sc);
+      if (b == nb1 - 1) {                          // the rows the write-out phases add: Uh (zh1) and h (h')
+        load_rows(uh, a.Uh, kH, i0);
+        load_rows(hr, a.h, kH, i0);
+      }
       issue(tmem + kNH_ACC1, s_, wq, b > 0);
       pend_bits |= 1u << s_;
       wq = wn;
+      ++g;
+    };
+    for (int b = 0; b < nb1; b += 2) {
+      block_iter(b, 0, areg0, sc0);
+      if (b + 1 < nb1) block_iter(b + 1, 1, areg1, sc1);
     }
     // ---- output Linear = one more block whose operand is made on chip
     const int s2 = g & 1, so = s2 ^ 1, wn = wq == 2 ? 0 : wq + 1;
@@ -379,8 +394,6 @@ __global__ void __launch_bounds__(256, 1) node_h_fwd_tc_kernel(NodeHArgs a) {
     fetch_w(more ? 0 : -1, wn);                    // first block of the next tile
     VTR();
     wait_slot(so);                                 // zh1 - Uh is complete in tensor memory; both operand slots are free
-    load_rows(hr, a.h, kH, i0);
-    if (more) load_a(0, (tile + gridDim.x) * kTM);
     VTR();
     uint8_t* ST = At(so);                          // staging tile (row owners -> (row, chunk) order)
     {
